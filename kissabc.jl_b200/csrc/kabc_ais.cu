@@ -1,0 +1,590 @@
+// kabc_ais.cu -- sample(ApproxKernelizedPosterior(prior,cost,scale), AIS(N), Ns; ...) on device.
+// Restates, per transition, KissABC.jl 3.0.1:
+//   propose (mixture 4/7,2/7,1/7)   src/transition.jl:61-65
+//   stretch move, a = 3             src/transition.jl:46-59
+//   DE move                         src/transition.jl:2-22
+//   walk move                       src/transition.jl:24-43
+//   kernelized loglike              src/types.jl:51-58
+//   accept (-randexp <= lW)         src/types.jl:62-75
+//   init + retry budget             src/KissABC.jl:50-61
+//   step / walker rotation / record src/KissABC.jl:66-80, :82-94
+// Schedule: the reference moves one walker at a time (Gauss-Seidel).  The device moves a whole colour at
+// once: walkers [0,h) ("red") against [h,N) ("black") and conversely, h = N/2, partners drawn from the
+// complementary colour only, which keeps every simultaneous move a valid MH step (emcee's parallel
+// stretch).  A sweep = two half-steps = one transition of every walker.
+#include "kabc_host.hpp"
+#include "kabc_gk.cuh"
+
+namespace kabc {
+
+struct AisCtrl {
+    unsigned long long accepted, cost_evals, retries;
+    long long sweeps;
+    unsigned int work_count, epoch;
+    int err;
+};
+
+struct AisParams {
+    long long N;
+    int d;
+    double scale;
+    long long retry_cap; // per-walker attempt cap = budget + 1
+};
+
+struct AisTrace {
+    unsigned char *move, *dec;
+    long long *a, *b, *c;
+    double *corr, *lpp, *llp, *e;
+};
+
+struct AisBufs {
+    double *th, *lp, *ll;
+    double *thp, *lpp, *corr;
+    unsigned int *work;
+    AisCtrl *ctrl;
+    AisTrace tr;
+    int trace_on;
+};
+
+// ref src/types.jl:51-58 given the prior value and the cost
+__device__ __forceinline__ double kernel_ll(double cost, double scale) {
+    double q = xdiv(cost, scale);
+    return xmul(-0.5, xmul(q, q));
+}
+
+// ------------------------------------------------------------------ init with retry, ref src/KissABC.jl:50-61
+template <int KIND, int PREC>
+__global__ void __launch_bounds__(256)
+k_ais_init(AisBufs B, AisParams P, DPriors pri, DModel m, RoundKeys rk) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    const long long N = P.N;
+    double lp = 0, ll = 0;
+    long long t = 0, evals = 0;
+    bool ok = true;
+    for (;; ++t) {
+        Stream st(rk, ST_PRIOR, (uint32_t)i, (uint32_t)t);
+        for (int k = 0; k < P.d; ++k) {
+            double x;
+            ok &= prior1_sample(pri.p[k], st, x);
+            B.th[(long long)k * N + i] = x;
+        }
+        const double *th = B.th;
+        lp = prior_logpdf(pri, [&](int k) { return th[(long long)k * N + i]; });
+        ll = lp;
+        if (dfinite(lp)) {
+            long long ev;
+            double c = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, (uint32_t)i, (uint32_t)t,
+                                               [&](int k) { return th[(long long)k * N + i]; }, ev);
+            ll = kernel_ll(c, P.scale);
+            evals += 1;
+        }
+        if (dfinite(xadd(lp, ll)) || t >= P.retry_cap) break;
+    }
+    B.lp[i] = lp;
+    B.ll[i] = ll;
+    if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
+    if (t) atomicAdd(&B.ctrl->retries, (unsigned long long)t);
+    atomicAdd(&B.ctrl->cost_evals, (unsigned long long)evals);
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(GK_THREADS)
+k_ais_init_gk(AisBufs B, AisParams P, DPriors pri, DModel m, RoundKeys rk) {
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    const long long N = P.N;
+    for (long long i = blockIdx.x; i < N; i += gridDim.x) {
+        double lp = 0, ll = 0, x[4];
+        long long t = 0, evals = 0;
+        bool ok = true;
+        for (;; ++t) { // every thread draws the same prior sample (same stream), so the loop is uniform
+            Stream st(rk, ST_PRIOR, (uint32_t)i, (uint32_t)t);
+            for (int k = 0; k < 4; ++k) ok &= prior1_sample(pri.p[k], st, x[k]);
+            lp = prior_logpdf(pri, [&](int k) { return x[k]; });
+            ll = lp;
+            if (dfinite(lp)) {
+                double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, (uint32_t)t, x[0], x[1], x[2], x[3], gk_smem);
+                ll = kernel_ll(c, P.scale);
+                evals += 1;
+            }
+            if (dfinite(xadd(lp, ll)) || t >= P.retry_cap) break;
+        }
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 4; ++k) B.th[(long long)k * N + i] = x[k];
+            B.lp[i] = lp;
+            B.ll[i] = ll;
+            if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
+            if (t) atomicAdd(&B.ctrl->retries, (unsigned long long)t);
+            atomicAdd(&B.ctrl->cost_evals, (unsigned long long)evals);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ propose, ref src/transition.jl:2-65
+// colour range [lo,hi) moves; partners from [clo, clo+cn)
+__global__ void __launch_bounds__(256)
+k_ais_propose(AisBufs B, AisParams P, DPriors pri, RoundKeys rk, long long lo, long long hi, long long clo, long long cn) {
+    AisCtrl *ctl = B.ctrl;
+    const long long N = P.N;
+    const int d = P.d;
+    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool push = false;
+    if (i < hi) {
+        const double *th = B.th;
+        const uint32_t epoch = ctl->epoch;
+        Stream st(rk, ST_PROPOSE, (uint32_t)i, epoch);
+        long long a = i, b = i, c = i;
+        double corr = 0.0;
+        const uint32_t slot = index_of(st.next(), 7u); // ref :62 rand(rng,(1,1,1,1,2,2,3))
+        const int move = slot < 4 ? 1 : (slot < 6 ? 2 : 3);
+        if (move == 1) { // stretch
+            while (a == i) a = clo + (long long)index_of(st.next(), (uint32_t)cn);
+            const double u = next_uniform(st);
+            const double sa = xsqrt(3.0), ra = xsqrt(xdiv(1.0, 3.0));
+            const double t = xadd(xmul(u, xsub(sa, ra)), ra);
+            const double Z = xmul(t, t);
+            for (int k = 0; k < d; ++k) {
+                const double xa = th[(long long)k * N + a], xi = th[(long long)k * N + i];
+                B.thp[(long long)k * N + i] = xadd(xa, xmul(xsub(xi, xa), Z));
+            }
+            corr = xmul((double)(d - 1), xlog(Z));
+            b = -1; c = -1;
+        } else if (move == 2) { // differential evolution
+            const double z0 = next_normal(st);
+            const double gam = xmul(xdiv(2.38, xsqrt((double)(2 * d))), xexp(xmul(z0, 0.1)));
+            while (a == i) a = clo + (long long)index_of(st.next(), (uint32_t)cn);
+            while (b == a || b == i) b = clo + (long long)index_of(st.next(), (uint32_t)cn);
+            for (int k = 0; k < d; ++k) {
+                const double xa = th[(long long)k * N + a], xb = th[(long long)k * N + b], xi = th[(long long)k * N + i];
+                const double W = xmul(xsub(xa, xb), gam);
+                const double S = xadd(xadd(fabs(xsub(xa, xb)), fabs(xsub(xi, xb))), fabs(xsub(xa, xi)));
+                const double T = xmul(xdiv(xmul(gam, S), 300.0), next_normal(st));
+                B.thp[(long long)k * N + i] = xadd(xadd(xi, W), T);
+            }
+            c = -1;
+        } else { // walk
+            while (a == i) a = clo + (long long)index_of(st.next(), (uint32_t)cn);
+            while (b == a || b == i) b = clo + (long long)index_of(st.next(), (uint32_t)cn);
+            while (c == b || c == a || c == i) c = clo + (long long)index_of(st.next(), (uint32_t)cn);
+            const double z1 = next_normal(st), z2 = next_normal(st), z3 = next_normal(st);
+            for (int k = 0; k < d; ++k) {
+                const double xa = th[(long long)k * N + a], xb = th[(long long)k * N + b], xc = th[(long long)k * N + c];
+                const double xs = xdiv(xadd(xa, xadd(xb, xc)), 3.0);
+                const double W = xadd(xadd(xmul(z1, xsub(xa, xs)), xmul(z2, xsub(xb, xs))), xmul(z3, xsub(xc, xs)));
+                B.thp[(long long)k * N + i] = xadd(th[(long long)k * N + i], W);
+            }
+        }
+        const double *thp = B.thp;
+        const double lpp = prior_logpdf(pri, [&](int k) { return thp[(long long)k * N + i]; });
+        B.lpp[i] = lpp;
+        B.corr[i] = corr;
+        push = dfinite(lpp);
+        if (B.trace_on) {
+            B.tr.move[i] = (unsigned char)move; B.tr.a[i] = a; B.tr.b[i] = b; B.tr.c[i] = c; B.tr.corr[i] = corr;
+            B.tr.lpp[i] = lpp; B.tr.llp[i] = lpp; B.tr.e[i] = dnan(); B.tr.dec[i] = 0;
+        }
+    }
+    unsigned int ball = __ballot_sync(0xffffffffu, push);
+    unsigned int lane = threadIdx.x & 31, base = 0;
+    if (ball) {
+        if (lane == 0) base = atomicAdd(&ctl->work_count, (unsigned int)__popc(ball));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) B.work[base + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
+    }
+}
+
+// ref src/types.jl:62-75 + src/transition.jl:76-79
+__device__ __forceinline__ unsigned int ais_accept(AisBufs &B, const AisParams &P, const RoundKeys &rk, long long i,
+                                                   uint32_t epoch, double cost) {
+    const long long N = P.N;
+    const double lpp = B.lpp[i];
+    const double llp = kernel_ll(cost, P.scale);
+    int dec = 0;
+    double e = dnan();
+    if (dfinite(xadd(lpp, llp))) {
+        Stream sa(rk, ST_ACCEPT, (uint32_t)i, epoch);
+        e = next_exp(sa);
+        const double lW = xsub(xadd(B.corr[i], xadd(lpp, llp)), xadd(B.lp[i], B.ll[i]));
+        dec = (-e <= lW) ? 2 : 1;
+    }
+    if (dec == 2) {
+        for (int k = 0; k < P.d; ++k) B.th[(long long)k * N + i] = B.thp[(long long)k * N + i];
+        B.lp[i] = lpp;
+        B.ll[i] = llp;
+    }
+    if (B.trace_on) { B.tr.llp[i] = llp; B.tr.e[i] = e; B.tr.dec[i] = (unsigned char)dec; }
+    return dec == 2;
+}
+
+template <int KIND, int PREC>
+__global__ void __launch_bounds__(256) k_ais_simulate(AisBufs B, AisParams P, DModel m, RoundKeys rk) {
+    AisCtrl *ctl = B.ctrl;
+    const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nwork = ctl->work_count;
+    if ((w & ~31u) >= nwork) return;
+    unsigned int acc = 0;
+    if (w < nwork) {
+        const long long i = B.work[w];
+        const long long N = P.N;
+        const double *thp = B.thp;
+        long long ev;
+        const uint32_t epoch = ctl->epoch;
+        double c = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)i, epoch, [&](int k) { return thp[(long long)k * N + i]; }, ev);
+        acc = ais_accept(B, P, rk, i, epoch, c);
+    }
+    unsigned int nacc = __popc(__ballot_sync(0xffffffffu, acc));
+    if ((threadIdx.x & 31) == 0 && nacc) atomicAdd(&ctl->accepted, (unsigned long long)nacc);
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(GK_THREADS) k_ais_simulate_gk(AisBufs B, AisParams P, DModel m, RoundKeys rk) {
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    AisCtrl *ctl = B.ctrl;
+    const unsigned int nwork = ctl->work_count;
+    const long long N = P.N;
+    const uint32_t epoch = ctl->epoch;
+    for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const long long i = B.work[w];
+        const double *thp = B.thp;
+        double c = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, epoch, thp[i], thp[N + i], thp[2 * N + i], thp[3 * N + i], gk_smem);
+        if (threadIdx.x == 0 && ais_accept(B, P, rk, i, epoch, c)) atomicAdd(&ctl->accepted, 1ull);
+    }
+}
+
+__global__ void k_ais_post_half(AisBufs B, int colour) {
+    AisCtrl *c = B.ctrl;
+    c->cost_evals += c->work_count;
+    c->work_count = 0;
+    c->epoch += 1;
+    if (colour == 1) c->sweeps += 1;
+}
+
+__global__ void k_ais_reset(AisBufs B) {
+    AisCtrl *c = B.ctrl;
+    c->accepted = 0; c->cost_evals = 0; c->retries = 0; c->sweeps = 0; c->work_count = 0; c->epoch = 0; c->err = 0;
+}
+
+// bundle_samples, ref src/KissABC.jl:78,90-93: saved sample m is walker w_m of the current ensemble
+__global__ void k_ais_record(AisBufs B, AisParams P, double *out, long long Ns, long long m0, long long m1,
+                             long long discard, long long thinning) {
+    long long m = m0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= m1) return;
+    const long long target = discard + m * thinning;
+    const long long w = target > 0 ? (target - 1) % P.N : P.N - 1;
+    for (int k = 0; k < P.d; ++k) out[(long long)k * Ns + m] = B.th[(long long)k * P.N + w];
+}
+
+} // namespace kabc
+
+using namespace kabc;
+
+struct kabc_ais {
+    kabc_ctx *ctx = nullptr;
+    DPriors pri;
+    DModel model;
+    AisParams P;
+    kabc_ais_config_t cfg;
+    AisBufs B;
+    DevBuf<double> th, lp, ll, thp, lpp, corr;
+    DevBuf<unsigned int> work;
+    DevBuf<AisCtrl> ctrl;
+    DevBuf<unsigned char> tmove, tdec;
+    DevBuf<long long> ta, tb, tc;
+    DevBuf<double> tcorr, tlpp, tllp, te;
+    AisCtrl *h_ctrl = nullptr;
+    bool inited = false;
+    long long launches = 0;
+};
+
+#define AIS_LAUNCHED(s) do { (s)->launches += 1; (s)->ctx->launches += 1; } while (0)
+
+static int ais_read_ctrl(kabc_ais *s) {
+    KABC_CUDA_TRY(cudaMemcpyAsync(s->h_ctrl, s->B.ctrl, sizeof(AisCtrl), cudaMemcpyDeviceToHost, s->ctx->stream));
+    KABC_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    return KABC_OK;
+}
+
+static int ais_gk_grid(kabc_ais *s, long long n, size_t &smem) {
+    smem = gk_smem_bytes(s->model.n_draws, s->model.precision);
+    long long cap = (long long)s->ctx->sm_count * gk_blocks_per_sm(s->model.n_draws, s->model.precision);
+    return (int)(n < cap ? n : cap);
+}
+
+template <int KIND>
+static void ais_launch_init_t(kabc_ais *s) {
+    const unsigned blocks = (unsigned)((s->P.N + 255) / 256);
+    if (s->model.precision == KABC_F64)
+        k_ais_init<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk);
+    else
+        k_ais_init<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk);
+    AIS_LAUNCHED(s);
+}
+
+template <int KIND>
+static void ais_launch_sim_t(kabc_ais *s, long long n) {
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (s->model.precision == KABC_F64)
+        k_ais_simulate<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk);
+    else
+        k_ais_simulate<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk);
+    AIS_LAUNCHED(s);
+}
+
+static int ais_enqueue_half(kabc_ais *s, int colour) {
+    kabc_ctx *ctx = s->ctx;
+    const long long N = s->P.N, h = N / 2;
+    const long long lo = colour == 0 ? 0 : h, hi = colour == 0 ? h : N;
+    const long long clo = colour == 0 ? h : 0, cn = colour == 0 ? N - h : h;
+    const long long n = hi - lo;
+    k_ais_propose<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, lo, hi, clo, cn);
+    AIS_LAUNCHED(s);
+    switch (s->model.kind) {
+    case KABC_MODEL_NORMAL_MEANSTD: ais_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s, n); break;
+    case KABC_MODEL_MA2_AUTOCOV: ais_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s, n); break;
+    case KABC_MODEL_LV_SSA: ais_launch_sim_t<KABC_MODEL_LV_SSA>(s, n); break;
+    case KABC_MODEL_DETERMINISTIC: ais_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s, n); break;
+    case KABC_MODEL_GK_OCTILE: {
+        size_t smem;
+        int grid = ais_gk_grid(s, n, smem);
+        if (s->model.precision == KABC_F64) {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_ais_simulate_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_ais_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
+        } else {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_ais_simulate_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_ais_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
+        }
+        AIS_LAUNCHED(s);
+        break;
+    }
+    }
+    k_ais_post_half<<<1, 1, 0, ctx->stream>>>(s->B, colour);
+    AIS_LAUNCHED(s);
+    KABC_CUDA_TRY(cudaGetLastError());
+    return KABC_OK;
+}
+
+extern "C" {
+
+int kabc_ais_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model,
+                    const kabc_ais_config_t *cfg, kabc_ais_t **out) {
+    if (!ctx || !cfg || !out) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
+    DPriors pri;
+    DModel m;
+    if (int rc = ingest_priors(prior, d, pri)) return rc;
+    // ref src/KissABC.jl:43-48
+    if (cfg->nwalkers < d + 5)
+        return set_error(KABC_ERR_INVALID_ARG, "nparticles = %lld is insufficient, set number of particles in AIS(.) atleast to %d",
+                         (long long)cfg->nwalkers, d + 5);
+    if (cfg->nwalkers > 0x7FFFFFFFll) return set_error(KABC_ERR_INVALID_ARG, "nwalkers must be < 2^31");
+    if (!(cfg->scale > 0)) return set_error(KABC_ERR_INVALID_ARG, "kernel scale (target_average_cost) must be > 0");
+    if (cfg->nsamples < 0 || cfg->ntransitions < 1 || cfg->discard_initial < 0 || cfg->thinning < 1 || cfg->retry_sampling < 0)
+        return set_error(KABC_ERR_INVALID_ARG, "bad AIS configuration");
+    if (int rc = ingest_model(model, d, m)) return rc;
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    kabc_ais *s = new kabc_ais();
+    s->ctx = ctx; s->pri = pri; s->model = m; s->cfg = *cfg;
+    const long long N = cfg->nwalkers;
+    s->P.N = N; s->P.d = d; s->P.scale = cfg->scale; s->P.retry_cap = cfg->retry_sampling * N + 1;
+    const size_t nd = (size_t)N * d;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(s->th.alloc(nd)); A(s->thp.alloc(nd)); A(s->lp.alloc(N)); A(s->ll.alloc(N)); A(s->lpp.alloc(N));
+    A(s->corr.alloc(N)); A(s->work.alloc(N)); A(s->ctrl.alloc(1));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_ctrl, sizeof(AisCtrl));
+    if (e != cudaSuccess) {
+        delete s;
+        return set_error(KABC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    memset(s->h_ctrl, 0, sizeof(AisCtrl));
+    s->B.th = s->th.p; s->B.lp = s->lp.p; s->B.ll = s->ll.p; s->B.thp = s->thp.p; s->B.lpp = s->lpp.p;
+    s->B.corr = s->corr.p; s->B.work = s->work.p; s->B.ctrl = s->ctrl.p;
+    memset(&s->B.tr, 0, sizeof s->B.tr);
+    s->B.trace_on = 0;
+    KABC_CUDA_TRY(cudaMemsetAsync(s->ctrl.p, 0, sizeof(AisCtrl), ctx->stream));
+    *out = s;
+    return KABC_OK;
+}
+
+int kabc_ais_destroy(kabc_ais_t *s) {
+    if (!s) return KABC_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    delete s;
+    return KABC_OK;
+}
+
+int kabc_ais_init(kabc_ais_t *s) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "ais is NULL");
+    kabc_ctx *ctx = s->ctx;
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    k_ais_reset<<<1, 1, 0, ctx->stream>>>(s->B);
+    AIS_LAUNCHED(s);
+    switch (s->model.kind) {
+    case KABC_MODEL_NORMAL_MEANSTD: ais_launch_init_t<KABC_MODEL_NORMAL_MEANSTD>(s); break;
+    case KABC_MODEL_MA2_AUTOCOV: ais_launch_init_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
+    case KABC_MODEL_LV_SSA: ais_launch_init_t<KABC_MODEL_LV_SSA>(s); break;
+    case KABC_MODEL_DETERMINISTIC: ais_launch_init_t<KABC_MODEL_DETERMINISTIC>(s); break;
+    case KABC_MODEL_GK_OCTILE: {
+        size_t smem;
+        int grid = ais_gk_grid(s, s->P.N, smem);
+        if (s->model.precision == KABC_F64) {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_ais_init_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_ais_init_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->pri, s->model, ctx->rk);
+        } else {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_ais_init_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_ais_init_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->pri, s->model, ctx->rk);
+        }
+        AIS_LAUNCHED(s);
+        break;
+    }
+    }
+    KABC_CUDA_TRY(cudaGetLastError());
+    if (int rc = ais_read_ctrl(s)) return rc;
+    if (s->h_ctrl->err) return set_error(KABC_ERR_INVALID_ARG, "prior sampling failed (truncation too extreme)");
+    if ((long long)s->h_ctrl->retries > s->cfg.retry_sampling * s->P.N)
+        return set_error(KABC_ERR_RETRY_BUDGET, "Prior leads to \xe2\x88\x9e costs too often, tune the prior or increase `retry_sampling`.");
+    s->inited = true;
+    return KABC_OK;
+}
+
+int kabc_ais_sweep(kabc_ais_t *s, int nsweeps, float *out_ms) {
+    if (!s || nsweeps < 0) return set_error(KABC_ERR_INVALID_ARG, "bad argument");
+    if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_ais_init must be called first");
+    if (s->P.N / 2 < 3) return set_error(KABC_ERR_INVALID_ARG, "red/black AIS needs >= 3 walkers per colour");
+    kabc_ctx *ctx = s->ctx;
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    KABC_CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int r = 0; r < nsweeps; ++r) {
+        if (int rc = ais_enqueue_half(s, 0)) return rc;
+        if (int rc = ais_enqueue_half(s, 1)) return rc;
+    }
+    KABC_CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (out_ms) KABC_CUDA_TRY(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+    return KABC_OK;
+}
+
+int kabc_ais_get_state(kabc_ais_t *s, double *theta, double *lp, double *ll) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "ais is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    const size_t N = (size_t)s->P.N;
+    cudaStream_t st = s->ctx->stream;
+    if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(theta, s->B.th, 8 * N * s->P.d, cudaMemcpyDeviceToHost, st));
+    if (lp) KABC_CUDA_TRY(cudaMemcpyAsync(lp, s->B.lp, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (ll) KABC_CUDA_TRY(cudaMemcpyAsync(ll, s->B.ll, 8 * N, cudaMemcpyDeviceToHost, st));
+    KABC_CUDA_TRY(cudaStreamSynchronize(st));
+    return KABC_OK;
+}
+
+int kabc_ais_set_state(kabc_ais_t *s, const double *theta, const double *lp, const double *ll) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "ais is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    const size_t N = (size_t)s->P.N;
+    cudaStream_t st = s->ctx->stream;
+    if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.th, theta, 8 * N * s->P.d, cudaMemcpyHostToDevice, st));
+    if (lp) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.lp, lp, 8 * N, cudaMemcpyHostToDevice, st));
+    if (ll) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.ll, ll, 8 * N, cudaMemcpyHostToDevice, st));
+    KABC_CUDA_TRY(cudaStreamSynchronize(st));
+    s->inited = true;
+    return KABC_OK;
+}
+
+int kabc_ais_get_counters(kabc_ais_t *s, int64_t *cost_evals, int64_t *accepted, int64_t *sweeps, int64_t *retries) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "ais is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (int rc = ais_read_ctrl(s)) return rc;
+    if (cost_evals) *cost_evals = (int64_t)s->h_ctrl->cost_evals;
+    if (accepted) *accepted = (int64_t)s->h_ctrl->accepted;
+    if (sweeps) *sweeps = s->h_ctrl->sweeps;
+    if (retries) *retries = (int64_t)s->h_ctrl->retries;
+    return KABC_OK;
+}
+
+int64_t kabc_ais_kernel_launches(kabc_ais_t *s) { return s ? s->launches : -1; }
+
+int kabc_ais_trace_enable(kabc_ais_t *s, int on) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "ais is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    KABC_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    if (on && !s->ta.p) {
+        const size_t N = (size_t)s->P.N;
+        KABC_CUDA_TRY(s->tmove.alloc(N)); KABC_CUDA_TRY(s->tdec.alloc(N)); KABC_CUDA_TRY(s->ta.alloc(N));
+        KABC_CUDA_TRY(s->tb.alloc(N)); KABC_CUDA_TRY(s->tc.alloc(N)); KABC_CUDA_TRY(s->tcorr.alloc(N));
+        KABC_CUDA_TRY(s->tlpp.alloc(N)); KABC_CUDA_TRY(s->tllp.alloc(N)); KABC_CUDA_TRY(s->te.alloc(N));
+        s->B.tr.move = s->tmove.p; s->B.tr.dec = s->tdec.p; s->B.tr.a = s->ta.p; s->B.tr.b = s->tb.p; s->B.tr.c = s->tc.p;
+        s->B.tr.corr = s->tcorr.p; s->B.tr.lpp = s->tlpp.p; s->B.tr.llp = s->tllp.p; s->B.tr.e = s->te.p;
+    }
+    s->B.trace_on = on ? 1 : 0;
+    return KABC_OK;
+}
+
+int kabc_ais_get_trace(kabc_ais_t *s, uint8_t *move, int64_t *a, int64_t *b, int64_t *c, double *corr, double *theta_p,
+                       double *lp_p, double *ll_p, double *e, uint8_t *decision) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "ais is NULL");
+    if (!s->ta.p) return set_error(KABC_ERR_STATE, "trace was never enabled");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    const size_t N = (size_t)s->P.N;
+    cudaStream_t st = s->ctx->stream;
+    if (move) KABC_CUDA_TRY(cudaMemcpyAsync(move, s->tmove.p, N, cudaMemcpyDeviceToHost, st));
+    if (a) KABC_CUDA_TRY(cudaMemcpyAsync(a, s->ta.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (b) KABC_CUDA_TRY(cudaMemcpyAsync(b, s->tb.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (c) KABC_CUDA_TRY(cudaMemcpyAsync(c, s->tc.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (corr) KABC_CUDA_TRY(cudaMemcpyAsync(corr, s->tcorr.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (theta_p) KABC_CUDA_TRY(cudaMemcpyAsync(theta_p, s->thp.p, 8 * N * s->P.d, cudaMemcpyDeviceToHost, st));
+    if (lp_p) KABC_CUDA_TRY(cudaMemcpyAsync(lp_p, s->tlpp.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (ll_p) KABC_CUDA_TRY(cudaMemcpyAsync(ll_p, s->tllp.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (e) KABC_CUDA_TRY(cudaMemcpyAsync(e, s->te.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (decision) KABC_CUDA_TRY(cudaMemcpyAsync(decision, s->tdec.p, N, cudaMemcpyDeviceToHost, st));
+    KABC_CUDA_TRY(cudaStreamSynchronize(st));
+    return KABC_OK;
+}
+
+int kabc_ais_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model,
+                 const kabc_ais_config_t *cfg, double *out_samples, int64_t *out_cost_evals, int64_t *out_accepted) {
+    if (!out_samples) return set_error(KABC_ERR_INVALID_ARG, "out_samples is NULL");
+    kabc_ais *s = nullptr;
+    if (int rc = kabc_ais_create(ctx, prior, d, model, cfg, &s)) return rc;
+    int rc = kabc_ais_init(s);
+    const long long N = s->P.N, Ns = cfg->nsamples;
+    DevBuf<double> dout;
+    if (!rc && Ns > 0) {
+        cudaError_t e = dout.alloc((size_t)Ns * d);
+        if (e != cudaSuccess) rc = set_error(KABC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    auto need_of = [&](long long m) {
+        long long target = cfg->discard_initial + m * cfg->thinning;
+        return target > 0 ? (target + N - 1) / N : 0ll;
+    };
+    long long rounds = 0, m = 0;
+    if (!rc && Ns > 0 && need_of(Ns - 1) > 0 && N / 2 < 3) rc = set_error(KABC_ERR_INVALID_ARG, "red/black AIS needs >= 3 walkers per colour");
+    while (!rc && m < Ns) {
+        const long long need = need_of(m);
+        while (!rc && rounds < need) { // one round = ntransitions sweeps of the whole ensemble
+            for (long long r = 0; !rc && r < cfg->ntransitions; ++r) {
+                rc = ais_enqueue_half(s, 0);
+                if (!rc) rc = ais_enqueue_half(s, 1);
+            }
+            ++rounds;
+        }
+        long long m1 = m;
+        while (m1 < Ns && need_of(m1) == need) ++m1;
+        if (!rc) {
+            k_ais_record<<<(unsigned)((m1 - m + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, dout.p, Ns, m, m1, cfg->discard_initial, cfg->thinning);
+            AIS_LAUNCHED(s);
+        }
+        m = m1;
+    }
+    if (!rc && Ns > 0) {
+        cudaError_t e = cudaMemcpyAsync(out_samples, dout.p, sizeof(double) * (size_t)Ns * d, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = set_error(KABC_ERR_CUDA, "copy of samples failed: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = kabc_ais_get_counters(s, out_cost_evals, out_accepted, nullptr, nullptr);
+    std::string keep = g_last_error;
+    kabc_ais_destroy(s);
+    g_last_error = keep;
+    return rc;
+}
+
+} // extern "C"

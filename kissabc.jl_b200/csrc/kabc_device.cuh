@@ -1,0 +1,265 @@
+// kabc_device.cuh -- device building blocks of the KissABC hot path (sm_100a).
+//   * Philox4x32-10 counter streams (DESIGN.md "Variate spec")
+//   * exactly-rounded FP64 elementary functions: a fixed sequence of IEEE ops, so the F64 path is
+//     bit-reproducible on any IEEE machine (this is what the parity tests rely on)
+//   * priors: logpdf(Factored) ref src/priors.jl:30-36, rand(Factored) ref src/priors.jl:42-43
+//   * fast FP32 Box-Muller on the MUFU pipe for the F32_ACC64 simulators
+// Compile with -fmad=false: every fused multiply-add in this file is explicit.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/kissabc_cuda.h"
+
+namespace kabc {
+
+enum StreamTag : uint32_t { ST_PRIOR = 1, ST_PROPOSE = 2, ST_COST = 3, ST_ACCEPT = 4, ST_COST_INIT = 5 };
+
+// Philox round keys, precomputed on the host: they are launch constants, so in SASS they become
+// constant-bank operands of the LOP3 and cost no instruction.
+struct RoundKeys {
+    uint32_t k0[10], k1[10];
+};
+
+__host__ __device__ inline RoundKeys make_round_keys(uint64_t seed) {
+    RoundKeys rk;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk.k0[r] = a;
+        rk.k1[r] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return rk;
+}
+
+__device__ __forceinline__ void philox4x32_10(const RoundKeys &rk, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k0[r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk.k1[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// sequential word stream (seed ; block j, id, epoch, tag): used by the low-rate code (proposals, priors, accept)
+struct Stream {
+    const RoundKeys &rk;
+    uint32_t j, id, epoch, tag;
+    uint32_t b0, b1, b2, b3;
+    int pos;
+    __device__ __forceinline__ Stream(const RoundKeys &rk_, uint32_t tag_, uint32_t id_, uint32_t epoch_)
+        : rk(rk_), j(0), id(id_), epoch(epoch_), tag(tag_), b0(0), b1(0), b2(0), b3(0), pos(4) {}
+    __device__ __forceinline__ uint32_t next() {
+        if (pos == 4) {
+            philox4x32_10(rk, j, id, epoch, tag, b0, b1, b2, b3);
+            j += 1;
+            pos = 0;
+        }
+        uint32_t w = pos == 0 ? b0 : (pos == 1 ? b1 : (pos == 2 ? b2 : b3));
+        pos += 1;
+        return w;
+    }
+};
+
+// ---------------------------------------------------------------- exact FP64 functions
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
+
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7FF0000000000000ll); }
+__device__ __forceinline__ double dnan() { return __longlong_as_double(0x7FF8000000000000ll); }
+__device__ __forceinline__ bool dfinite(double x) {
+    return ((unsigned long long)__double_as_longlong(x) & 0x7FF0000000000000ull) != 0x7FF0000000000000ull;
+}
+
+static __device__ __noinline__ double xlog(double x) {
+    if (x != x) return x;
+    if (x < 0.0) return dnan();
+    if (x == 0.0) return -dinf();
+    if (x == dinf()) return x;
+    int e = 0;
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    if ((b >> 52) == 0) {
+        x = xmul(x, 18014398509481984.0);
+        b = (unsigned long long)__double_as_longlong(x);
+        e = -54;
+    }
+    e += (int)(b >> 52) - 1023;
+    double m = __longlong_as_double((long long)((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+    if (m > 1.4142135623730951) { m = xmul(m, 0.5); e += 1; }
+    double s = xdiv(xsub(m, 1.0), xadd(m, 1.0));
+    double s2 = xmul(s, s);
+    double p = 1.0 / 23.0;
+    p = xfma(p, s2, 1.0 / 21.0);
+    p = xfma(p, s2, 1.0 / 19.0);
+    p = xfma(p, s2, 1.0 / 17.0);
+    p = xfma(p, s2, 1.0 / 15.0);
+    p = xfma(p, s2, 1.0 / 13.0);
+    p = xfma(p, s2, 1.0 / 11.0);
+    p = xfma(p, s2, 1.0 / 9.0);
+    p = xfma(p, s2, 1.0 / 7.0);
+    p = xfma(p, s2, 1.0 / 5.0);
+    p = xfma(p, s2, 1.0 / 3.0);
+    double t = xmul(xmul(s, s2), p);
+    double r = xadd(xmul(2.0, s), xmul(2.0, t));
+    double ef = (double)e;
+    return xadd(xmul(ef, 6.93147180369123816490e-01), xadd(r, xmul(ef, 1.90821492927058770002e-10)));
+}
+
+static __device__ __noinline__ double xexp(double x) {
+    if (x != x) return x;
+    if (x > 709.78) return dinf();
+    if (x < -745.2) return 0.0;
+    double k = floor(xadd(xmul(x, 1.4426950408889634), 0.5));
+    double r = xfma(-k, 6.93147180369123816490e-01, x);
+    r = xfma(-k, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 87178291200.0;
+    p = xfma(p, r, 1.0 / 6227020800.0);
+    p = xfma(p, r, 1.0 / 479001600.0);
+    p = xfma(p, r, 1.0 / 39916800.0);
+    p = xfma(p, r, 1.0 / 3628800.0);
+    p = xfma(p, r, 1.0 / 362880.0);
+    p = xfma(p, r, 1.0 / 40320.0);
+    p = xfma(p, r, 1.0 / 5040.0);
+    p = xfma(p, r, 1.0 / 720.0);
+    p = xfma(p, r, 1.0 / 120.0);
+    p = xfma(p, r, 1.0 / 24.0);
+    p = xfma(p, r, 1.0 / 6.0);
+    p = xfma(p, r, 0.5);
+    p = xfma(p, r, 1.0);
+    p = xfma(p, r, 1.0);
+    int ki = (int)k;
+    int k1 = ki / 2, k2 = ki - k1;
+    double f1 = __longlong_as_double((long long)(k1 + 1023) << 52);
+    double f2 = __longlong_as_double((long long)(k2 + 1023) << 52);
+    return xmul(xmul(p, f1), f2);
+}
+
+__device__ __forceinline__ void xsincos2pi(double u, double &sn, double &cs) {
+    double q = floor(xadd(xmul(4.0, u), 0.5));
+    double t = xsub(u, xmul(0.25, q));
+    double phi = xmul(t, 6.283185307179586);
+    double p2 = xmul(phi, phi);
+    double ps = -1.0 / 121645100408832000.0;
+    ps = xfma(ps, p2, 1.0 / 355687428096000.0);
+    ps = xfma(ps, p2, -1.0 / 1307674368000.0);
+    ps = xfma(ps, p2, 1.0 / 6227020800.0);
+    ps = xfma(ps, p2, -1.0 / 39916800.0);
+    ps = xfma(ps, p2, 1.0 / 362880.0);
+    ps = xfma(ps, p2, -1.0 / 5040.0);
+    ps = xfma(ps, p2, 1.0 / 120.0);
+    ps = xfma(ps, p2, -1.0 / 6.0);
+    double s = xfma(xmul(phi, p2), ps, phi);
+    double pc = 1.0 / 6402373705728000.0;
+    pc = xfma(pc, p2, -1.0 / 20922789888000.0);
+    pc = xfma(pc, p2, 1.0 / 87178291200.0);
+    pc = xfma(pc, p2, -1.0 / 479001600.0);
+    pc = xfma(pc, p2, 1.0 / 3628800.0);
+    pc = xfma(pc, p2, -1.0 / 40320.0);
+    pc = xfma(pc, p2, 1.0 / 720.0);
+    pc = xfma(pc, p2, -1.0 / 24.0);
+    pc = xfma(pc, p2, 0.5);
+    double c = xfma(-p2, pc, 1.0);
+    int qi = ((int)q) & 3;
+    sn = qi == 0 ? s : (qi == 1 ? c : (qi == 2 ? -s : -c));
+    cs = qi == 0 ? c : (qi == 1 ? -s : (qi == 2 ? -c : s));
+}
+
+__device__ __forceinline__ double u01(uint32_t w) { return xmul(xadd((double)w, 0.5), 2.3283064365386962890625e-10); }
+__device__ __forceinline__ uint32_t index_of(uint32_t w, uint32_t n) { return __umulhi(w, n); }
+
+__device__ __forceinline__ void normal_pair64(uint32_t w0, uint32_t w1, double &z0, double &z1) {
+    double r = xsqrt(xmul(-2.0, xlog(u01(w0))));
+    double s, c;
+    xsincos2pi(u01(w1), s, c);
+    z0 = xmul(r, c);
+    z1 = xmul(r, s);
+}
+__device__ __forceinline__ double next_uniform(Stream &st) { return u01(st.next()); }
+__device__ __forceinline__ double next_normal(Stream &st) {
+    uint32_t w0 = st.next(), w1 = st.next();
+    double z0, z1;
+    normal_pair64(w0, w1, z0, z1);
+    return z0;
+}
+__device__ __forceinline__ double next_exp(Stream &st) { return -xlog(next_uniform(st)); }
+
+// ---------------------------------------------------------------- fast FP32 normals (MUFU pipe)
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Same words, same Box-Muller map as normal_pair64, evaluated in FP32 with hardware approximations:
+// u = (w+0.5)/2^32 rounded to float; r = sqrt(-2 ln2 * lg2(u1)); angle = 2 pi u2.
+__device__ __forceinline__ void normal_pair32(uint32_t w0, uint32_t w1, float &z0, float &z1) {
+    float u1 = __fmaf_rn(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float ang = __fmaf_rn(__uint2float_rn(w1), 1.4629180792671596e-09f, 7.3145903963357980e-10f); // 2pi(w+0.5)/2^32
+    float r = mufu_sqrt(__fmul_rn(mufu_lg2(u1), -1.3862943611198906f));
+    z0 = __fmul_rn(r, mufu_cos(ang));
+    z1 = __fmul_rn(r, mufu_sin(ang));
+}
+
+// ---------------------------------------------------------------- priors
+#define KABC_LOG2PI 1.8378770664093453
+struct DPrior {
+    int kind;
+    double p0, p1, lo, hi;
+    double c0; // Uniform: log(b-a); Normal/Truncated: log(sigma)     (host libm, same expression as the oracle)
+    double c1; // Truncated: log(Phi((hi-mu)/sigma) - Phi((lo-mu)/sigma))
+};
+struct DPriors {
+    int d;
+    DPrior p[KABC_MAX_DIM];
+};
+
+__device__ __forceinline__ double prior1_logpdf(const DPrior &p, double x) {
+    if (p.kind == KABC_PRIOR_UNIFORM) return (x >= p.p0 && x <= p.p1) ? -p.c0 : -dinf();
+    if (p.kind == KABC_PRIOR_TRUNC_NORMAL && !(x >= p.lo && x <= p.hi)) return -dinf();
+    double z = xdiv(xsub(x, p.p0), p.p1);
+    double base = xsub(xdiv(-xadd(xmul(z, z), KABC_LOG2PI), 2.0), p.c0);
+    return p.kind == KABC_PRIOR_NORMAL ? base : xsub(base, p.c1);
+}
+// ref src/priors.jl:30-36: left-to-right sum from component 1
+template <typename F>
+__device__ __forceinline__ double prior_logpdf(const DPriors &P, F get) {
+    double s = prior1_logpdf(P.p[0], get(0));
+    for (int k = 1; k < P.d; ++k) s = xadd(s, prior1_logpdf(P.p[k], get(k)));
+    return s;
+}
+#define KABC_TRUNC_MAX_TRIES (1 << 20)
+__device__ __forceinline__ bool prior1_sample(const DPrior &p, Stream &st, double &out) {
+    if (p.kind == KABC_PRIOR_UNIFORM) {
+        out = xadd(p.p0, xmul(xsub(p.p1, p.p0), next_uniform(st)));
+        return true;
+    }
+    if (p.kind == KABC_PRIOR_NORMAL) {
+        out = xadd(p.p0, xmul(p.p1, next_normal(st)));
+        return true;
+    }
+    for (int t = 0; t < KABC_TRUNC_MAX_TRIES; ++t) {
+        double x = xadd(p.p0, xmul(p.p1, next_normal(st)));
+        if (x >= p.lo && x <= p.hi) { out = x; return true; }
+    }
+    out = dnan();
+    return false;
+}
+
+// ---------------------------------------------------------------- small reductions
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+} // namespace kabc

@@ -1,0 +1,267 @@
+// kabc_models.cuh -- registered device simulators + distances: the replacement of the opaque `cost`
+// closure of the reference (src/types.jl:55, src/smc.jl:123,176).  One thread evaluates one particle
+// (normal, MA(2), Lotka-Volterra); g-and-k uses one warp per particle (kabc_gk.cuh).
+//
+// Each simulator exists in two precisions:
+//   KABC_F64        fixed sequence of IEEE double ops == oracle/kabc_oracle.c bit for bit
+//   KABC_F32_ACC64  draws generated in FP32 on the MUFU pipe from the SAME Philox words, accumulated in FP32
+//                   partial sums around a known shift, distance finished in FP64
+#pragma once
+#include "kabc_device.cuh"
+
+namespace kabc {
+
+struct DModel {
+    int kind, precision, n_draws, n_target;
+    double target[KABC_MAX_TARGET];
+    double param[KABC_MAX_PARAM];
+};
+
+// ------------------------------------------------------------------ normal model, ref README.md:35-52
+// x = randn(n).*sigma .+ mu ; hypot(mean(x)-t0, (std(x)-t1)*w) ; std with n-1.
+__device__ __forceinline__ double cost_normal_f64(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                                  uint32_t epoch, double mu, double sigma) {
+    const int n = m.n_draws;
+    const int nb = (n + 3) >> 2;
+    double sum = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        uint32_t w0, w1, w2, w3;
+        philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);
+        double z[4];
+        normal_pair64(w0, w1, z[0], z[1]);
+        normal_pair64(w2, w3, z[2], z[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * b + q < n) sum = xadd(sum, xadd(xmul(z[q], sigma), mu));
+    }
+    const double mean = xdiv(sum, (double)n);
+    double ss = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        uint32_t w0, w1, w2, w3;
+        philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);
+        double z[4];
+        normal_pair64(w0, w1, z[0], z[1]);
+        normal_pair64(w2, w3, z[2], z[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * b + q < n) {
+                double dx = xsub(xadd(xmul(z[q], sigma), mu), mean);
+                ss = xadd(ss, xmul(dx, dx));
+            }
+    }
+    const double sd = xsqrt(xdiv(ss, (double)(n - 1)));
+    const double d1 = xsub(mean, m.target[0]);
+    const double d2 = xmul(xsub(sd, m.target[1]), m.param[0]);
+    return xsqrt(xadd(xmul(d1, d1), xmul(d2, d2)));
+}
+
+// FP32 draws; shifted one-pass sums of (x - mu) = sigma*z (exact algebra, well conditioned in FP32).
+__device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                                  uint32_t epoch, double mu, double sigma) {
+    const int n = m.n_draws;
+    const int nbf = n >> 2; // full blocks
+    const float sg = (float)sigma;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int b = 0; b < nbf; ++b) {
+        uint32_t w0, w1, w2, w3;
+        philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);
+        float z[4];
+        normal_pair32(w0, w1, z[0], z[1]);
+        normal_pair32(w2, w3, z[2], z[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float dx = __fmul_rn(sg, z[q]);
+            s1[q] = __fadd_rn(s1[q], dx);
+            s2[q] = __fmaf_rn(dx, dx, s2[q]);
+        }
+    }
+    if (n & 3) {
+        uint32_t w0, w1, w2, w3;
+        philox4x32_10(rk, (uint32_t)nbf, id, epoch, tag, w0, w1, w2, w3);
+        float z[4];
+        normal_pair32(w0, w1, z[0], z[1]);
+        normal_pair32(w2, w3, z[2], z[3]);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < (n & 3)) {
+                float dx = __fmul_rn(sg, z[q]);
+                s1[q] = __fadd_rn(s1[q], dx);
+                s2[q] = __fmaf_rn(dx, dx, s2[q]);
+            }
+    }
+    const double S1 = ((double)s1[0] + (double)s1[1]) + ((double)s1[2] + (double)s1[3]);
+    const double S2 = ((double)s2[0] + (double)s2[1]) + ((double)s2[2] + (double)s2[3]);
+    const double dn = (double)n;
+    const double mean = mu + S1 / dn;
+    double var = (S2 - S1 * S1 / dn) / (double)(n - 1);
+    if (var < 0.0) var = 0.0;
+    const double sd = sqrt(var);
+    const double d1 = mean - m.target[0];
+    const double d2 = (sd - m.target[1]) * m.param[0];
+    return sqrt(d1 * d1 + d2 * d2);
+}
+
+// ------------------------------------------------------------------ MA(2), SURVEY.md Appendix B
+// y_t = e_{t+2} + th1 e_{t+1} + th2 e_t ; tau_j = (1/n) sum_{t>=j} y_t y_{t-j} ; || tau - target ||_2
+__device__ __forceinline__ bool ma2_in_triangle(double t1, double t2) {
+    return t1 > -2.0 && t1 < 2.0 && xadd(t1, t2) > -1.0 && xsub(t1, t2) < 1.0;
+}
+__device__ __forceinline__ double cost_ma2_f64(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                               uint32_t epoch, double t1, double t2) {
+    if (!ma2_in_triangle(t1, t2)) return dinf();
+    const int n = m.n_draws;
+    const int nb = (n + 2 + 3) >> 2;
+    double e0 = 0, e1 = 0, y1 = 0, y2 = 0, a1 = 0, a2 = 0;
+    int t = -2;
+    for (int b = 0; b < nb; ++b) {
+        uint32_t w0, w1, w2, w3;
+        philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);
+        double z[4];
+        normal_pair64(w0, w1, z[0], z[1]);
+        normal_pair64(w2, w3, z[2], z[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (4 * b + q < n + 2) {
+                double e2 = z[q];
+                if (t >= 0) {
+                    double y = xadd(xadd(e2, xmul(t1, e1)), xmul(t2, e0));
+                    if (t >= 1) a1 = xadd(a1, xmul(y, y1));
+                    if (t >= 2) a2 = xadd(a2, xmul(y, y2));
+                    y2 = y1;
+                    y1 = y;
+                }
+                e0 = e1;
+                e1 = e2;
+                ++t;
+            }
+        }
+    }
+    const double d1 = xsub(xdiv(a1, (double)n), m.target[0]);
+    const double d2 = xsub(xdiv(a2, (double)n), m.target[1]);
+    return xsqrt(xadd(xmul(d1, d1), xmul(d2, d2)));
+}
+__device__ __forceinline__ double cost_ma2_f32(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                               uint32_t epoch, double t1d, double t2d) {
+    if (!ma2_in_triangle(t1d, t2d)) return dinf();
+    const int n = m.n_draws;
+    const int nb = (n + 2 + 3) >> 2;
+    const float t1 = (float)t1d, t2 = (float)t2d;
+    float e0 = 0.f, e1 = 0.f, y1 = 0.f, y2 = 0.f, a1 = 0.f, a2 = 0.f;
+    int t = -2;
+    for (int b = 0; b < nb; ++b) {
+        uint32_t w0, w1, w2, w3;
+        philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);
+        float z[4];
+        normal_pair32(w0, w1, z[0], z[1]);
+        normal_pair32(w2, w3, z[2], z[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (4 * b + q < n + 2) {
+                float e2 = z[q];
+                if (t >= 0) {
+                    float y = __fmaf_rn(t2, e0, __fmaf_rn(t1, e1, e2));
+                    if (t >= 1) a1 = __fmaf_rn(y, y1, a1);
+                    if (t >= 2) a2 = __fmaf_rn(y, y2, a2);
+                    y2 = y1;
+                    y1 = y;
+                }
+                e0 = e1;
+                e1 = e2;
+                ++t;
+            }
+        }
+    }
+    const double d1 = (double)a1 / (double)n - m.target[0];
+    const double d2 = (double)a2 / (double)n - m.target[1];
+    return sqrt(d1 * d1 + d2 * d2);
+}
+
+// ------------------------------------------------------------------ Lotka-Volterra, Gillespie direct method
+// theta = log rates; param = {X0, Y0, T, G, max_events}; target = [X(t_1..t_G), Y(t_1..t_G)], t_g = g T/G.
+template <bool F32>
+__device__ __forceinline__ double cost_lv(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                          uint32_t epoch, double l1, double l2, double l3, long long &events) {
+    const double c1 = xexp(l1), c2 = xexp(l2), c3 = xexp(l3);
+    double X = m.param[0], Y = m.param[1];
+    const double T = m.param[2];
+    const int G = (int)m.param[3];
+    const long long max_events = (long long)m.param[4];
+    const double dt = xdiv(T, (double)G);
+    double t = 0.0, acc = 0.0;
+    int g = 0;
+    long long ev = 0;
+    uint32_t blk = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    int have = 0; // unread word pairs left in the current Philox block
+    double ret = 0.0;
+    bool capped = false;
+    while (g < G) {
+        const double a1 = xmul(c1, X), a2 = xmul(xmul(c2, X), Y), a3 = xmul(c3, Y);
+        const double a0 = xadd(xadd(a1, a2), a3);
+        double tn;
+        uint32_t u0 = 0, u1 = 0;
+        if (a0 > 0.0) {
+            if (ev >= max_events) { capped = true; break; }
+            if (have == 0) {
+                philox4x32_10(rk, blk, id, epoch, tag, w0, w1, w2, w3);
+                blk += 1;
+                have = 2;
+                u0 = w0; u1 = w1;
+            } else {
+                u0 = w2; u1 = w3;
+            }
+            have -= 1;
+            double lg;
+            if (F32) {
+                float uf = __fmaf_rn(__uint2float_rn(u0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+                lg = (double)__fmul_rn(mufu_lg2(uf), 0.6931471805599453f);
+            } else {
+                lg = xlog(u01(u0));
+            }
+            tn = xadd(t, xdiv(-lg, a0));
+        } else {
+            tn = dinf();
+        }
+        while (g < G && xmul((double)(g + 1), dt) <= tn) {
+            const double dx = xsub(X, m.target[g]), dy = xsub(Y, m.target[G + g]);
+            acc = xadd(acc, xmul(dx, dx));
+            acc = xadd(acc, xmul(dy, dy));
+            ++g;
+        }
+        if (g >= G) break;
+        const double r = xmul(u01(u1), a0);
+        if (r < a1) X = xadd(X, 1.0);
+        else if (r < xadd(a1, a2)) { X = xsub(X, 1.0); Y = xadd(Y, 1.0); }
+        else Y = xsub(Y, 1.0);
+        t = tn;
+        ++ev;
+    }
+    events = ev;
+    ret = capped ? dinf() : xsqrt(xdiv(acc, (double)(2 * G)));
+    return ret;
+}
+
+// ------------------------------------------------------------------ deterministic costs of the reference's tests
+__device__ __forceinline__ double cost_det(const DModel &m, double th0) {
+    if (m.param[0] == 0.0) return fabs(xsub(xadd(xmul(th0, th0), 1.0), m.target[0]));
+    return fabs(xsub(th0, m.target[0]));
+}
+
+// thread-per-particle dispatch.  KIND and PREC are compile-time so each kernel holds one simulator.
+template <int KIND, int PREC, typename F>
+__device__ __forceinline__ double cost_thread(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                              uint32_t epoch, F th, long long &events) {
+    events = 0;
+    if (KIND == KABC_MODEL_NORMAL_MEANSTD)
+        return PREC == KABC_F64 ? cost_normal_f64(m, rk, tag, id, epoch, th(0), th(1))
+                                : cost_normal_f32(m, rk, tag, id, epoch, th(0), th(1));
+    if (KIND == KABC_MODEL_MA2_AUTOCOV)
+        return PREC == KABC_F64 ? cost_ma2_f64(m, rk, tag, id, epoch, th(0), th(1))
+                                : cost_ma2_f32(m, rk, tag, id, epoch, th(0), th(1));
+    if (KIND == KABC_MODEL_LV_SSA)
+        return cost_lv<PREC != KABC_F64>(m, rk, tag, id, epoch, th(0), th(1), th(2), events);
+    if (KIND == KABC_MODEL_DETERMINISTIC) return cost_det(m, th(0));
+    return dnan();
+}
+
+} // namespace kabc

@@ -1,0 +1,970 @@
+// kabc_smc.cu -- smc(prior, cost; ...) on device.  Restates src/smc.jl:92-206 of KissABC.jl 3.0.1:
+//   init                      :119-129   k_smc_init / k_smc_init_gk
+//   eps = quantile(Xs[alive]) :134       k_sel_begin + 6 x k_sel_pass  (two-rank radix select on FP64 keys, type-7 rule)
+//   alive cut, flag, ESS      :135-142   k_alive_cut
+//   cyclic-tiling resample    :145-153   k_alive_cut (decision + scan), k_resample_scatter, k_resample_gather
+//   propose                   :160-167   k_smc_propose  (+ prior-MH pre-test :172-175, builds the work list)
+//   simulate + accept         :176-189   k_smc_simulate / k_smc_simulate_gk
+//   retry / stop rules        :156-159,192-198   k_post_sweep, k_post_iter
+// Every scalar that steers control flow lives in SmcCtrl in device memory; the host only reads `stop`.
+// State is SoA FP64: th[k*N+i], X[i], lpi[i], alive[i]; two copies (ping-pong) for the resampling gather.
+#include "kabc_host.hpp"
+#include "kabc_gk.cuh"
+#include "kabc_nccl.hpp"
+
+namespace kabc {
+
+int eval_cost_device(kabc_ctx *ctx, const DModel &m, const double *d_th, long long n, uint32_t first_id, uint32_t epoch,
+                     double *d_out, long long *d_ev);
+
+constexpr int SEL_MAXBINS = 4096;
+constexpr int SCAN_THREADS = 1024;
+
+struct SmcCtrl {
+    double eps, eps_prev, xmin, gamma;
+    unsigned long long xmin_key;
+    unsigned long long sel_prefix[2];
+    long long sel_rank[2];
+    long long n_alive; // number of alive particles (input of the next quantile)
+    long long ess;     // ESS = sum(alive) right after the cut (what the reference prints)
+    unsigned long long accepted, cost_evals, events;
+    long long iteration;
+    unsigned int work_count, ticket, ticket2, epoch;
+    int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log;
+};
+
+struct SmcParams { // launch constants
+    long long N;
+    int d;
+    double alpha, mcmc_tol, epstol, r_epstol, min_r_ess, max_stretch;
+    long long mcmc_retrys;
+    int max_iterations;
+};
+
+struct SmcTrace {
+    long long *a, *b;
+    double *z, *lprob, *lpip, *xp, *thp;
+    unsigned char *dec;
+};
+
+struct SmcBufs {
+    double *th[2], *X[2], *lpi[2];
+    unsigned char *alive;
+    double *thp, *lpip;
+    unsigned int *work, *idxalive, *blockcnt, *hist;
+    SmcCtrl *ctrl;
+    kabc_smc_log_t *log;
+    long long log_cap;
+    SmcTrace tr;
+    int trace_on;
+};
+
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// ------------------------------------------------------------------ init, ref src/smc.jl:119-129
+template <int KIND, int PREC>
+__global__ void __launch_bounds__(256)
+k_smc_init(SmcBufs B, SmcParams P, DPriors pri, DModel m, RoundKeys rk, long long lo, long long hi) {
+    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const long long N = P.N;
+    Stream st(rk, ST_PRIOR, (uint32_t)i, 0u);
+    bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < P.d; ++k) {
+        double x;
+        ok &= prior1_sample(pri.p[k], st, x);
+        B.th[0][(long long)k * N + i] = x;
+    }
+    if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
+    long long ev;
+    double *thv = B.th[0];
+    double X = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, [&](int k) { return thv[(long long)k * N + i]; }, ev);
+    B.X[0][i] = X;
+    B.lpi[0][i] = prior_logpdf(pri, [&](int k) { return thv[(long long)k * N + i]; });
+    B.alive[i] = 1;
+    unsigned long long e = warp_sum_u64((unsigned long long)ev);
+    if ((threadIdx.x & 31) == 0 && e) atomicAdd(&B.ctrl->events, e);
+}
+
+__global__ void k_smc_init_prior(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi) {
+    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const long long N = P.N;
+    Stream st(rk, ST_PRIOR, (uint32_t)i, 0u);
+    bool ok = true;
+    for (int k = 0; k < P.d; ++k) {
+        double x;
+        ok &= prior1_sample(pri.p[k], st, x);
+        B.th[0][(long long)k * N + i] = x;
+    }
+    if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
+    double *thv = B.th[0];
+    B.lpi[0][i] = prior_logpdf(pri, [&](int k) { return thv[(long long)k * N + i]; });
+    B.alive[i] = 1;
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(GK_THREADS)
+k_smc_init_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, long long lo, long long hi) {
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    const long long N = P.N;
+    for (long long i = lo + blockIdx.x; i < hi; i += gridDim.x) {
+        const double *th = B.th[0];
+        double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, th[i], th[N + i], th[2 * N + i], th[3 * N + i], gk_smem);
+        if (threadIdx.x == 0) B.X[0][i] = c;
+    }
+}
+
+__global__ void k_smc_reset(SmcBufs B, SmcParams P) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int q = t; q < 2 * SEL_MAXBINS; q += gridDim.x * blockDim.x) B.hist[q] = 0;
+    if (t == 0) {
+        SmcCtrl *c = B.ctrl;
+        c->eps = dinf(); c->eps_prev = dinf(); c->xmin = 0; c->gamma = 0;
+        c->xmin_key = ~0ull;
+        c->n_alive = P.N; c->ess = P.N;
+        c->accepted = 0; c->cost_evals = (unsigned long long)P.N; c->events = 0;
+        c->iteration = 0; c->work_count = 0; c->ticket = 0; c->ticket2 = 0; c->epoch = 0;
+        c->flag = 0; c->resample = 0; c->stop = 0; c->cur = 0; c->err = 0; c->sweeps = 0; c->retry_done = 0;
+        c->resampled_log = 0;
+    }
+}
+
+// ------------------------------------------------------------------ quantile, ref src/smc.jl:134 (Statistics type 7)
+__global__ void k_sel_begin(SmcBufs B, SmcParams P) {
+    SmcCtrl *c = B.ctrl;
+    c->iteration += 1;
+    c->eps_prev = c->eps;
+    const long long n = c->n_alive;
+    if (n <= 0) { c->err = KABC_ERR_DEGENERATE; return; }
+    // aleph = n*p + (1-p); j = clamp(trunc(aleph),1,n-1); gamma = clamp(aleph-j,0,1)
+    double aleph = xadd(xmul((double)n, P.alpha), xsub(1.0, P.alpha));
+    long long j = (long long)aleph;
+    if (j > n - 1) j = n - 1;
+    if (j < 1) j = 1;
+    double g = xsub(aleph, (double)j);
+    g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+    c->gamma = g;
+    c->sel_rank[0] = (n == 1) ? 0 : j - 1; // 0-based rank of v[j]
+    c->sel_rank[1] = (n == 1) ? 0 : j;     // 0-based rank of v[j+1]
+    c->sel_prefix[0] = 0; c->sel_prefix[1] = 0;
+    c->xmin_key = ~0ull;
+    c->sweeps = 0; c->retry_done = 0; c->accepted = 0; c->resampled_log = 0;
+}
+
+template <int SHIFT, int BITS, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(512) k_sel_pass(SmcBufs B, SmcParams P) {
+    constexpr int NB = 1 << BITS;
+    __shared__ unsigned int sh[2][NB];
+    __shared__ unsigned int s_scan[512];
+    __shared__ int s_last;
+    SmcCtrl *c = B.ctrl;
+    if (c->err) return;
+    for (int q = threadIdx.x; q < 2 * NB; q += blockDim.x) (&sh[0][0])[q] = 0;
+    __syncthreads();
+    const double *X = B.X[c->cur];
+    const unsigned long long p0 = c->sel_prefix[0], p1 = c->sel_prefix[1];
+    unsigned long long kmin = ~0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += (long long)gridDim.x * blockDim.x) {
+        if (!B.alive[i]) continue;
+        unsigned long long key = dkey(X[i]);
+        unsigned int digit = (unsigned int)(key >> SHIFT) & (NB - 1);
+        if constexpr (FIRST) {
+            kmin = key < kmin ? key : kmin;
+            atomicAdd(&sh[0][digit], 1u);
+            atomicAdd(&sh[1][digit], 1u);
+        } else {
+            constexpr int HS = SHIFT + BITS; // < 64 when !FIRST
+            if ((key >> HS) == (p0 >> HS)) atomicAdd(&sh[0][digit], 1u);
+            if ((key >> HS) == (p1 >> HS)) atomicAdd(&sh[1][digit], 1u);
+        }
+    }
+    if (FIRST) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, kmin, o);
+            kmin = other < kmin ? other : kmin;
+        }
+        if ((threadIdx.x & 31) == 0 && kmin != ~0ull) atomicMin(&c->xmin_key, kmin);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < 2 * NB; q += blockDim.x) {
+        unsigned int v = (&sh[0][0])[q];
+        if (v) atomicAdd(&B.hist[(q / NB) * SEL_MAXBINS + (q % NB)], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&c->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: locate, for both ranks, the digit whose cumulative count passes the rank
+    constexpr int PER = (NB + 511) / 512;
+    for (int r = 0; r < 2; ++r) {
+        const long long rank = c->sel_rank[r];
+        unsigned int loc[PER];
+        unsigned int sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            int bin = threadIdx.x * PER + q;
+            loc[q] = bin < NB ? __ldcg(&B.hist[r * SEL_MAXBINS + bin]) : 0u;
+            sum += loc[q];
+        }
+        s_scan[threadIdx.x] = sum;
+        __syncthreads();
+        for (int o = 1; o < 512; o <<= 1) { // inclusive Hillis-Steele scan
+            unsigned int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        long long excl = (long long)s_scan[threadIdx.x] - sum;
+        if (rank >= excl && rank < excl + (long long)sum) {
+            long long cum = excl;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                if (rank >= cum && rank < cum + (long long)loc[q]) {
+                    c->sel_prefix[r] |= (unsigned long long)(threadIdx.x * PER + q) << SHIFT;
+                    c->sel_rank[r] = rank - cum;
+                }
+                cum += loc[q];
+            }
+        }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < 2 * SEL_MAXBINS; q += blockDim.x) B.hist[q] = 0;
+    if (threadIdx.x == 0) {
+        c->ticket = 0;
+        if (FIRST) c->xmin = dunkey(c->xmin_key);
+        if (LAST) {
+            const double a = dunkey(c->sel_prefix[0]), b = dunkey(c->sel_prefix[1]), g = c->gamma;
+            double eps;
+            if (dfinite(a) && dfinite(b)) eps = xadd(a, xmul(g, xsub(b, a)));
+            else eps = xadd(xmul(xsub(1.0, g), a), xmul(g, b));
+            c->eps = eps;
+            c->flag = (eps > c->xmin) ? 0 : 1; // ref :136-141
+        }
+    }
+}
+
+// ------------------------------------------------------------------ alive cut + ESS + resample decision, ref :136-147
+__global__ void __launch_bounds__(SCAN_THREADS) k_alive_cut(SmcBufs B, SmcParams P, int nblocks) {
+    __shared__ unsigned int s_w[32];
+    __shared__ int s_last;
+    SmcCtrl *c = B.ctrl;
+    if (c->err) return;
+    const double *X = B.X[c->cur];
+    const double eps = c->eps;
+    const int flag = c->flag;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int a = 0;
+    if (i < P.N) {
+        double x = X[i];
+        a = flag ? (x <= eps) : (x < eps);
+        B.alive[i] = (unsigned char)a;
+    }
+    unsigned int cnt = __syncthreads_count(a);
+    if (threadIdx.x == 0) {
+        B.blockcnt[blockIdx.x] = cnt;
+        __threadfence();
+        s_last = (atomicAdd(&c->ticket2, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: exclusive scan of the per-block counts (in place), total = ESS
+    unsigned long long carry = 0;
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        int q = base + threadIdx.x;
+        unsigned int v = q < nblocks ? __ldcg(&B.blockcnt[q]) : 0u;
+        unsigned int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = s_w[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            s_w[threadIdx.x] = wi - w; // exclusive warp offsets
+        }
+        __syncthreads();
+        unsigned int excl = incl - v + s_w[threadIdx.x >> 5];
+        if (q < nblocks) B.blockcnt[q] = (unsigned int)(carry + excl);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_w[0] = excl + v;
+        __syncthreads();
+        carry += s_w[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long ess = (long long)carry;
+        c->ess = ess;
+        c->n_alive = ess;
+        c->ticket2 = 0;
+        // ref :145  alpha*ESS <= nparticles*min_r_ess, FP64, exactly these operands
+        c->resample = xmul(P.alpha, (double)ess) <= xmul((double)P.N, P.min_r_ess);
+        if (c->resample && ess == 0) c->err = KABC_ERR_DEGENERATE;
+    }
+}
+
+// idxalive = (1:N)[alive], ref :146
+__global__ void __launch_bounds__(SCAN_THREADS) k_resample_scatter(SmcBufs B, SmcParams P) {
+    __shared__ unsigned int s_w[32];
+    SmcCtrl *c = B.ctrl;
+    if (c->err || !c->resample) return;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int a = (i < P.N) ? B.alive[i] : 0u;
+    unsigned int ball = __ballot_sync(0xffffffffu, a);
+    unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_w[warp] = __popc(ball);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned int w = s_w[threadIdx.x], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= o) wi += t;
+        }
+        s_w[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    if (a) {
+        unsigned int pos = B.blockcnt[blockIdx.x] + s_w[warp] + __popc(ball & ((1u << lane) - 1u));
+        B.idxalive[pos] = (unsigned int)i;
+    }
+}
+
+// theta, X, lpi = (...)[idx], idx[k] = idxalive[k mod n_alive]; alive .= true.  ref :147-152
+__global__ void __launch_bounds__(256) k_resample_gather(SmcBufs B, SmcParams P) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err || !c->resample) return;
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.N) return;
+    const int cur = c->cur;
+    const unsigned long long n = (unsigned long long)c->ess;
+    const unsigned int src = B.idxalive[(unsigned long long)k % n];
+    const long long N = P.N;
+    for (int q = 0; q < P.d; ++q) B.th[cur ^ 1][(long long)q * N + k] = B.th[cur][(long long)q * N + src];
+    B.X[cur ^ 1][k] = B.X[cur][src];
+    B.lpi[cur ^ 1][k] = B.lpi[cur][src];
+    B.alive[k] = 1;
+}
+
+// single thread between phases: commits the resample (buffer flip) and opens a sweep
+__global__ void k_pre_sweep(SmcBufs B, SmcParams P) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err) return;
+    if (c->resample) {
+        c->cur ^= 1;
+        c->n_alive = P.N;
+        c->resample = 0;
+        c->resampled_log = 1;
+    }
+    c->work_count = 0;
+}
+
+// ------------------------------------------------------------------ propose, ref :160-167 and :172-175
+__global__ void __launch_bounds__(256)
+k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err || c->retry_done) return;
+    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long N = P.N;
+    const double *th = B.th[c->cur];
+    const double *lpi = B.lpi[c->cur];
+    const uint32_t epoch = c->epoch;
+    bool push = false;
+    int dec = 0;
+    long long a = -1, b = -1;
+    double z = dnan(), lprob = dnan(), lpip = dnan();
+    if (i < hi && B.alive[i]) {
+        Stream st(rk, ST_PROPOSE, (uint32_t)i, epoch);
+        a = i; b = i;
+        while (a == i) a = (long long)index_of(st.next(), (uint32_t)N);
+        while (b == i || b == a) b = (long long)index_of(st.next(), (uint32_t)N);
+        z = next_normal(st);
+        const double sc = xdiv(xmul(P.max_stretch, z), xsqrt((double)P.d));
+        for (int k = 0; k < P.d; ++k) {
+            const double *t = th + (long long)k * N;
+            B.thp[(long long)k * N + i] = xadd(t[i], xmul(xsub(t[b], t[a]), sc));
+        }
+        lprob = xlog(next_uniform(st));
+        const double *thp = B.thp;
+        lpip = prior_logpdf(pri, [&](int k) { return thp[(long long)k * N + i]; });
+        if (lpip < 0.0 && !dfinite(lpip)) dec = 1;
+        else {
+            const double lM = fmin(xadd(xsub(lpip, lpi[i]), 0.0), 0.0);
+            if (!(lprob < lM)) dec = 2;
+            else { push = true; B.lpip[i] = lpip; }
+        }
+    }
+    // warp-aggregated append to the work list
+    unsigned int ball = __ballot_sync(0xffffffffu, push);
+    unsigned int lane = threadIdx.x & 31, base = 0;
+    if (ball) {
+        if (lane == 0) base = atomicAdd(&c->work_count, (unsigned int)__popc(ball));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) B.work[base + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
+    }
+    if (B.trace_on && i < hi) {
+        B.tr.a[i] = a; B.tr.b[i] = b; B.tr.z[i] = z; B.tr.lprob[i] = lprob; B.tr.lpip[i] = lpip;
+        B.tr.dec[i] = (unsigned char)dec; B.tr.xp[i] = dnan();
+        if (!B.alive[i]) for (int k = 0; k < P.d; ++k) B.thp[(long long)k * N + i] = dnan();
+    }
+}
+
+// ------------------------------------------------------------------ simulate + accept, ref :176-189
+__device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCtrl *c, long long i, double Xp,
+                                           unsigned int &acc) {
+    const long long N = P.N;
+    const int cur = c->cur;
+    const bool reject = c->flag ? (Xp > c->eps) : (Xp >= c->eps);
+    if (!reject) {
+        for (int k = 0; k < P.d; ++k) B.th[cur][(long long)k * N + i] = B.thp[(long long)k * N + i];
+        B.X[cur][i] = Xp;
+        B.lpi[cur][i] = B.lpip[i];
+        acc = 1;
+    }
+    if (B.trace_on) { B.tr.xp[i] = Xp; B.tr.dec[i] = reject ? 3 : 4; }
+}
+
+template <int KIND, int PREC>
+__global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DModel m, RoundKeys rk) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err || c->retry_done) return;
+    const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nwork = c->work_count;
+    if ((w & ~31u) >= nwork) return; // whole warp idle
+    unsigned int acc = 0;
+    long long ev = 0;
+    if (w < nwork) {
+        const long long i = B.work[w];
+        const long long N = P.N;
+        const double *thp = B.thp;
+        double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, [&](int k) { return thp[(long long)k * N + i]; }, ev);
+        smc_accept(B, P, c, i, Xp, acc);
+    }
+    unsigned int nacc = __popc(__ballot_sync(0xffffffffu, acc));
+    unsigned long long e = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
+    if ((threadIdx.x & 31) == 0) {
+        if (nacc) atomicAdd(&c->accepted, (unsigned long long)nacc);
+        if (e) atomicAdd(&c->events, e);
+    }
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk) {
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    SmcCtrl *c = B.ctrl;
+    if (c->err || c->retry_done) return;
+    const unsigned int nwork = c->work_count;
+    const long long N = P.N;
+    for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const long long i = B.work[w];
+        const double *thp = B.thp;
+        double Xp = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, thp[i], thp[N + i], thp[2 * N + i], thp[3 * N + i], gk_smem);
+        if (threadIdx.x == 0) {
+            unsigned int acc = 0;
+            smc_accept(B, P, c, i, Xp, acc);
+            if (acc) atomicAdd(&c->accepted, 1ull);
+        }
+    }
+}
+
+// closes a sweep, ref :192 (`accepted >= mcmc_tol*nparticles && break`)
+__global__ void k_post_sweep(SmcBufs B, SmcParams P) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err || c->retry_done) return;
+    c->cost_evals += c->work_count;
+    c->sweeps += 1;
+    c->epoch += 1;
+    if ((double)c->accepted >= xmul(P.mcmc_tol, (double)P.N)) c->retry_done = 1;
+}
+
+// closes an iteration, ref :194-198
+__global__ void k_post_iter(SmcBufs B, SmcParams P) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err) { c->stop = -1; return; }
+    const double eps = c->eps, epsv = c->eps_prev;
+    int stop = 0;
+    if (xmul(2.0, fabs(xsub(epsv, eps))) < xmul(P.r_epstol, xadd(fabs(epsv), fabs(eps)))) stop = 1;
+    else if (eps <= P.epstol) stop = 2;
+    else if ((double)c->accepted < xmul(P.mcmc_tol, (double)P.N)) stop = 3;
+    else if (P.max_iterations > 0 && c->iteration >= P.max_iterations) stop = 4;
+    c->stop = stop;
+    const long long it = c->iteration;
+    if (it >= 1 && it <= B.log_cap) {
+        kabc_smc_log_t &L = B.log[it - 1];
+        L.iteration = it; L.eps = eps; L.n_alive = c->ess; L.flag = c->flag; L.resampled = c->resampled_log;
+        L.accepted = (long long)c->accepted; L.cost_evals = (long long)c->cost_evals; L.sweeps = c->sweeps;
+    }
+}
+
+} // namespace kabc
+
+using namespace kabc;
+
+// =================================================================== host side
+struct kabc_smc {
+    kabc_ctx *ctx = nullptr;
+    DPriors pri;
+    DModel model;
+    SmcParams P;
+    kabc_smc_config_t cfg;
+    SmcBufs B;
+    DevBuf<double> th0, th1, X0, X1, lpi0, lpi1, thp, lpip;
+    DevBuf<unsigned char> alive;
+    DevBuf<unsigned int> work, idxalive, blockcnt, hist;
+    DevBuf<SmcCtrl> ctrl;
+    DevBuf<kabc_smc_log_t> log;
+    // trace
+    DevBuf<long long> ta, tb;
+    DevBuf<double> tz, tlprob, tlpip, txp;
+    DevBuf<unsigned char> tdec;
+    SmcCtrl *h_ctrl = nullptr; // pinned
+    long long lo = 0, hi = 0;  // owned particle range [lo,hi) of this rank
+    bool inited = false;
+    long long launches = 0;
+    int nblocks_scan = 0;
+};
+
+static int smc_check_cfg(const kabc_smc_config_t *cfg, int d) {
+    // ref src/smc.jl:107-118, same order
+    if (!(cfg->min_r_ess > 0)) return set_error(KABC_ERR_INVALID_ARG, "min_r_ess must be > 0.");
+    if (!(cfg->mcmc_retrys >= 0)) return set_error(KABC_ERR_INVALID_ARG, "mcmc_retrys must be >= 0.");
+    if (!(cfg->alpha > 0)) return set_error(KABC_ERR_INVALID_ARG, "alpha must be > 0.");
+    if (!(cfg->r_epstol >= 0)) return set_error(KABC_ERR_INVALID_ARG, "r_epstol must be >= 0");
+    if (!(cfg->mcmc_tol >= 0)) return set_error(KABC_ERR_INVALID_ARG, "mcmc_tol must be >= 0");
+    if (!(cfg->max_stretch > 1)) return set_error(KABC_ERR_INVALID_ARG, "max_stretch must be > 1");
+    double mn = cfg->alpha < cfg->min_r_ess ? cfg->alpha : cfg->min_r_ess;
+    long long min_np = (long long)ceil(3.0 * (double)d / mn);
+    if (cfg->nparticles < min_np) return set_error(KABC_ERR_INVALID_ARG, "nparticles must be >= %lld.", min_np);
+    if (cfg->nparticles > 0xFFFFFFFFll) return set_error(KABC_ERR_INVALID_ARG, "nparticles must be < 2^32");
+    return KABC_OK;
+}
+
+#define SMC_LAUNCHED(s) do { (s)->launches += 1; (s)->ctx->launches += 1; } while (0)
+
+template <int KIND>
+static void smc_launch_init_t(kabc_smc *s) {
+    const long long n = s->hi - s->lo;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (s->model.precision == KABC_F64)
+        k_smc_init<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk, s->lo, s->hi);
+    else
+        k_smc_init<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk, s->lo, s->hi);
+    SMC_LAUNCHED(s);
+}
+
+template <int KIND>
+static void smc_launch_sim_t(kabc_smc *s) {
+    const long long n = s->hi - s->lo;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (s->model.precision == KABC_F64)
+        k_smc_simulate<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk);
+    else
+        k_smc_simulate<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk);
+    SMC_LAUNCHED(s);
+}
+
+static int smc_gk_grid(kabc_smc *s, size_t &smem) {
+    smem = gk_smem_bytes(s->model.n_draws, s->model.precision);
+    long long cap = (long long)s->ctx->sm_count * gk_blocks_per_sm(s->model.n_draws, s->model.precision);
+    long long n = s->hi - s->lo;
+    return (int)(n < cap ? n : cap);
+}
+
+// all-gather of the ranks' shards of the current state (multi-GPU only): theta planes, X, lpi
+static int smc_allgather_state(kabc_smc *s, int cur) {
+    kabc_ctx *ctx = s->ctx;
+    if (ctx->world == 1) return KABC_OK;
+    const long long N = s->P.N, per = N / ctx->world;
+    if (int rc = nccl_group_start()) return rc;
+    for (int k = 0; k < s->P.d; ++k)
+        if (int rc = nccl_allgather_inplace(ctx, s->B.th[cur] + (long long)k * N, (size_t)per * 8)) return rc;
+    if (int rc = nccl_allgather_inplace(ctx, s->B.X[cur], (size_t)per * 8)) return rc;
+    if (int rc = nccl_allgather_inplace(ctx, s->B.lpi[cur], (size_t)per * 8)) return rc;
+    if (int rc = nccl_group_end()) return rc;
+    return KABC_OK;
+}
+
+static int smc_enqueue_init(kabc_smc *s) {
+    kabc_ctx *ctx = s->ctx;
+    k_smc_reset<<<8, 1024, 0, ctx->stream>>>(s->B, s->P);
+    SMC_LAUNCHED(s);
+    switch (s->model.kind) {
+    case KABC_MODEL_NORMAL_MEANSTD: smc_launch_init_t<KABC_MODEL_NORMAL_MEANSTD>(s); break;
+    case KABC_MODEL_MA2_AUTOCOV: smc_launch_init_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
+    case KABC_MODEL_LV_SSA: smc_launch_init_t<KABC_MODEL_LV_SSA>(s); break;
+    case KABC_MODEL_DETERMINISTIC: smc_launch_init_t<KABC_MODEL_DETERMINISTIC>(s); break;
+    case KABC_MODEL_GK_OCTILE: {
+        const long long n = s->hi - s->lo;
+        k_smc_init_prior<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
+        SMC_LAUNCHED(s);
+        size_t smem;
+        int grid = smc_gk_grid(s, smem);
+        if (s->model.precision == KABC_F64) {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_init_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_smc_init_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, s->lo, s->hi);
+        } else {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_init_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_smc_init_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, s->lo, s->hi);
+        }
+        SMC_LAUNCHED(s);
+        break;
+    }
+    }
+    KABC_CUDA_TRY(cudaGetLastError());
+    if (ctx->world > 1) {
+        if (int rc = smc_allgather_state(s, 0)) return rc;
+        KABC_CUDA_TRY(cudaMemsetAsync(s->B.alive, 1, (size_t)s->P.N, ctx->stream));
+        // events were counted per rank
+        if (int rc = nccl_allreduce_sum_u64(ctx, &s->B.ctrl->events, 1)) return rc;
+    }
+    return KABC_OK;
+}
+
+// one MCMC sweep: propose -> (work list) -> simulate+accept -> bookkeeping
+static int smc_enqueue_sweep(kabc_smc *s) {
+    kabc_ctx *ctx = s->ctx;
+    const long long n = s->hi - s->lo;
+    k_pre_sweep<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
+    SMC_LAUNCHED(s);
+    k_smc_propose<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
+    SMC_LAUNCHED(s);
+    switch (s->model.kind) {
+    case KABC_MODEL_NORMAL_MEANSTD: smc_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s); break;
+    case KABC_MODEL_MA2_AUTOCOV: smc_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
+    case KABC_MODEL_LV_SSA: smc_launch_sim_t<KABC_MODEL_LV_SSA>(s); break;
+    case KABC_MODEL_DETERMINISTIC: smc_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s); break;
+    case KABC_MODEL_GK_OCTILE: {
+        size_t smem;
+        int grid = smc_gk_grid(s, smem);
+        if (s->model.precision == KABC_F64) {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_smc_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
+        } else {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_smc_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
+        }
+        SMC_LAUNCHED(s);
+        break;
+    }
+    }
+    if (ctx->world > 1) {
+        // the sweep only touched this rank's shard of the current buffers; `cur` is known on the host
+        // only through ctrl, so gather both candidates' current one: cur is mirrored in s->h_cur
+        return set_error(KABC_ERR_STATE, "internal: multi-GPU sweep must go through smc_enqueue_sweep_dist");
+    }
+    k_post_sweep<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
+    SMC_LAUNCHED(s);
+    KABC_CUDA_TRY(cudaGetLastError());
+    return KABC_OK;
+}
+
+static int smc_enqueue_cut(kabc_smc *s) {
+    kabc_ctx *ctx = s->ctx;
+    const long long N = s->P.N;
+    int sel_blocks = (int)((N + 512 * 8 - 1) / (512 * 8));
+    if (sel_blocks > ctx->sm_count * 2) sel_blocks = ctx->sm_count * 2;
+    if (sel_blocks < 1) sel_blocks = 1;
+    k_sel_begin<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_pass<52, 12, true, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_pass<41, 11, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_pass<30, 11, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_pass<20, 10, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_pass<10, 10, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_pass<0, 10, false, true><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
+    k_alive_cut<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P, s->nblocks_scan);
+    k_resample_scatter<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    k_resample_gather<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P);
+    s->launches += 10;
+    ctx->launches += 10;
+    KABC_CUDA_TRY(cudaGetLastError());
+    return KABC_OK;
+}
+
+static int smc_read_ctrl(kabc_smc *s) {
+    KABC_CUDA_TRY(cudaMemcpyAsync(s->h_ctrl, s->B.ctrl, sizeof(SmcCtrl), cudaMemcpyDeviceToHost, s->ctx->stream));
+    KABC_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    return KABC_OK;
+}
+
+static int smc_ctrl_error(kabc_smc *s) {
+    switch (s->h_ctrl->err) {
+    case 0: return KABC_OK;
+    case KABC_ERR_DEGENERATE: return set_error(KABC_ERR_DEGENERATE, "no alive particles left (ESS = 0): cannot resample");
+    default: return set_error(s->h_ctrl->err, "prior sampling failed (truncation too extreme)");
+    }
+}
+
+// one body of the reference's `while true` loop
+static int smc_enqueue_iteration(kabc_smc *s, bool sync_retries) {
+    if (int rc = smc_enqueue_cut(s)) return rc;
+    const long long retry_n = 1 + s->P.mcmc_retrys;
+    for (long long r = 0; r < retry_n; ++r) {
+        if (int rc = smc_enqueue_sweep(s)) return rc;
+        if (sync_retries && r + 1 < retry_n) {
+            // ref :192 -- leave the retry loop as soon as enough moves were accepted
+            if (int rc = smc_read_ctrl(s)) return rc;
+            if (s->h_ctrl->err || s->h_ctrl->retry_done) break;
+        }
+    }
+    k_post_iter<<<1, 1, 0, s->ctx->stream>>>(s->B, s->P);
+    SMC_LAUNCHED(s);
+    KABC_CUDA_TRY(cudaGetLastError());
+    return KABC_OK;
+}
+
+extern "C" {
+
+int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model,
+                    const kabc_smc_config_t *cfg, kabc_smc_t **out) {
+    if (!ctx || !cfg || !out) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
+    DPriors pri;
+    DModel m;
+    if (int rc = ingest_priors(prior, d, pri)) return rc;
+    if (int rc = smc_check_cfg(cfg, d)) return rc;
+    if (int rc = ingest_model(model, d, m)) return rc;
+    const long long N = cfg->nparticles;
+    if (ctx->world > 1 && N % ctx->world) return set_error(KABC_ERR_INVALID_ARG, "nparticles must be a multiple of the number of ranks");
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    kabc_smc *s = new kabc_smc();
+    s->ctx = ctx; s->pri = pri; s->model = m; s->cfg = *cfg;
+    s->P.N = N; s->P.d = d; s->P.alpha = cfg->alpha; s->P.mcmc_tol = cfg->mcmc_tol; s->P.epstol = cfg->epstol;
+    s->P.r_epstol = cfg->r_epstol; s->P.min_r_ess = cfg->min_r_ess; s->P.max_stretch = cfg->max_stretch;
+    s->P.mcmc_retrys = cfg->mcmc_retrys; s->P.max_iterations = cfg->max_iterations;
+    s->lo = N / ctx->world * ctx->rank;
+    s->hi = N / ctx->world * (ctx->rank + 1);
+    s->nblocks_scan = (int)((N + SCAN_THREADS - 1) / SCAN_THREADS);
+    const size_t nd = (size_t)N * d;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(s->th0.alloc(nd)); A(s->th1.alloc(nd)); A(s->thp.alloc(nd));
+    A(s->X0.alloc(N)); A(s->X1.alloc(N)); A(s->lpi0.alloc(N)); A(s->lpi1.alloc(N)); A(s->lpip.alloc(N));
+    A(s->alive.alloc(N)); A(s->work.alloc(N)); A(s->idxalive.alloc(N)); A(s->blockcnt.alloc(s->nblocks_scan));
+    A(s->hist.alloc(2 * SEL_MAXBINS)); A(s->ctrl.alloc(1));
+    const long long log_cap = 1 << 16;
+    A(s->log.alloc(log_cap));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_ctrl, sizeof(SmcCtrl));
+    if (e != cudaSuccess) {
+        delete s;
+        return set_error(KABC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    memset(s->h_ctrl, 0, sizeof(SmcCtrl));
+    s->B.th[0] = s->th0.p; s->B.th[1] = s->th1.p; s->B.X[0] = s->X0.p; s->B.X[1] = s->X1.p;
+    s->B.lpi[0] = s->lpi0.p; s->B.lpi[1] = s->lpi1.p; s->B.alive = s->alive.p; s->B.thp = s->thp.p;
+    s->B.lpip = s->lpip.p; s->B.work = s->work.p; s->B.idxalive = s->idxalive.p; s->B.blockcnt = s->blockcnt.p;
+    s->B.hist = s->hist.p; s->B.ctrl = s->ctrl.p; s->B.log = s->log.p; s->B.log_cap = log_cap;
+    memset(&s->B.tr, 0, sizeof s->B.tr);
+    s->B.trace_on = 0;
+    KABC_CUDA_TRY(cudaMemsetAsync(s->ctrl.p, 0, sizeof(SmcCtrl), ctx->stream));
+    *out = s;
+    return KABC_OK;
+}
+
+int kabc_smc_destroy(kabc_smc_t *s) {
+    if (!s) return KABC_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    delete s;
+    return KABC_OK;
+}
+
+int kabc_smc_init(kabc_smc_t *s) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (s->ctx->world > 1) return set_error(KABC_ERR_STATE, "multi-rank smc is not wired in this build step");
+    if (int rc = smc_enqueue_init(s)) return rc;
+    if (int rc = smc_read_ctrl(s)) return rc;
+    if (int rc = smc_ctrl_error(s)) return rc;
+    s->inited = true;
+    return KABC_OK;
+}
+
+int kabc_smc_iterate(kabc_smc_t *s, int *stop) {
+    if (!s || !stop) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
+    if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_smc_init must be called first");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (int rc = smc_enqueue_iteration(s, true)) return rc;
+    if (int rc = smc_read_ctrl(s)) return rc;
+    if (int rc = smc_ctrl_error(s)) return rc;
+    *stop = s->h_ctrl->stop;
+    return KABC_OK;
+}
+
+int kabc_smc_iterate_n(kabc_smc_t *s, int n, int ignore_stop, int *done, float *out_ms) {
+    if (!s || n < 0) return set_error(KABC_ERR_INVALID_ARG, "bad argument");
+    if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_smc_init must be called first");
+    kabc_ctx *ctx = s->ctx;
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    KABC_CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    int it = 0;
+    for (; it < n; ++it) {
+        if (int rc = smc_enqueue_iteration(s, !ignore_stop)) return rc;
+        if (!ignore_stop) {
+            if (int rc = smc_read_ctrl(s)) return rc;
+            if (int rc = smc_ctrl_error(s)) return rc;
+            if (s->h_ctrl->stop) { ++it; break; }
+        }
+    }
+    KABC_CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (int rc = smc_read_ctrl(s)) return rc;
+    if (int rc = smc_ctrl_error(s)) return rc;
+    if (done) *done = it;
+    if (out_ms) KABC_CUDA_TRY(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+    return KABC_OK;
+}
+
+int kabc_smc_get_state(kabc_smc_t *s, double *theta, double *X, double *lpi, uint8_t *alive) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (int rc = smc_read_ctrl(s)) return rc;
+    const int cur = s->h_ctrl->cur;
+    const size_t N = (size_t)s->P.N;
+    cudaStream_t st = s->ctx->stream;
+    if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(theta, s->B.th[cur], 8 * N * s->P.d, cudaMemcpyDeviceToHost, st));
+    if (X) KABC_CUDA_TRY(cudaMemcpyAsync(X, s->B.X[cur], 8 * N, cudaMemcpyDeviceToHost, st));
+    if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(lpi, s->B.lpi[cur], 8 * N, cudaMemcpyDeviceToHost, st));
+    if (alive) KABC_CUDA_TRY(cudaMemcpyAsync(alive, s->B.alive, N, cudaMemcpyDeviceToHost, st));
+    KABC_CUDA_TRY(cudaStreamSynchronize(st));
+    return KABC_OK;
+}
+
+__global__ void k_count_alive(SmcBufs B, long long N) {
+    __shared__ unsigned long long s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    unsigned long long n = 0;
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) n += B.alive[i];
+    n = warp_sum_u64(n);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0) { B.ctrl->n_alive = (long long)s_n; B.ctrl->ess = (long long)s_n; }
+}
+
+int kabc_smc_set_state(kabc_smc_t *s, const double *theta, const double *X, const double *lpi, const uint8_t *alive) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (int rc = smc_read_ctrl(s)) return rc;
+    const int cur = s->h_ctrl->cur;
+    const size_t N = (size_t)s->P.N;
+    cudaStream_t st = s->ctx->stream;
+    if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.th[cur], theta, 8 * N * s->P.d, cudaMemcpyHostToDevice, st));
+    if (X) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.X[cur], X, 8 * N, cudaMemcpyHostToDevice, st));
+    if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.lpi[cur], lpi, 8 * N, cudaMemcpyHostToDevice, st));
+    if (alive) {
+        KABC_CUDA_TRY(cudaMemcpyAsync(s->B.alive, alive, N, cudaMemcpyHostToDevice, st));
+        k_count_alive<<<1, 1024, 0, st>>>(s->B, s->P.N);
+        SMC_LAUNCHED(s);
+    }
+    KABC_CUDA_TRY(cudaStreamSynchronize(st));
+    return KABC_OK;
+}
+
+int kabc_smc_get_scalars(kabc_smc_t *s, double *eps, int32_t *flag, int64_t *iteration, int64_t *n_alive,
+                         int64_t *accepted, int64_t *cost_evals, int64_t *next_epoch, int64_t *events) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (int rc = smc_read_ctrl(s)) return rc;
+    const SmcCtrl *c = s->h_ctrl;
+    if (eps) *eps = c->eps;
+    if (flag) *flag = c->flag;
+    if (iteration) *iteration = c->iteration;
+    if (n_alive) *n_alive = c->n_alive;
+    if (accepted) *accepted = (int64_t)c->accepted;
+    if (cost_evals) *cost_evals = (int64_t)c->cost_evals;
+    if (next_epoch) *next_epoch = c->epoch;
+    if (events) *events = (int64_t)c->events;
+    return KABC_OK;
+}
+
+int64_t kabc_smc_get_log(kabc_smc_t *s, kabc_smc_log_t *log, int64_t cap) {
+    if (!s) return -1;
+    cudaSetDevice(s->ctx->device);
+    if (smc_read_ctrl(s)) return -1;
+    int64_t n = s->h_ctrl->iteration;
+    if (n > s->B.log_cap) n = s->B.log_cap;
+    int64_t m = n < cap ? n : cap;
+    if (log && m > 0) {
+        if (cudaMemcpyAsync(log, s->B.log, sizeof(kabc_smc_log_t) * (size_t)m, cudaMemcpyDeviceToHost, s->ctx->stream) != cudaSuccess) return -1;
+        cudaStreamSynchronize(s->ctx->stream);
+    }
+    return n;
+}
+
+int64_t kabc_smc_kernel_launches(kabc_smc_t *s) { return s ? s->launches : -1; }
+
+int kabc_smc_trace_enable(kabc_smc_t *s, int on) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    KABC_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    if (on && !s->ta.p) {
+        const size_t N = (size_t)s->P.N;
+        KABC_CUDA_TRY(s->ta.alloc(N)); KABC_CUDA_TRY(s->tb.alloc(N)); KABC_CUDA_TRY(s->tz.alloc(N));
+        KABC_CUDA_TRY(s->tlprob.alloc(N)); KABC_CUDA_TRY(s->tlpip.alloc(N)); KABC_CUDA_TRY(s->txp.alloc(N));
+        KABC_CUDA_TRY(s->tdec.alloc(N));
+        s->B.tr.a = s->ta.p; s->B.tr.b = s->tb.p; s->B.tr.z = s->tz.p; s->B.tr.lprob = s->tlprob.p;
+        s->B.tr.lpip = s->tlpip.p; s->B.tr.xp = s->txp.p; s->B.tr.dec = s->tdec.p; s->B.tr.thp = s->thp.p;
+    }
+    s->B.trace_on = on ? 1 : 0;
+    return KABC_OK;
+}
+
+int kabc_smc_get_trace(kabc_smc_t *s, int64_t *a, int64_t *b, double *z, double *lprob, double *lpi_p, double *xp,
+                       uint8_t *decision, double *theta_p) {
+    if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
+    if (!s->ta.p) return set_error(KABC_ERR_STATE, "trace was never enabled");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    const size_t N = (size_t)s->P.N;
+    cudaStream_t st = s->ctx->stream;
+    if (a) KABC_CUDA_TRY(cudaMemcpyAsync(a, s->ta.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (b) KABC_CUDA_TRY(cudaMemcpyAsync(b, s->tb.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (z) KABC_CUDA_TRY(cudaMemcpyAsync(z, s->tz.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (lprob) KABC_CUDA_TRY(cudaMemcpyAsync(lprob, s->tlprob.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (lpi_p) KABC_CUDA_TRY(cudaMemcpyAsync(lpi_p, s->tlpip.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (xp) KABC_CUDA_TRY(cudaMemcpyAsync(xp, s->txp.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (decision) KABC_CUDA_TRY(cudaMemcpyAsync(decision, s->tdec.p, N, cudaMemcpyDeviceToHost, st));
+    if (theta_p) KABC_CUDA_TRY(cudaMemcpyAsync(theta_p, s->thp.p, 8 * N * s->P.d, cudaMemcpyDeviceToHost, st));
+    KABC_CUDA_TRY(cudaStreamSynchronize(st));
+    return KABC_OK;
+}
+
+int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model,
+                 const kabc_smc_config_t *cfg, double *out_theta, uint8_t *out_alive, double *out_cost, double *out_eps,
+                 int64_t *out_iterations, int64_t *out_cost_evals, kabc_smc_log_t *log, int64_t log_cap) {
+    kabc_smc *s = nullptr;
+    if (int rc = kabc_smc_create(ctx, prior, d, model, cfg, &s)) return rc;
+    int rc = kabc_smc_init(s);
+    int stop = 0;
+    while (!rc && !stop) rc = kabc_smc_iterate(s, &stop);
+    if (!rc) rc = kabc_smc_get_state(s, out_theta, out_cost, nullptr, out_alive);
+    if (!rc) {
+        if (out_eps) *out_eps = s->h_ctrl->eps;
+        if (out_iterations) *out_iterations = s->h_ctrl->iteration;
+        if (out_cost_evals) *out_cost_evals = (int64_t)s->h_ctrl->cost_evals;
+        if (log && log_cap > 0 && kabc_smc_get_log(s, log, log_cap) < 0) rc = set_error(KABC_ERR_CUDA, "log copy failed");
+    }
+    std::string keep = g_last_error;
+    kabc_smc_destroy(s);
+    g_last_error = keep;
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,1052 @@
+/*
+ * kabc_oracle.c -- CPU ORACLE (test infrastructure, not product).  See kabc_oracle.h.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
+ * -ffp-contract=off matters: every fused multiply-add below is an explicit fma()
+ * so the arithmetic is a fixed sequence of correctly rounded IEEE-754 double
+ * operations that the device F64 path reproduces bit for bit.
+ *
+ * Citations "ref:" are into /root/reference (KissABC.jl 3.0.1).
+ */
+#include "kabc_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static __thread char g_err[256];
+const char *kor_last_error(void) { return g_err; }
+static int fail(const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return 1;
+}
+
+/* ------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al., SC'11): counter-based RNG             */
+/* ------------------------------------------------------------------ */
+void kor_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* stream = (seed ; block j, id, epoch, stream-tag); words are consumed in order */
+enum { ST_PRIOR = 1, ST_PROPOSE = 2, ST_COST = 3, ST_ACCEPT = 4, ST_COST_INIT = 5 };
+typedef struct {
+    uint32_t key[2], ctr[4], buf[4];
+    int pos;
+} stream_t;
+
+static void stream_init(stream_t *s, uint64_t seed, uint32_t tag, uint32_t id, uint32_t epoch) {
+    s->key[0] = (uint32_t)seed;
+    s->key[1] = (uint32_t)(seed >> 32);
+    s->ctr[0] = 0; s->ctr[1] = id; s->ctr[2] = epoch; s->ctr[3] = tag;
+    s->pos = 4;
+}
+static uint32_t next_u32(stream_t *s) {
+    if (s->pos == 4) {
+        kor_philox4x32_10(s->ctr, s->key, s->buf);
+        s->ctr[0] += 1;
+        s->pos = 0;
+    }
+    return s->buf[s->pos++];
+}
+uint32_t kor_stream_word(uint64_t seed, uint32_t tag, uint32_t id, uint32_t epoch, uint32_t k) {
+    stream_t s;
+    stream_init(&s, seed, tag, id, epoch);
+    s.ctr[0] = k / 4;
+    uint32_t w = 0;
+    for (uint32_t j = 0; j <= k % 4; ++j) w = next_u32(&s);
+    return w;
+}
+
+/* ------------------------------------------------------------------ */
+/* exactly reproducible elementary functions (DESIGN.md "Variate spec") */
+/* only +,-,*,/,sqrt,floor and explicit fma: same bits on CPU and GPU   */
+/* ------------------------------------------------------------------ */
+static inline uint64_t d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
+static inline double u2d(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
+
+double kor_log(double x) {
+    if (x != x) return x;
+    if (x < 0.0) return NAN;
+    if (x == 0.0) return -INFINITY;
+    if (x == INFINITY) return x;
+    int e = 0;
+    uint64_t b = d2u(x);
+    if ((b >> 52) == 0) { /* subnormal: scale by 2^54 */
+        x = x * 18014398509481984.0;
+        b = d2u(x);
+        e = -54;
+    }
+    e += (int)(b >> 52) - 1023;
+    double m = u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double s2 = s * s;
+    /* log(m) = 2 atanh(s) = 2s + 2 s^3 (1/3 + s2/5 + ... + s2^10/23) */
+    double p = 1.0 / 23.0;
+    p = fma(p, s2, 1.0 / 21.0);
+    p = fma(p, s2, 1.0 / 19.0);
+    p = fma(p, s2, 1.0 / 17.0);
+    p = fma(p, s2, 1.0 / 15.0);
+    p = fma(p, s2, 1.0 / 13.0);
+    p = fma(p, s2, 1.0 / 11.0);
+    p = fma(p, s2, 1.0 / 9.0);
+    p = fma(p, s2, 1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0);
+    p = fma(p, s2, 1.0 / 3.0);
+    double t = (s * s2) * p;
+    double r = 2.0 * s + 2.0 * t;
+    double ef = (double)e;
+    /* ln2 split: hi has 21 trailing zero bits so ef*hi is exact */
+    return ef * 6.93147180369123816490e-01 + (r + ef * 1.90821492927058770002e-10);
+}
+
+double kor_exp(double x) {
+    if (x != x) return x;
+    if (x > 709.78) return INFINITY;
+    if (x < -745.2) return 0.0;
+    double k = floor(x * 1.4426950408889634 + 0.5);
+    double r = fma(-k, 6.93147180369123816490e-01, x);
+    r = fma(-k, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 87178291200.0; /* 1/14! */
+    p = fma(p, r, 1.0 / 6227020800.0);
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    int ki = (int)k;
+    /* 2^ki in two exact factors so results stay finite/normal whenever representable */
+    int k1 = ki / 2, k2 = ki - k1;
+    double f1 = u2d((uint64_t)(k1 + 1023) << 52);
+    double f2 = u2d((uint64_t)(k2 + 1023) << 52);
+    return (p * f1) * f2;
+}
+
+void kor_sincos2pi(double u, double *sn, double *cs) {
+    double q = floor(4.0 * u + 0.5);
+    double t = u - 0.25 * q; /* exact for the u grid we use */
+    double phi = t * 6.283185307179586;
+    double p2 = phi * phi;
+    double ps = -1.0 / 121645100408832000.0; /* -1/19! */
+    ps = fma(ps, p2, 1.0 / 355687428096000.0); /* 1/17! */
+    ps = fma(ps, p2, -1.0 / 1307674368000.0);  /* -1/15! */
+    ps = fma(ps, p2, 1.0 / 6227020800.0);      /* 1/13! */
+    ps = fma(ps, p2, -1.0 / 39916800.0);       /* -1/11! */
+    ps = fma(ps, p2, 1.0 / 362880.0);          /* 1/9! */
+    ps = fma(ps, p2, -1.0 / 5040.0);           /* -1/7! */
+    ps = fma(ps, p2, 1.0 / 120.0);             /* 1/5! */
+    ps = fma(ps, p2, -1.0 / 6.0);              /* -1/3! */
+    double s = fma(phi * p2, ps, phi);
+    double pc = 1.0 / 6402373705728000.0; /* 1/18! */
+    pc = fma(pc, p2, -1.0 / 20922789888000.0); /* -1/16! */
+    pc = fma(pc, p2, 1.0 / 87178291200.0);     /* 1/14! */
+    pc = fma(pc, p2, -1.0 / 479001600.0);      /* -1/12! */
+    pc = fma(pc, p2, 1.0 / 3628800.0);         /* 1/10! */
+    pc = fma(pc, p2, -1.0 / 40320.0);          /* -1/8! */
+    pc = fma(pc, p2, 1.0 / 720.0);             /* 1/6! */
+    pc = fma(pc, p2, -1.0 / 24.0);             /* -1/4! */
+    pc = fma(pc, p2, 0.5);                     /* 1/2! (sign applied below) */
+    double c = fma(-p2, pc, 1.0);
+    int qi = ((int)q) & 3;
+    switch (qi) {
+    case 0: *sn = s; *cs = c; break;
+    case 1: *sn = c; *cs = -s; break;
+    case 2: *sn = -s; *cs = -c; break;
+    default: *sn = -c; *cs = s; break;
+    }
+}
+
+double kor_u01(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386962890625e-10; }
+uint32_t kor_index(uint32_t w, uint32_t n) { return (uint32_t)(((uint64_t)w * (uint64_t)n) >> 32); }
+void kor_normal_pair(uint32_t w0, uint32_t w1, double *z0, double *z1) {
+    double r = sqrt(-2.0 * kor_log(kor_u01(w0)));
+    double s, c;
+    kor_sincos2pi(kor_u01(w1), &s, &c);
+    *z0 = r * c;
+    *z1 = r * s;
+}
+static double next_uniform(stream_t *s) { return kor_u01(next_u32(s)); }
+static double next_normal(stream_t *s) { /* consumes 2 words, keeps the cosine branch */
+    uint32_t w0 = next_u32(s), w1 = next_u32(s);
+    double z0, z1;
+    kor_normal_pair(w0, w1, &z0, &z1);
+    return z0;
+}
+static double next_exp(stream_t *s) { return -kor_log(next_uniform(s)); }
+
+/* ------------------------------------------------------------------ */
+/* priors -- ref: src/priors.jl:30-43 + Distributions.jl closed forms   */
+/* ------------------------------------------------------------------ */
+#define LOG2PI 1.8378770664093453
+static double std_normal_cdf(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+
+static double prior1_logpdf(const kor_prior_t *p, double x) {
+    switch (p->kind) {
+    case KOR_PRIOR_UNIFORM: /* Distributions: insupport ? -log(b-a) : -Inf */
+        return (x >= p->p0 && x <= p->p1) ? -log(p->p1 - p->p0) : -INFINITY;
+    case KOR_PRIOR_NORMAL: {
+        double z = (x - p->p0) / p->p1;
+        return -(z * z + LOG2PI) / 2.0 - log(p->p1);
+    }
+    case KOR_PRIOR_TRUNC_NORMAL: {
+        if (!(x >= p->lo && x <= p->hi)) return -INFINITY;
+        double z = (x - p->p0) / p->p1;
+        double logtp = log(std_normal_cdf((p->hi - p->p0) / p->p1) - std_normal_cdf((p->lo - p->p0) / p->p1));
+        return (-(z * z + LOG2PI) / 2.0 - log(p->p1)) - logtp;
+    }
+    }
+    return NAN;
+}
+/* ref: src/priors.jl:30-36 -- left-to-right sum starting from component 1 */
+double kor_prior_logpdf(const kor_prior_t *prior, int d, const double *x) {
+    double s = prior1_logpdf(&prior[0], x[0]);
+    for (int k = 1; k < d; ++k) s += prior1_logpdf(&prior[k], x[k]);
+    return s;
+}
+#define TRUNC_MAX_TRIES (1 << 20)
+static int prior1_sample(const kor_prior_t *p, stream_t *s, double *out) {
+    switch (p->kind) {
+    case KOR_PRIOR_UNIFORM: *out = p->p0 + (p->p1 - p->p0) * next_uniform(s); return 0;
+    case KOR_PRIOR_NORMAL: *out = p->p0 + p->p1 * next_normal(s); return 0;
+    case KOR_PRIOR_TRUNC_NORMAL:
+        for (int t = 0; t < TRUNC_MAX_TRIES; ++t) {
+            double x = p->p0 + p->p1 * next_normal(s);
+            if (x >= p->lo && x <= p->hi) { *out = x; return 0; }
+        }
+        *out = NAN;
+        return 1;
+    }
+    return 1;
+}
+/* ref: src/priors.jl:42-43 -- components drawn in order from one stream */
+int kor_prior_sample(uint64_t seed, const kor_prior_t *prior, int d, uint32_t id, uint32_t epoch, double *x) {
+    stream_t s;
+    stream_init(&s, seed, ST_PRIOR, id, epoch);
+    int rc = 0;
+    for (int k = 0; k < d; ++k) rc |= prior1_sample(&prior[k], &s, &x[k]);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
+/* simulators + distances                      */
+/* ------------------------------------------------------------------ */
+static __thread int64_t g_last_events;
+int64_t kor_last_events(void) { return g_last_events; }
+
+/* ref: README.md:35-52 / test/runtests.jl:281-286.
+ * x = randn(n).*sigma .+ mu ; hypot(mean(x)-t0, (std(x)-t1)*w), std with n-1.
+ * Two sequential passes over the same counter-generated draws. */
+static double cost_normal(const kor_model_t *m, stream_t *s0, const double *th) {
+    const int n = m->n_draws;
+    const double mu = th[0], sigma = th[1];
+    double z[4];
+    stream_t s = *s0;
+    double sum = 0.0;
+    for (int j = 0; j < n; j += 4) {
+        uint32_t w0 = next_u32(&s), w1 = next_u32(&s), w2 = next_u32(&s), w3 = next_u32(&s);
+        kor_normal_pair(w0, w1, &z[0], &z[1]);
+        kor_normal_pair(w2, w3, &z[2], &z[3]);
+        for (int q = 0; q < 4 && j + q < n; ++q) sum += z[q] * sigma + mu;
+    }
+    double mean = sum / (double)n;
+    s = *s0;
+    double ss = 0.0;
+    for (int j = 0; j < n; j += 4) {
+        uint32_t w0 = next_u32(&s), w1 = next_u32(&s), w2 = next_u32(&s), w3 = next_u32(&s);
+        kor_normal_pair(w0, w1, &z[0], &z[1]);
+        kor_normal_pair(w2, w3, &z[2], &z[3]);
+        for (int q = 0; q < 4 && j + q < n; ++q) {
+            double dx = (z[q] * sigma + mu) - mean;
+            ss += dx * dx;
+        }
+    }
+    double sd = sqrt(ss / (double)(n - 1));
+    double d1 = mean - m->target[0];
+    double d2 = (sd - m->target[1]) * m->param[0];
+    return sqrt(d1 * d1 + d2 * d2);
+}
+
+/* MA(2): y_t = e_{t+2} + th1 e_{t+1} + th2 e_t, t = 0..n-1 (n+2 normals);
+ * tau_j = (1/n) sum_{t>=j} y_t y_{t-j}; distance = || tau - target ||_2;
+ * +Inf outside the invertibility triangle (no variates consumed). */
+static double cost_ma2(const kor_model_t *m, stream_t *s, const double *th) {
+    const int n = m->n_draws;
+    const double t1 = th[0], t2 = th[1];
+    if (!(t1 > -2.0 && t1 < 2.0 && t1 + t2 > -1.0 && t1 - t2 < 1.0)) return INFINITY;
+    double e0 = 0, e1 = 0, y1 = 0, y2 = 0, a1 = 0, a2 = 0;
+    double z[4];
+    int t = -2; /* index of the y produced by the current normal */
+    for (int j = 0; j < n + 2; j += 4) {
+        uint32_t w0 = next_u32(s), w1 = next_u32(s), w2 = next_u32(s), w3 = next_u32(s);
+        kor_normal_pair(w0, w1, &z[0], &z[1]);
+        kor_normal_pair(w2, w3, &z[2], &z[3]);
+        for (int q = 0; q < 4 && j + q < n + 2; ++q, ++t) {
+            double e2 = z[q];
+            if (t >= 0) {
+                double y = (e2 + t1 * e1) + t2 * e0;
+                if (t >= 1) a1 += y * y1;
+                if (t >= 2) a2 += y * y2;
+                y2 = y1; y1 = y;
+            }
+            e0 = e1; e1 = e2;
+        }
+    }
+    double d1 = a1 / (double)n - m->target[0];
+    double d2 = a2 / (double)n - m->target[1];
+    return sqrt(d1 * d1 + d2 * d2);
+}
+
+/* g-and-k: x = A + B (1 + c (1-e^{-gz})/(1+e^{-gz})) (1+z^2)^k z, c = param[0] (0.8);
+ * summaries = order statistics at 1-based ranks round(i n/8), i=1..7; Euclidean distance. */
+static int cmp_double(const void *a, const void *b) {
+    double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+static double gk_transform(double A, double B, double g, double k, double c, double z) {
+    double eg = kor_exp(-g * z);
+    double skew = 1.0 + c * ((1.0 - eg) / (1.0 + eg));
+    double kurt = kor_exp(k * kor_log(1.0 + z * z));
+    return A + ((B * skew) * kurt) * z;
+}
+static double cost_gk(const kor_model_t *m, stream_t *s, const double *th) {
+    const int n = m->n_draws;
+    double *x = (double *)malloc(sizeof(double) * (size_t)(n + 4));
+    double z[4];
+    for (int j = 0; j < n; j += 4) {
+        uint32_t w0 = next_u32(s), w1 = next_u32(s), w2 = next_u32(s), w3 = next_u32(s);
+        kor_normal_pair(w0, w1, &z[0], &z[1]);
+        kor_normal_pair(w2, w3, &z[2], &z[3]);
+        for (int q = 0; q < 4 && j + q < n; ++q)
+            x[j + q] = gk_transform(th[0], th[1], th[2], th[3], m->param[0], z[q]);
+    }
+    qsort(x, (size_t)n, sizeof(double), cmp_double);
+    double acc = 0.0;
+    for (int i = 1; i <= 7; ++i) {
+        int64_t rank = ((int64_t)i * n + 4) / 8; /* round(i n/8), half up */
+        if (rank < 1) rank = 1;
+        double dq = x[rank - 1] - m->target[i - 1];
+        acc += dq * dq;
+    }
+    free(x);
+    return sqrt(acc);
+}
+
+/* Lotka-Volterra, Gillespie direct method.  theta = log rates; param = {X0, Y0, T, n_grid, max_events};
+ * target = [X(t_1..t_G), Y(t_1..t_G)], t_g = g T/G.  RMS distance; +Inf if the event cap is hit. */
+static double cost_lv(const kor_model_t *m, stream_t *s, const double *th) {
+    const double c1 = kor_exp(th[0]), c2 = kor_exp(th[1]), c3 = kor_exp(th[2]);
+    double X = m->param[0], Y = m->param[1];
+    const double T = m->param[2];
+    const int G = (int)m->param[3];
+    const int64_t max_events = (int64_t)m->param[4];
+    const double dt = T / (double)G;
+    double t = 0.0, acc = 0.0;
+    int g = 0;
+    int64_t ev = 0;
+    while (g < G) {
+        double a1 = c1 * X, a2 = (c2 * X) * Y, a3 = c3 * Y;
+        double a0 = (a1 + a2) + a3;
+        double tn;
+        uint32_t w0 = 0, w1 = 0;
+        if (a0 > 0.0) {
+            if (ev >= max_events) { g_last_events = ev; return INFINITY; }
+            w0 = next_u32(s); w1 = next_u32(s);
+            tn = t + (-kor_log(kor_u01(w0))) / a0;
+        } else {
+            tn = INFINITY;
+        }
+        while (g < G && (double)(g + 1) * dt <= tn) { /* record the pre-event state */
+            double dx = X - m->target[g], dy = Y - m->target[G + g];
+            acc += dx * dx;
+            acc += dy * dy;
+            ++g;
+        }
+        if (g >= G) break;
+        double r = kor_u01(w1) * a0;
+        if (r < a1) X += 1.0;
+        else if (r < a1 + a2) { X -= 1.0; Y += 1.0; }
+        else Y -= 1.0;
+        t = tn;
+        ++ev;
+    }
+    g_last_events = ev;
+    return sqrt(acc / (double)(2 * G));
+}
+
+/* same simulator, returning the grid observations instead of the distance (used to make synthetic targets) */
+int kor_lv_trajectory(const kor_model_t *m, uint64_t seed, const double *th, uint32_t id, uint32_t epoch, double *out) {
+    const int G = (int)m->param[3];
+    stream_t s;
+    stream_init(&s, seed, ST_COST, id, epoch);
+    const double c1 = kor_exp(th[0]), c2 = kor_exp(th[1]), c3 = kor_exp(th[2]);
+    double X = m->param[0], Y = m->param[1];
+    const double T = m->param[2];
+    const int64_t max_events = (int64_t)m->param[4];
+    const double dt = T / (double)G;
+    double t = 0.0;
+    int g = 0;
+    int64_t ev = 0;
+    while (g < G) {
+        double a1 = c1 * X, a2 = (c2 * X) * Y, a3 = c3 * Y;
+        double a0 = (a1 + a2) + a3, tn;
+        uint32_t w0 = 0, w1 = 0;
+        if (a0 > 0.0) {
+            if (ev >= max_events) return 1;
+            w0 = next_u32(&s); w1 = next_u32(&s);
+            tn = t + (-kor_log(kor_u01(w0))) / a0;
+        } else tn = INFINITY;
+        while (g < G && (double)(g + 1) * dt <= tn) { out[g] = X; out[G + g] = Y; ++g; }
+        if (g >= G) break;
+        double r = kor_u01(w1) * a0;
+        if (r < a1) X += 1.0;
+        else if (r < a1 + a2) { X -= 1.0; Y += 1.0; }
+        else Y -= 1.0;
+        t = tn;
+        ++ev;
+    }
+    return 0;
+}
+
+/* deterministic costs used by the reference's own tests:
+ * param[0]=0: |th0^2 + 1 - 1.5|  (test/runtests.jl:77-86, sim(mu)=mu*mu+1)
+ * param[0]=1: |th0 - 1.5|        (test/runtests.jl:177-182) */
+static double cost_det(const kor_model_t *m, const double *th) {
+    if (m->param[0] == 0.0) return fabs((th[0] * th[0] + 1.0) - m->target[0]);
+    return fabs(th[0] - m->target[0]);
+}
+
+static double cost_dispatch(const kor_model_t *m, uint64_t seed, uint32_t tag, int d, const double *th,
+                            uint32_t id, uint32_t epoch) {
+    (void)d;
+    stream_t s;
+    stream_init(&s, seed, tag, id, epoch);
+    g_last_events = 0;
+    switch (m->kind) {
+    case KOR_MODEL_NORMAL_MEANSTD: return cost_normal(m, &s, th);
+    case KOR_MODEL_MA2_AUTOCOV: return cost_ma2(m, &s, th);
+    case KOR_MODEL_GK_OCTILE: return cost_gk(m, &s, th);
+    case KOR_MODEL_LV_SSA: return cost_lv(m, &s, th);
+    case KOR_MODEL_DETERMINISTIC: return cost_det(m, th);
+    }
+    return NAN;
+}
+double kor_cost(const kor_model_t *model, uint64_t seed, int d, const double *theta, uint32_t id, uint32_t epoch) {
+    return cost_dispatch(model, seed, ST_COST, d, theta, id, epoch);
+}
+void kor_eval_cost(const kor_model_t *model, uint64_t seed, int d, const double *theta_soa, int64_t n,
+                   uint32_t first_id, uint32_t epoch, double *out, int nthreads) {
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t i = 0; i < n; ++i) {
+        double th[16];
+        for (int k = 0; k < d; ++k) th[k] = theta_soa[(int64_t)k * n + i];
+        out[i] = cost_dispatch(model, seed, ST_COST, d, th, first_id + (uint32_t)i, epoch);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Statistics.quantile, type 7 (alpha=beta=1) -- ref: src/smc.jl:134    */
+/* [dep, restated from the published Statistics.jl algorithm]           */
+/* ------------------------------------------------------------------ */
+static double quantile7_sorted(const double *v, int64_t n, double p) {
+    double aleph = (double)n * p + (1.0 - p);
+    int64_t j = (int64_t)aleph; /* trunc */
+    if (j < 1) j = 1;
+    if (j > n - 1) j = n - 1;
+    double gam = aleph - (double)j;
+    if (gam < 0.0) gam = 0.0;
+    if (gam > 1.0) gam = 1.0;
+    double a, b;
+    if (n == 1) { a = v[0]; b = v[0]; }
+    else { a = v[j - 1]; b = v[j]; }
+    if (isfinite(a) && isfinite(b)) return a + gam * (b - a);
+    return (1.0 - gam) * a + gam * b;
+}
+double kor_quantile7(const double *v, int64_t n, double p) {
+    double *c = (double *)malloc(sizeof(double) * (size_t)n);
+    memcpy(c, v, sizeof(double) * (size_t)n);
+    qsort(c, (size_t)n, sizeof(double), cmp_double);
+    double q = quantile7_sorted(c, n, p);
+    free(c);
+    return q;
+}
+
+/* ------------------------------------------------------------------ */
+/* smc -- ref: src/smc.jl:92-206                                        */
+/* ------------------------------------------------------------------ */
+struct kor_smc {
+    uint64_t seed;
+    kor_prior_t prior[16];
+    int d;
+    kor_model_t model;
+    kor_smc_config_t cfg;
+    int nthreads;
+    int64_t N;
+    double *th, *X, *lpi;      /* th SoA: th[k*N+i] */
+    uint8_t *alive;
+    double *th2, *X2, *lpi2;   /* gather scratch */
+    /* proposal / trace buffers */
+    int64_t *ta, *tb;
+    double *tz, *tlprob, *tlpip, *txp, *thp;
+    uint8_t *tdec;
+    double eps;
+    int flag;
+    int64_t iteration, n_alive, accepted, cost_evals, events;
+    uint32_t next_epoch;
+    const double *override_xp;
+    kor_smc_log_t *log;
+    int64_t nlog, caplog;
+};
+
+int kor_smc_create(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model,
+                   const kor_smc_config_t *cfg, int nthreads, kor_smc_t **out) {
+    /* ref: src/smc.jl:107-118 argument checks, same order and messages */
+    if (!(cfg->min_r_ess > 0)) return fail("min_r_ess must be > 0.");
+    if (!(cfg->mcmc_retrys >= 0)) return fail("mcmc_retrys must be >= 0.");
+    if (!(cfg->alpha > 0)) return fail("alpha must be > 0.");
+    if (!(cfg->r_epstol >= 0)) return fail("r_epstol must be >= 0");
+    if (!(cfg->mcmc_tol >= 0)) return fail("mcmc_tol must be >= 0");
+    if (!(cfg->max_stretch > 1)) return fail("max_stretch must be > 1");
+    if (d < 1 || d > 16) return fail("d out of range");
+    double mn = cfg->alpha < cfg->min_r_ess ? cfg->alpha : cfg->min_r_ess;
+    int64_t min_np = (int64_t)ceil(3.0 * (double)d / mn);
+    if (cfg->nparticles < min_np) {
+        snprintf(g_err, sizeof g_err, "nparticles must be >= %lld.", (long long)min_np);
+        return 1;
+    }
+    kor_smc_t *s = (kor_smc_t *)calloc(1, sizeof *s);
+    s->seed = seed;
+    memcpy(s->prior, prior, sizeof(kor_prior_t) * (size_t)d);
+    s->d = d;
+    s->model = *model;
+    s->cfg = *cfg;
+    s->nthreads = nthreads > 0 ? nthreads : 1;
+    int64_t N = s->N = cfg->nparticles;
+    size_t nd = (size_t)N * (size_t)d;
+    s->th = (double *)calloc(nd, 8); s->th2 = (double *)calloc(nd, 8); s->thp = (double *)calloc(nd, 8);
+    s->X = (double *)calloc((size_t)N, 8); s->X2 = (double *)calloc((size_t)N, 8);
+    s->lpi = (double *)calloc((size_t)N, 8); s->lpi2 = (double *)calloc((size_t)N, 8);
+    s->alive = (uint8_t *)calloc((size_t)N, 1);
+    s->ta = (int64_t *)calloc((size_t)N, 8); s->tb = (int64_t *)calloc((size_t)N, 8);
+    s->tz = (double *)calloc((size_t)N, 8); s->tlprob = (double *)calloc((size_t)N, 8);
+    s->tlpip = (double *)calloc((size_t)N, 8); s->txp = (double *)calloc((size_t)N, 8);
+    s->tdec = (uint8_t *)calloc((size_t)N, 1);
+    s->eps = INFINITY;
+    *out = s;
+    return 0;
+}
+void kor_smc_destroy(kor_smc_t *s) {
+    if (!s) return;
+    free(s->th); free(s->th2); free(s->thp); free(s->X); free(s->X2); free(s->lpi); free(s->lpi2);
+    free(s->alive); free(s->ta); free(s->tb); free(s->tz); free(s->tlprob); free(s->tlpip); free(s->txp);
+    free(s->tdec); free(s->log); free(s);
+}
+void kor_smc_set_cost_override(kor_smc_t *s, const double *xp) { s->override_xp = xp; }
+
+/* ref: src/smc.jl:119-129 */
+int kor_smc_init(kor_smc_t *s) {
+    const int64_t N = s->N;
+    const int d = s->d;
+    int bad = 0;
+    int64_t events = 0;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(s->nthreads) reduction(| : bad) reduction(+ : events)
+    for (int64_t i = 0; i < N; ++i) {
+        double th[16];
+        bad |= kor_prior_sample(s->seed, s->prior, d, (uint32_t)i, 0, th);
+        for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = th[k];
+        s->X[i] = cost_dispatch(&s->model, s->seed, ST_COST_INIT, d, th, (uint32_t)i, 0);
+        events += g_last_events;
+        s->lpi[i] = kor_prior_logpdf(s->prior, d, th);
+        s->alive[i] = 1;
+    }
+    if (bad) return fail("prior sampling failed (truncation too extreme)");
+    s->eps = INFINITY;
+    s->flag = 0;
+    s->iteration = 0;
+    s->n_alive = N;
+    s->accepted = 0;
+    s->cost_evals = N;
+    s->events = events;
+    s->next_epoch = 0;
+    s->nlog = 0;
+    return 0;
+}
+
+/* ref: src/smc.jl:160-191 -- one synchronous MCMC sweep with epoch e */
+static void smc_sweep(kor_smc_t *s, uint32_t e) {
+    const int64_t N = s->N;
+    const int d = s->d;
+    const double eps = s->eps;
+    const int flag = s->flag;
+    const double sqNp = sqrt((double)d);
+    /* phase A (ref :160-167): proposals from the pre-sweep ensemble */
+#pragma omp parallel for schedule(static) num_threads(s->nthreads)
+    for (int64_t i = 0; i < N; ++i) {
+        s->tdec[i] = 0;
+        s->ta[i] = s->tb[i] = -1;
+        s->tz[i] = s->tlprob[i] = s->tlpip[i] = s->txp[i] = NAN;
+        for (int k = 0; k < d; ++k) s->thp[(int64_t)k * N + i] = NAN;
+        if (!s->alive[i]) continue;
+        stream_t st;
+        stream_init(&st, s->seed, ST_PROPOSE, (uint32_t)i, e);
+        int64_t a = i, b = i;
+        while (a == i) a = kor_index(next_u32(&st), (uint32_t)N);
+        while (b == i || b == a) b = kor_index(next_u32(&st), (uint32_t)N);
+        double z = next_normal(&st);
+        double sc = (s->cfg.max_stretch * z) / sqNp;
+        for (int k = 0; k < d; ++k) {
+            const double *t = s->th + (int64_t)k * N;
+            s->thp[(int64_t)k * N + i] = t[i] + (t[b] - t[a]) * sc;
+        }
+        s->tlprob[i] = kor_log(next_uniform(&st));
+        s->ta[i] = a; s->tb[i] = b; s->tz[i] = z;
+    }
+    /* phase B (ref :168-191) */
+    int64_t acc = 0, evals = 0, events = 0;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(s->nthreads) reduction(+ : acc, evals, events)
+    for (int64_t i = 0; i < N; ++i) {
+        if (!s->alive[i]) continue;
+        double thp[16];
+        for (int k = 0; k < d; ++k) thp[k] = s->thp[(int64_t)k * N + i];
+        double lpip = kor_prior_logpdf(s->prior, d, thp);
+        s->tlpip[i] = lpip;
+        if (lpip < 0 && !isfinite(lpip)) { s->tdec[i] = 1; continue; }
+        double lM = fmin((lpip - s->lpi[i]) + 0.0, 0.0);
+        if (!(s->tlprob[i] < lM)) { s->tdec[i] = 2; continue; }
+        double Xp;
+        if (s->override_xp) Xp = s->override_xp[i];
+        else {
+            Xp = cost_dispatch(&s->model, s->seed, ST_COST, d, thp, (uint32_t)i, e);
+            events += g_last_events;
+        }
+        evals += 1;
+        s->txp[i] = Xp;
+        if (flag ? (Xp > eps) : (Xp >= eps)) { s->tdec[i] = 3; continue; }
+        for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = thp[k];
+        s->X[i] = Xp;
+        s->lpi[i] = lpip;
+        s->tdec[i] = 4;
+        acc += 1;
+    }
+    s->accepted += acc;
+    s->cost_evals += evals;
+    s->events += events;
+}
+
+int kor_smc_iterate(kor_smc_t *s, int *stop) {
+    const int64_t N = s->N;
+    const int d = s->d;
+    const kor_smc_config_t *c = &s->cfg;
+    *stop = 0;
+    s->iteration += 1;
+    double epsv = s->eps;
+    /* ref :134 quantile(Xs[alive], alpha) and :136 minimum(Xs[alive]) */
+    int64_t na = 0;
+    double *xa = s->X2;
+    double mn = INFINITY;
+    for (int64_t i = 0; i < N; ++i)
+        if (s->alive[i]) { xa[na++] = s->X[i]; if (s->X[i] < mn) mn = s->X[i]; }
+    if (na == 0) return fail("no alive particles");
+    qsort(xa, (size_t)na, sizeof(double), cmp_double);
+    double eps = quantile7_sorted(xa, na, c->alpha);
+    int flag = 0;
+    int64_t ess = 0;
+    if (eps > mn) {
+        for (int64_t i = 0; i < N; ++i) { s->alive[i] = s->X[i] < eps; ess += s->alive[i]; }
+    } else {
+        for (int64_t i = 0; i < N; ++i) { s->alive[i] = s->X[i] <= eps; ess += s->alive[i]; }
+        flag = 1;
+    }
+    s->eps = eps;
+    s->flag = flag;
+    s->n_alive = ess;
+    int resampled = 0;
+    /* ref :145-153 */
+    if (c->alpha * (double)ess <= (double)N * c->min_r_ess) {
+        if (ess == 0) return fail("resampling with zero alive particles");
+        int64_t *idxalive = s->ta; /* scratch */
+        int64_t n = 0;
+        for (int64_t i = 0; i < N; ++i) if (s->alive[i]) idxalive[n++] = i;
+        for (int64_t k = 0; k < N; ++k) {
+            int64_t src = idxalive[k % n];
+            for (int q = 0; q < d; ++q) s->th2[(int64_t)q * N + k] = s->th[(int64_t)q * N + src];
+            s->X2[k] = s->X[src];
+            s->lpi2[k] = s->lpi[src];
+        }
+        double *tmp;
+        tmp = s->th; s->th = s->th2; s->th2 = tmp;
+        tmp = s->X; s->X = s->X2; s->X2 = tmp;
+        tmp = s->lpi; s->lpi = s->lpi2; s->lpi2 = tmp;
+        memset(s->alive, 1, (size_t)N);
+        resampled = 1;
+    }
+    /* ref :156-193 */
+    s->accepted = 0;
+    int64_t sweeps = 0;
+    for (int64_t r = 0; r < 1 + c->mcmc_retrys; ++r) {
+        smc_sweep(s, s->next_epoch);
+        s->next_epoch += 1;
+        sweeps += 1;
+        if ((double)s->accepted >= c->mcmc_tol * (double)N) break;
+    }
+    if (s->nlog == s->caplog) {
+        s->caplog = s->caplog ? 2 * s->caplog : 64;
+        s->log = (kor_smc_log_t *)realloc(s->log, sizeof(kor_smc_log_t) * (size_t)s->caplog);
+    }
+    kor_smc_log_t *L = &s->log[s->nlog++];
+    L->iteration = s->iteration; L->eps = eps; L->n_alive = ess; L->flag = flag; L->resampled = resampled;
+    L->accepted = s->accepted; L->cost_evals = s->cost_evals; L->sweeps = sweeps;
+    if (c->verbose) fprintf(stderr, "(iteration, eps, ESS) = (%lld, %.17g, %lld)\n", (long long)s->iteration, eps, (long long)ess);
+    /* ref :194-198 */
+    if (2.0 * fabs(epsv - eps) < c->r_epstol * (fabs(epsv) + fabs(eps))) *stop = 1;
+    else if (eps <= c->epstol) *stop = 2;
+    else if ((double)s->accepted < c->mcmc_tol * (double)N) *stop = 3;
+    else if (c->max_iterations > 0 && s->iteration >= c->max_iterations) *stop = 4;
+    return 0;
+}
+int kor_smc_run(kor_smc_t *s) {
+    if (kor_smc_init(s)) return 1;
+    int stop = 0;
+    while (!stop)
+        if (kor_smc_iterate(s, &stop)) return 1;
+    return 0;
+}
+void kor_smc_get_state(const kor_smc_t *s, double *th, double *X, double *lpi, uint8_t *alive) {
+    if (th) memcpy(th, s->th, sizeof(double) * (size_t)s->N * (size_t)s->d);
+    if (X) memcpy(X, s->X, sizeof(double) * (size_t)s->N);
+    if (lpi) memcpy(lpi, s->lpi, sizeof(double) * (size_t)s->N);
+    if (alive) memcpy(alive, s->alive, (size_t)s->N);
+}
+void kor_smc_set_state(kor_smc_t *s, const double *th, const double *X, const double *lpi, const uint8_t *alive) {
+    if (th) memcpy(s->th, th, sizeof(double) * (size_t)s->N * (size_t)s->d);
+    if (X) memcpy(s->X, X, sizeof(double) * (size_t)s->N);
+    if (lpi) memcpy(s->lpi, lpi, sizeof(double) * (size_t)s->N);
+    if (alive) memcpy(s->alive, alive, (size_t)s->N);
+}
+void kor_smc_get_scalars(const kor_smc_t *s, double *eps, int32_t *flag, int64_t *iteration, int64_t *n_alive,
+                         int64_t *accepted, int64_t *cost_evals, int64_t *next_epoch) {
+    if (eps) *eps = s->eps;
+    if (flag) *flag = s->flag;
+    if (iteration) *iteration = s->iteration;
+    if (n_alive) *n_alive = s->n_alive;
+    if (accepted) *accepted = s->accepted;
+    if (cost_evals) *cost_evals = s->cost_evals;
+    if (next_epoch) *next_epoch = s->next_epoch;
+}
+int64_t kor_smc_get_log(const kor_smc_t *s, kor_smc_log_t *log, int64_t cap) {
+    int64_t n = s->nlog < cap ? s->nlog : cap;
+    if (log) memcpy(log, s->log, sizeof(kor_smc_log_t) * (size_t)n);
+    return s->nlog;
+}
+void kor_smc_get_trace(const kor_smc_t *s, int64_t *a, int64_t *b, double *z, double *lprob, double *lpi_p,
+                       double *xp, uint8_t *decision, double *thp) {
+    size_t N = (size_t)s->N;
+    if (a) memcpy(a, s->ta, 8 * N);
+    if (b) memcpy(b, s->tb, 8 * N);
+    if (z) memcpy(z, s->tz, 8 * N);
+    if (lprob) memcpy(lprob, s->tlprob, 8 * N);
+    if (lpi_p) memcpy(lpi_p, s->tlpip, 8 * N);
+    if (xp) memcpy(xp, s->txp, 8 * N);
+    if (decision) memcpy(decision, s->tdec, N);
+    if (thp) memcpy(thp, s->thp, 8 * N * (size_t)s->d);
+}
+
+/* ------------------------------------------------------------------ */
+/* AIS -- ref: src/transition.jl, src/types.jl:51-75, src/KissABC.jl    */
+/* ------------------------------------------------------------------ */
+struct kor_ais {
+    uint64_t seed;
+    kor_prior_t prior[16];
+    int d;
+    kor_model_t model;
+    kor_ais_config_t cfg;
+    int nthreads;
+    int64_t N;
+    double *th, *lp, *ll;
+    /* trace */
+    uint8_t *tmove, *tdec;
+    int64_t *ta, *tb, *tc;
+    double *tcorr, *thp, *tlpp, *tllp, *te;
+    int64_t cost_evals, accepted, sweeps, retries;
+};
+
+int kor_ais_create(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model,
+                   const kor_ais_config_t *cfg, int nthreads, kor_ais_t **out) {
+    if (d < 1 || d > 16) return fail("d out of range");
+    /* ref: src/KissABC.jl:43-48 */
+    if (cfg->nwalkers < d + 5) {
+        snprintf(g_err, sizeof g_err, "nparticles = %lld is insufficient, set number of particles in AIS(.) atleast to %d",
+                 (long long)cfg->nwalkers, d + 5);
+        return 1;
+    }
+    kor_ais_t *s = (kor_ais_t *)calloc(1, sizeof *s);
+    s->seed = seed;
+    memcpy(s->prior, prior, sizeof(kor_prior_t) * (size_t)d);
+    s->d = d; s->model = *model; s->cfg = *cfg; s->nthreads = nthreads > 0 ? nthreads : 1;
+    size_t N = (size_t)(s->N = cfg->nwalkers);
+    s->th = (double *)calloc(N * (size_t)d, 8); s->thp = (double *)calloc(N * (size_t)d, 8);
+    s->lp = (double *)calloc(N, 8); s->ll = (double *)calloc(N, 8);
+    s->tmove = (uint8_t *)calloc(N, 1); s->tdec = (uint8_t *)calloc(N, 1);
+    s->ta = (int64_t *)calloc(N, 8); s->tb = (int64_t *)calloc(N, 8); s->tc = (int64_t *)calloc(N, 8);
+    s->tcorr = (double *)calloc(N, 8); s->tlpp = (double *)calloc(N, 8); s->tllp = (double *)calloc(N, 8);
+    s->te = (double *)calloc(N, 8);
+    *out = s;
+    return 0;
+}
+void kor_ais_destroy(kor_ais_t *s) {
+    if (!s) return;
+    free(s->th); free(s->thp); free(s->lp); free(s->ll); free(s->tmove); free(s->tdec); free(s->ta);
+    free(s->tb); free(s->tc); free(s->tcorr); free(s->tlpp); free(s->tllp); free(s->te); free(s);
+}
+
+/* ref: src/types.jl:51-58 -- (logprior, loglikelihood) of the kernelized posterior */
+static void ais_loglike(kor_ais_t *s, const double *x, uint32_t tag, uint32_t id, uint32_t epoch, double *lp,
+                        double *ll, int *evals) {
+    double p = kor_prior_logpdf(s->prior, s->d, x);
+    double l = p;
+    if (isfinite(p)) {
+        double c = cost_dispatch(&s->model, s->seed, tag, s->d, x, id, epoch);
+        double q = c / s->cfg.scale;
+        l = -0.5 * (q * q);
+        *evals += 1;
+    }
+    *lp = p;
+    *ll = l;
+}
+
+/* ref: src/KissABC.jl:50-61.  attempt t of walker i uses epoch t of the PRIOR / COST_INIT streams */
+int kor_ais_init(kor_ais_t *s) {
+    const int64_t N = s->N;
+    const int d = s->d;
+    int64_t budget = s->cfg.retry_sampling * N;
+    int64_t cap = budget + 1; /* per-walker retries beyond this always exhaust the budget */
+    int64_t retries = 0, evals_total = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(s->nthreads) reduction(+ : retries, evals_total) reduction(| : bad)
+    for (int64_t i = 0; i < N; ++i) {
+        double th[16], lp = 0, ll = 0;
+        int evals = 0;
+        int64_t t = 0;
+        for (;; ++t) {
+            bad |= kor_prior_sample(s->seed, s->prior, d, (uint32_t)i, (uint32_t)t, th);
+            ais_loglike(s, th, ST_COST_INIT, (uint32_t)i, (uint32_t)t, &lp, &ll, &evals);
+            if (isfinite(lp + ll) || t >= cap) break;
+        }
+        retries += t;
+        evals_total += evals;
+        for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = th[k];
+        s->lp[i] = lp;
+        s->ll[i] = ll;
+    }
+    s->retries = retries;
+    s->cost_evals = evals_total;
+    s->accepted = 0;
+    s->sweeps = 0;
+    if (bad) return fail("prior sampling failed (truncation too extreme)");
+    if (retries > budget)
+        return fail("Prior leads to \xe2\x88\x9e costs too often, tune the prior or increase `retry_sampling`.");
+    return 0;
+}
+
+/* draw an index from [lo, lo+n) */
+static int64_t draw_idx(stream_t *st, int64_t lo, int64_t n) { return lo + (int64_t)kor_index(next_u32(st), (uint32_t)n); }
+
+/* ref: src/transition.jl:67-82 (transition!), :61-65 (propose), :51-59, :2-22, :24-43;
+ * src/types.jl:62-75 (accept).  The proposal is built from the ensemble `src` (the pre-half-step
+ * snapshot for the red/black schedule, the live ensemble for the sequential one). */
+static int ais_transition_from(kor_ais_t *s, const double *src, int64_t i, int64_t lo, int64_t n, uint32_t epoch) {
+    const int64_t N = s->N;
+    const int d = s->d;
+    stream_t st;
+    stream_init(&st, s->seed, ST_PROPOSE, (uint32_t)i, epoch);
+    double p[16], xi[16];
+    for (int k = 0; k < d; ++k) xi[k] = src[(int64_t)k * N + i];
+    double corr = 0.0;
+    int64_t a = i, b = i, c = i;
+    /* ref :62 rand(rng,(1,1,1,1,2,2,3)) */
+    uint32_t slot = kor_index(next_u32(&st), 7);
+    int move = slot < 4 ? 1 : (slot < 6 ? 2 : 3);
+    if (move == 1) { /* stretch, ref :51-59, a = 3.0 */
+        while (a == i) a = draw_idx(&st, lo, n);
+        double u = next_uniform(&st);
+        double sa = sqrt(3.0), ra = sqrt(1.0 / 3.0);
+        double t = u * (sa - ra) + ra;
+        double Z = t * t;
+        for (int k = 0; k < d; ++k) {
+            double xa = src[(int64_t)k * N + a];
+            p[k] = xa + (xi[k] - xa) * Z;
+        }
+        corr = (double)(d - 1) * kor_log(Z);
+        b = c = -1;
+    } else if (move == 2) { /* DE, ref :2-22 */
+        double z0 = next_normal(&st);
+        double gam = (2.38 / sqrt((double)(2 * d))) * kor_exp(z0 * 0.1);
+        while (a == i) a = draw_idx(&st, lo, n);
+        while (b == a || b == i) b = draw_idx(&st, lo, n);
+        for (int k = 0; k < d; ++k) {
+            double xa = src[(int64_t)k * N + a], xb = src[(int64_t)k * N + b];
+            double W = (xa - xb) * gam;
+            double S = (fabs(xa - xb) + fabs(xi[k] - xb)) + fabs(xa - xi[k]);
+            double T = ((gam * S) / 300.0) * next_normal(&st);
+            p[k] = (xi[k] + W) + T;
+        }
+        c = -1;
+    } else { /* walk, ref :24-43 */
+        while (a == i) a = draw_idx(&st, lo, n);
+        while (b == a || b == i) b = draw_idx(&st, lo, n);
+        while (c == b || c == a || c == i) c = draw_idx(&st, lo, n);
+        double z1 = next_normal(&st), z2 = next_normal(&st), z3 = next_normal(&st);
+        for (int k = 0; k < d; ++k) {
+            double xa = src[(int64_t)k * N + a], xb = src[(int64_t)k * N + b], xc = src[(int64_t)k * N + c];
+            double xs = (xa + (xb + xc)) / 3.0;
+            double W = ((z1 * (xa - xs)) + (z2 * (xb - xs))) + (z3 * (xc - xs));
+            p[k] = xi[k] + W;
+        }
+    }
+    double lpp, llp;
+    int evals = 0;
+    ais_loglike(s, p, ST_COST, (uint32_t)i, epoch, &lpp, &llp, &evals);
+    /* ref: src/types.jl:69-74 */
+    int dec;
+    double e = NAN;
+    if (!isfinite(lpp + llp)) dec = 0;
+    else {
+        stream_t sa;
+        stream_init(&sa, s->seed, ST_ACCEPT, (uint32_t)i, epoch);
+        e = next_exp(&sa);
+        double lW = (corr + (lpp + llp)) - (s->lp[i] + s->ll[i]);
+        dec = (-e <= lW) ? 2 : 1;
+    }
+    s->tmove[i] = (uint8_t)move; s->ta[i] = a; s->tb[i] = b; s->tc[i] = c; s->tcorr[i] = corr;
+    for (int k = 0; k < d; ++k) s->thp[(int64_t)k * N + i] = p[k];
+    s->tlpp[i] = lpp; s->tllp[i] = llp; s->te[i] = e; s->tdec[i] = (uint8_t)dec;
+#pragma omp atomic
+    s->cost_evals += evals;
+    if (dec == 2) {
+        for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = p[k];
+        s->lp[i] = lpp;
+        s->ll[i] = llp;
+#pragma omp atomic
+        s->accepted += 1;
+        return 1;
+    }
+    return 0;
+}
+int kor_ais_transition(kor_ais_t *s, int64_t i, int64_t lo, int64_t n, uint32_t epoch) {
+    return ais_transition_from(s, s->th, i, lo, n, epoch);
+}
+
+/* red/black sweep: colour 0 = walkers [0,h) move against [h,N); colour 1 = the converse; h = N/2.
+ * Within a half-step the moving walkers only READ the other colour, so updates are independent. */
+int kor_ais_sweep(kor_ais_t *s) {
+    const int64_t N = s->N, h = N / 2;
+    if (N - h < 3 || h < 3) return fail("red/black AIS needs >= 3 walkers per colour");
+    uint32_t e0 = (uint32_t)(2 * s->sweeps);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(s->nthreads)
+    for (int64_t i = 0; i < h; ++i) ais_transition_from(s, s->th, i, h, N - h, e0);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(s->nthreads)
+    for (int64_t i = h; i < N; ++i) ais_transition_from(s, s->th, i, 0, h, e0 + 1);
+    s->sweeps += 1;
+    return 0;
+}
+
+/* number of `step` calls AbstractMCMC.mcmcsample makes before saved sample m (0-based):
+ * discard_initial + m*thinning  [dep: AbstractMCMC 2.1-3.1, restated] */
+static int64_t steps_before(const kor_ais_config_t *c, int64_t m) { return c->discard_initial + m * c->thinning; }
+
+/* reference schedule, ref: src/KissABC.jl:66-80: step s (1-based) applies ntransitions moves to walker
+ * (s-1) mod N against the whole live ensemble, emits it, rotates. */
+int kor_ais_run_sequential(kor_ais_t *s, double *out) {
+    const int64_t N = s->N, Ns = s->cfg.nsamples;
+    const int d = s->d;
+    if (kor_ais_init(s)) return 1;
+    int64_t step = 0; /* steps done */
+    uint32_t epoch = 0;
+    for (int64_t m = 0; m < Ns; ++m) {
+        int64_t target = steps_before(&s->cfg, m);
+        int64_t w = N - 1; /* ref :63 first sample is particles[end] */
+        while (step < target) {
+            w = step % N;
+            for (int64_t r = 0; r < s->cfg.ntransitions; ++r) ais_transition_from(s, s->th, w, 0, N, epoch++);
+            ++step;
+        }
+        if (target > 0) w = (target - 1) % N;
+        for (int k = 0; k < d; ++k) out[(int64_t)k * Ns + m] = s->th[(int64_t)k * N + w];
+    }
+    return 0;
+}
+
+/* device schedule: steps are grouped in rounds of N; a round = ntransitions red/black sweeps of the whole
+ * ensemble; step s emits walker (s-1) mod N as it stands at the end of round ceil(s/N). */
+int kor_ais_run_parallel(kor_ais_t *s, double *out) {
+    const int64_t N = s->N, Ns = s->cfg.nsamples;
+    const int d = s->d;
+    if (kor_ais_init(s)) return 1;
+    int64_t rounds = 0;
+    for (int64_t m = 0; m < Ns; ++m) {
+        int64_t target = steps_before(&s->cfg, m);
+        int64_t w = N - 1, need = 0;
+        if (target > 0) { w = (target - 1) % N; need = (target + N - 1) / N; }
+        while (rounds < need) {
+            for (int64_t r = 0; r < s->cfg.ntransitions; ++r)
+                if (kor_ais_sweep(s)) return 1;
+            ++rounds;
+        }
+        for (int k = 0; k < d; ++k) out[(int64_t)k * Ns + m] = s->th[(int64_t)k * N + w];
+    }
+    return 0;
+}
+void kor_ais_get_state(const kor_ais_t *s, double *th, double *lp, double *ll) {
+    if (th) memcpy(th, s->th, 8 * (size_t)s->N * (size_t)s->d);
+    if (lp) memcpy(lp, s->lp, 8 * (size_t)s->N);
+    if (ll) memcpy(ll, s->ll, 8 * (size_t)s->N);
+}
+void kor_ais_set_state(kor_ais_t *s, const double *th, const double *lp, const double *ll) {
+    if (th) memcpy(s->th, th, 8 * (size_t)s->N * (size_t)s->d);
+    if (lp) memcpy(s->lp, lp, 8 * (size_t)s->N);
+    if (ll) memcpy(s->ll, ll, 8 * (size_t)s->N);
+}
+void kor_ais_get_counters(const kor_ais_t *s, int64_t *cost_evals, int64_t *accepted, int64_t *sweeps, int64_t *retries) {
+    if (cost_evals) *cost_evals = s->cost_evals;
+    if (accepted) *accepted = s->accepted;
+    if (sweeps) *sweeps = s->sweeps;
+    if (retries) *retries = s->retries;
+}
+void kor_ais_get_trace(const kor_ais_t *s, uint8_t *move, int64_t *a, int64_t *b, int64_t *c, double *corr,
+                       double *thp, double *lp_p, double *ll_p, double *e, uint8_t *decision) {
+    size_t N = (size_t)s->N;
+    if (move) memcpy(move, s->tmove, N);
+    if (a) memcpy(a, s->ta, 8 * N);
+    if (b) memcpy(b, s->tb, 8 * N);
+    if (c) memcpy(c, s->tc, 8 * N);
+    if (corr) memcpy(corr, s->tcorr, 8 * N);
+    if (thp) memcpy(thp, s->thp, 8 * N * (size_t)s->d);
+    if (lp_p) memcpy(lp_p, s->tlpp, 8 * N);
+    if (ll_p) memcpy(ll_p, s->tllp, 8 * N);
+    if (e) memcpy(e, s->te, 8 * N);
+    if (decision) memcpy(decision, s->tdec, N);
+}

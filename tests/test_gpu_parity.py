@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (north_star): F64 mode is BIT-EXACT against the oracle -- positions, costs, decisions, resampling
+indices, epsilon -- because both sides evaluate the same fixed sequence of IEEE double operations on the
+same Philox words.  F32_ACC64 mode: decisions are bit-exact when the device's own costs are replayed into
+the oracle; costs agree with the F64 oracle within the per-model tolerance stated in F32_TOL.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import SEED, models, prior_draws
+
+pytestmark = pytest.mark.gpu
+
+# |cost_f32 - cost_f64| <= atol + rtol*|cost_f64| on the same Philox words (MUFU lg2/sin/cos/sqrt/tanh/ex2
+# approximations, FP32 accumulation).  Stated per model; measured margins are printed by the tests.
+F32_TOL = {"normal": (2e-5, 1e-4), "ma2": (2e-5, 1e-4), "gk": (5e-4, 5e-4), "lv": (None, None)}
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_bits_equal(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, what
+    same = bits(a) == bits(b)
+    if not same.all():
+        idx = np.argwhere(~same)[:5]
+        raise AssertionError(f"{what}: {(~same).sum()} of {same.size} values differ, first at {idx.tolist()}: "
+                             f"{a[tuple(idx[0])]!r} vs {b[tuple(idx[0])]!r}")
+
+
+# ------------------------------------------------------------------ priors
+def test_prior_logpdf_bit_exact(oracle, kabc, ctx):
+    O = oracle
+    spec = [("uniform", 1, 3), ("truncnormal", 0, 0.1, 0, 100), ("normal", -1, 2.5)]
+    pri = O.make_priors(spec)
+    kpri = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100), kabc.Normal(-1, 2.5))
+    rng = np.random.default_rng(0)
+    n = 5000
+    th = np.vstack([rng.uniform(0.5, 3.5, n), rng.normal(0.05, 0.1, n), rng.normal(-1, 5, n)])
+    th[0, :4] = [1.0, 3.0, 0.999999, 3.0000001]  # support edges
+    th[1, 4:8] = [0.0, -0.0, 100.0, 100.1]
+    dev = ctx.prior_logpdf(kpri, th)
+    ref = np.array([O.lib().kor_prior_logpdf(pri, 3, np.ascontiguousarray(th[:, i]).ctypes.data_as(C.POINTER(C.c_double)))
+                    for i in range(n)])
+    assert_bits_equal(dev, ref, "prior logpdf")
+    assert np.isneginf(dev).sum() > 0
+
+
+def test_factored_exact_values(kabc, ctx):
+    """ref test/runtests.jl:8-15: Factored(Uniform(0,1), Uniform(100,101))."""
+    d = kabc.Factored(kabc.Uniform(0, 1), kabc.Uniform(100, 101))
+    lp = ctx.prior_logpdf(d, np.array([[0.0, 0.5, 0.0], [0.0, 100.5, 100.0]]))
+    assert lp[0] == -np.inf and lp[1] == 0.0 and lp[2] == 0.0
+    assert np.exp(lp[1]) == 1.0 and np.exp(lp[0]) == 0.0
+    assert len(d) == 2
+    s = ctx.prior_sample(d, 1000)
+    assert ((0 < s[0]) & (s[0] < 1)).all() and ((100 < s[1]) & (s[1] < 101)).all()
+
+
+def test_prior_sample_bit_exact(oracle, kabc, ctx):
+    O = oracle
+    spec = [("uniform", 1, 3), ("truncnormal", 0, 0.1, 0, 100), ("normal", -1, 2.5)]
+    kpri = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100), kabc.Normal(-1, 2.5))
+    n = 4096
+    dev = ctx.prior_sample(kpri, n, first_id=11, epoch=3)
+    pri = O.make_priors(spec)
+    ref = np.empty((3, n))
+    buf = (C.c_double * 3)()
+    for i in range(n):
+        O.lib().kor_prior_sample(SEED, pri, 3, 11 + i, 3, buf)
+        ref[:, i] = list(buf)
+    assert_bits_equal(dev, ref, "prior sample")
+    assert (dev[1] >= 0).all()
+
+
+# ------------------------------------------------------------------ simulators
+@pytest.mark.parametrize("name,n,ndraws", [("normal", 3000, 1000), ("normal", 257, 37), ("ma2", 4000, 100),
+                                            ("ma2", 300, 7), ("lv", 600, 0), ("gk", 96, 10000), ("gk", 64, 1001)])
+def test_cost_f64_bit_exact(oracle, kabc, ctx, name, n, ndraws):
+    O = oracle
+    M = models(O, kabc)[name]
+    th = prior_draws(O, M["ospec"], n)
+    dev = ctx.eval_cost(M["kcost"]("f64", ndraws), th, first_id=5, epoch=9)
+    ref = O.eval_cost(M["omodel"](ndraws), SEED, th, first_id=5, epoch=9, nthreads=8)
+    assert_bits_equal(dev, ref, f"{name} cost (F64)")
+    assert np.isfinite(dev).sum() > n // 4
+
+
+@pytest.mark.parametrize("name,n,ndraws", [("normal", 20000, 1000), ("ma2", 20000, 100), ("gk", 256, 10000)])
+def test_cost_f32_within_tolerance(oracle, kabc, ctx, name, n, ndraws):
+    O = oracle
+    M = models(O, kabc)[name]
+    th = prior_draws(O, M["ospec"], n)
+    dev = ctx.eval_cost(M["kcost"]("f32", ndraws), th, first_id=0, epoch=2)
+    ref = O.eval_cost(M["omodel"](ndraws), SEED, th, first_id=0, epoch=2, nthreads=8)
+    fin = np.isfinite(ref)
+    assert (np.isfinite(dev) == fin).all()
+    atol, rtol = F32_TOL[name]
+    err = np.abs(dev[fin] - ref[fin])
+    bound = atol + rtol * np.abs(ref[fin])
+    print(f"{name}: max abs err {err.max():.3e}, max err/bound {np.max(err / bound):.3f}")
+    assert (err <= bound).all()
+
+
+def test_lv_f32_statistically_equal(oracle, kabc, ctx):
+    """LV in F32 mode differs from F64 only in lg2.approx of the waiting times: trajectories decorrelate after a
+    few events, so the check is distributional: same finite fraction and cost quantiles within MC error."""
+    O = oracle
+    M = models(O, kabc)["lv"]
+    n = 4000
+    th = np.tile(np.log([[1.0], [0.005], [0.6]]), (1, n))
+    dev, ev32 = ctx.eval_cost(M["kcost"]("f32"), th, return_events=True)
+    ref, ev64 = ctx.eval_cost(M["kcost"]("f64"), th, return_events=True)
+    assert abs(np.isfinite(dev).mean() - np.isfinite(ref).mean()) < 0.03
+    q = [0.25, 0.5, 0.75]
+    qd, qr = np.quantile(dev[np.isfinite(dev)], q), np.quantile(ref[np.isfinite(ref)], q)
+    print("LV cost quartiles f32", qd, "f64", qr, "mean events", ev32.mean(), ev64.mean())
+    assert np.allclose(qd, qr, rtol=0.08)
+    assert abs(ev32.mean() / ev64.mean() - 1) < 0.05
+
+
+def test_lv_event_counts_match_oracle(oracle, kabc, ctx):
+    O = oracle
+    M = models(O, kabc)["lv"]
+    th = prior_draws(O, M["ospec"], 64)
+    dev, ev = ctx.eval_cost(M["kcost"]("f64"), th, first_id=0, epoch=1, return_events=True)
+    m = M["omodel"]()
+    for i in range(64):
+        t = np.ascontiguousarray(th[:, i])
+        c = O.lib().kor_cost(C.byref(m), SEED, 3, t.ctypes.data_as(C.POINTER(C.c_double)), i, 1)
+        assert O.lib().kor_last_events() == ev[i]
+        assert bits(np.array([c]))[0] == bits(dev[i:i + 1])[0]
+
+
+# ------------------------------------------------------------------ smc
+def _smc_pair(O, k, ctx, name, prec, cfg_kw, ndraws=None):
+    M = models(O, k)[name]
+    kw = {} if ndraws is None else {"n": ndraws}
+    osmc = O.Smc(SEED, O.make_priors(M["ospec"]), M["omodel"](**kw), O.smc_config(**cfg_kw), nthreads=8)
+    dsmc = k.SmcSession(ctx, M["kprior"](), M["kcost"](prec, **kw), k.smc_config(**cfg_kw))
+    return osmc, dsmc
+
+
+def _compare_smc_state(osmc, dsmc, what):
+    oth, oX, olpi, oal = osmc.state()
+    dth, dX, dlpi, dal = dsmc.state()
+    assert (oal == dal).all(), f"{what}: alive masks differ"
+    assert_bits_equal(dth, oth, f"{what}: theta")
+    assert_bits_equal(dX, oX, f"{what}: X")
+    assert_bits_equal(dlpi, olpi, f"{what}: lpi")
+    osc, dsc = osmc.scalars(), dsmc.scalars()
+    for key in ("flag", "iteration", "n_alive", "accepted", "cost_evals", "next_epoch"):
+        assert osc[key] == dsc[key], f"{what}: {key} {osc[key]} vs {dsc[key]}"
+    assert bits(np.array([osc["eps"]]))[0] == bits(np.array([dsc["eps"]]))[0], f"{what}: eps"
+
+
+@pytest.mark.parametrize("name,N,cfg", [
+    ("normal", 2000, dict()),                                        # defaults: resamples every iteration
+    ("normal", 1500, dict(alpha=0.9, min_r_ess=0.55)),               # sparse resampling, dead particles as partners
+    ("normal", 999, dict(alpha=0.5, mcmc_retrys=3, mcmc_tol=0.3)),   # retry sweeps, odd N
+    ("ma2", 4096, dict(alpha=0.9)),                                  # +Inf costs culled by the quantile cut
+    ("lv", 512, dict(alpha=0.8)),
+])
+def test_smc_f64_whole_run_bit_exact(oracle, kabc, ctx, name, N, cfg):
+    """Every iteration of a whole smc run: state, epsilon, flags, counters identical to the oracle's, bit for bit."""
+    cfg = dict(cfg, nparticles=N, max_iterations=40)
+    ndraws = 200 if name == "normal" else None
+    osmc, dsmc = _smc_pair(oracle, kabc, ctx, name, "f64", cfg, ndraws)
+    osmc.init(); dsmc.init()
+    _compare_smc_state(osmc, dsmc, f"{name} init")
+    for it in range(40):
+        so, sd = osmc.iterate(), dsmc.iterate()
+        _compare_smc_state(osmc, dsmc, f"{name} iteration {it + 1}")
+        assert so == sd
+        if so:
+            break
+    olog, dlog = osmc.log(), dsmc.log()
+    assert len(olog) == len(dlog) and len(olog) >= 3
+    for a, b in zip(olog, dlog):
+        for key in ("iteration", "n_alive", "flag", "resampled", "accepted", "cost_evals", "sweeps"):
+            assert a[key] == b[key], (key, a, b)
+        assert bits(np.array([a["eps"]]))[0] == bits(np.array([b["eps"]]))[0]
+    assert any(r["resampled"] for r in dlog)
+
+
+def test_smc_trace_matches_oracle(oracle, kabc, ctx):
+    """Replay hook: partner indices, variates, proposals and per-particle decisions of one sweep."""
+    cfg = dict(nparticles=3000, alpha=0.8, min_r_ess=0.3, max_iterations=10)
+    osmc, dsmc = _smc_pair(oracle, kabc, ctx, "normal", "f64", cfg, 100)
+    dsmc.trace_enable(True)
+    osmc.init(); dsmc.init()
+    for it in range(4):
+        osmc.iterate(); dsmc.iterate()
+        to, td = osmc.trace(), dsmc.trace()
+        assert (to["decision"] == td["decision"]).all()
+        assert (to["a"] == td["a"]).all() and (to["b"] == td["b"]).all()
+        for key in ("z", "lprob", "lpi_p", "xp", "theta_p"):
+            assert_bits_equal(td[key], to[key], f"trace {key} it {it}")
+    assert set(np.unique(td["decision"])) >= {0, 1, 3, 4}
+
+
+@pytest.mark.parametrize("name,N", [("normal", 20000), ("ma2", 20000)])
+def test_smc_f32_decisions_replayed(oracle, kabc, ctx, name, N):
+    """F32 simulators: feed the device's own costs (X after init, Xp per sweep) into the oracle's smc logic;
+    alive masks, resampling, accept decisions, theta and epsilon must then be bit-exact."""
+    cfg = dict(nparticles=N, alpha=0.9, min_r_ess=0.6, max_iterations=12)
+    osmc, dsmc = _smc_pair(oracle, kabc, ctx, name, "f32", cfg)
+    dsmc.trace_enable(True)
+    osmc.init(); dsmc.init()
+    dth, dX, dlpi, dal = dsmc.state()
+    oth, oX, olpi, oal = osmc.state()
+    assert_bits_equal(dth, oth, "init theta")
+    fin = np.isfinite(oX)
+    atol, rtol = F32_TOL[name]
+    assert (np.abs(dX[fin] - oX[fin]) <= atol + rtol * np.abs(oX[fin])).all()
+    osmc.set_state(oth, dX, olpi, oal)  # adopt the device's initial costs
+    for it in range(12):
+        sd = dsmc.iterate()
+        td = dsmc.trace()
+        osmc.set_cost_override(td["xp"])
+        so = osmc.iterate()
+        to = osmc.trace()
+        assert (to["decision"] == td["decision"]).all(), f"decisions differ at iteration {it + 1}"
+        _compare_smc_state(osmc, dsmc, f"{name} f32 replay iteration {it + 1}")
+        assert so == sd
+        if so:
+            break
+
+
+def test_smc_run_api_readme_posterior(kabc, ctx):
+    """smc(prior, cost) through the one-call C ABI; README.md:83-84 posterior: mu = 2.0 +- 0.0062, sigma = 0.0401 +- 0.00081."""
+    prior = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100))
+    for prec in ("f64", "f32"):
+        res = kabc.smc(prior, kabc.NormalMeanStd(1000, 2.0, 0.04, 50.0, precision=prec), nparticles=10000, epstol=0.012, ctx=ctx)
+        mu, sg = res.P
+        print(prec, mu, sg, res.eps, res.iterations, res.cost_evals)
+        assert res.eps <= 0.012 and res.C.shape == (10000,)
+        assert abs(mu.mean() - 2.0) < 0.002 and abs(sg.mean() - 0.04) < 0.0005
+        assert 0.0005 < sg.std() < 0.0025 and 0.0005 < mu.std() < 0.01
+        assert mu.approx(2.0) and sg.approx(0.04)
+
+
+def test_smc_argument_errors(kabc, ctx):
+    """ref src/smc.jl:107-118: same checks, same messages."""
+    prior = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100))
+    cost = kabc.NormalMeanStd()
+    cases = [(dict(min_r_ess=0.0), "min_r_ess must be > 0."), (dict(mcmc_retrys=-1), "mcmc_retrys must be >= 0."),
+             (dict(alpha=0.0), "alpha must be > 0."), (dict(r_epstol=-1.0), "r_epstol must be >= 0"),
+             (dict(mcmc_tol=-0.1), "mcmc_tol must be >= 0"), (dict(max_stretch=1.0), "max_stretch must be > 1"),
+             (dict(nparticles=6), "nparticles must be >= 7.")]
+    for kw, msg in cases:
+        with pytest.raises(kabc.KissABCError) as ei:
+            kabc.smc(prior, cost, ctx=ctx, **kw)
+        assert str(ei.value) == msg and ei.value.code == 1
+
+
+def test_smc_inf_costs_are_culled(kabc, ctx):
+    """ref test/runtests.jl:246-253: a cost that is Inf for a large share of the prior is culled by the quantile cut."""
+    prior = kabc.Factored(kabc.Uniform(-2, 2), kabc.Uniform(-1, 1))  # ~half of this box is outside the MA(2) triangle
+    res = kabc.smc(prior, kabc.MA2(100, (0.72, 0.2), precision="f64"), nparticles=4000, alpha=0.4, epstol=0.2, ctx=ctx)
+    assert np.isfinite(res.eps) and res.eps <= 0.5
+    assert np.isfinite(res.C).mean() > 0.3
+
+
+# ------------------------------------------------------------------ AIS
+def _ais_pair(O, k, ctx, name, prec, cfg_kw, ndraws=None):
+    M = models(O, k)[name]
+    kw = {} if ndraws is None else {"n": ndraws}
+    oa = O.Ais(SEED, O.make_priors(M["ospec"]), M["omodel"](**kw), O.ais_config(**cfg_kw), nthreads=8)
+    da = k.AisSession(ctx, M["kprior"](), M["kcost"](prec, **kw), k.ais_config(**cfg_kw))
+    return oa, da
+
+
+@pytest.mark.parametrize("name,N,scale,ndraws", [("normal", 64, 0.05, 200), ("normal", 11, 0.5, 50), ("ma2", 500, 0.1, 100),
+                                                  ("gk", 16, 0.5, 1000)])
+def test_ais_sweeps_f64_bit_exact(oracle, kabc, ctx, name, N, scale, ndraws):
+    """init (+retries) and every red/black sweep: ensemble, log-densities, per-walker move/partners/decision."""
+    cfg = dict(nwalkers=N, nsamples=1, scale=scale)
+    oa, da = _ais_pair(oracle, kabc, ctx, name, "f64", cfg, ndraws)
+    da.trace_enable(True)
+    oa.init(); da.init()
+    for a, b, what in zip(oa.state(), da.state(), ("theta", "lp", "ll")):
+        assert_bits_equal(b, a, f"ais init {what}")
+    assert oa.counters() == da.counters()
+    moves = set()
+    for sw in range(25):
+        oa.sweep(); da.sweep(1)
+        for a, b, what in zip(oa.state(), da.state(), ("theta", "lp", "ll")):
+            assert_bits_equal(b, a, f"ais sweep {sw} {what}")
+        to, td = oa.trace(), da.trace()
+        for key in ("move", "a", "b", "c", "decision"):
+            assert (to[key] == td[key]).all(), (key, sw)
+        for key in ("corr", "theta_p", "lp_p", "ll_p", "e"):
+            assert_bits_equal(td[key], to[key], f"ais trace {key} sweep {sw}")
+        moves |= set(np.unique(td["move"]))
+        assert oa.counters() == da.counters()
+    assert moves == {1, 2, 3}
+    assert da.counters()["accepted"] > 0
+
+
+def test_ais_run_matches_oracle_and_readme(oracle, kabc, ctx):
+    """sample(ApproxKernelizedPosterior(prior,cost,0.005), AIS(10), 1000, ntransitions=100) -- config 1 -- through
+    the one-call C ABI: bit-exact against the oracle's red/black run, and README.md:64-66 posterior."""
+    O = oracle
+    M = models(O, kabc)["normal"]
+    cfg = dict(nwalkers=10, nsamples=300, ntransitions=20, discard_initial=7, thinning=3, scale=0.05)
+    oa = O.Ais(SEED, O.make_priors(M["ospec"]), M["omodel"](100), O.ais_config(**cfg), nthreads=1)
+    ref = oa.run_parallel()
+    post = kabc.ApproxKernelizedPosterior(M["kprior"](), M["kcost"]("f64", 100), 0.05)
+    res, cnt = kabc.sample(post, kabc.AIS(10), 300, ntransitions=20, discard_initial=7, thinning=3, ctx=ctx, return_counters=True)
+    assert_bits_equal(np.vstack([p.particles for p in res]), ref, "AIS samples")
+    oc = oa.counters()
+    assert cnt["cost_evals"] == oc["cost_evals"] and cnt["accepted"] == oc["accepted"]
+
+
+def test_ais_readme_posterior_f32(kabc, ctx):
+    prior = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100))
+    post = kabc.ApproxKernelizedPosterior(prior, kabc.NormalMeanStd(1000, 2.0, 0.04, 50.0, precision="f32"), 0.005)
+    mu, sg = kabc.sample(post, kabc.AIS(64), 2000, ntransitions=60, discard_initial=640, ctx=ctx)
+    print(mu, sg)
+    assert abs(mu.mean() - 2.0) < 0.002 and abs(sg.mean() - 0.04) < 0.0005
+    assert 0.0005 < sg.std() < 0.002  # README.md:66: sigma = 0.0395 +- 0.00093
+
+
+def test_ais_errors(kabc, ctx):
+    prior = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100))
+    post = kabc.ApproxKernelizedPosterior(prior, kabc.NormalMeanStd(), 0.005)
+    with pytest.raises(kabc.KissABCError) as ei:  # ref src/KissABC.jl:43-48
+        kabc.sample(post, kabc.AIS(6), 10, ctx=ctx)
+    assert "is insufficient" in str(ei.value) and "atleast to 7" in str(ei.value)
+    # ref src/KissABC.jl:58-59 + test/runtests.jl:221-238: a prior that always leads to Inf costs exhausts the budget
+    bad = kabc.ApproxKernelizedPosterior(kabc.Factored(kabc.Uniform(3, 4), kabc.Uniform(-1, 1)), kabc.MA2(50, (0, 0)), 0.1)
+    with pytest.raises(kabc.KissABCError) as ei:
+        kabc.sample(bad, kabc.AIS(10), 10, retry_sampling=5, ctx=ctx)
+    assert ei.value.code == 4 and "Prior leads to" in str(ei.value)
+
+
+def test_deterministic_cost_reference_tests(kabc, ctx):
+    """ref test/runtests.jl:77-86: prior Normal(1,0.2), cost |mu^2+1-1.5| -> sim(res) ~ 1.5, i.e. mu ~ 0.707;
+    and :177-182 (issue #10): cost |x-1.5| with AIS(20)."""
+    pri = kabc.Normal(1, 0.2)
+    res = kabc.smc(pri, kabc.Deterministic(0, 1.5), epstol=0.1, ctx=ctx)
+    assert res.P.approx(0.707)
+    post = kabc.ApproxKernelizedPosterior(pri, kabc.Deterministic(0, 1.5), 0.001)
+    s = kabc.sample(post, kabc.AIS(12), 500, discard_initial=1000, ctx=ctx)
+    sim = kabc.Particles(s.particles ** 2 + 1)
+    assert abs(sim.mean() - 1.5) < 0.01
+    post = kabc.ApproxKernelizedPosterior(kabc.Uniform(-10, 10), kabc.Deterministic(1, 1.5), 0.01)
+    s = kabc.sample(post, kabc.AIS(20), 500, discard_initial=2000, ntransitions=5, ctx=ctx)
+    assert abs(s.mean() - 1.5) < 0.02
