@@ -887,7 +887,7 @@ int kabc_smc_get_scalars(kabc_smc_t *s, double *eps, int32_t *flag, int64_t *ite
     if (eps) *eps = c->eps;
     if (flag) *flag = c->flag;
     if (iteration) *iteration = c->iteration;
-    if (n_alive) *n_alive = c->n_alive;
+    if (n_alive) *n_alive = c->ess; /* ESS after the last cut, what the reference prints (src/smc.jl:142-143) */
     if (accepted) *accepted = (int64_t)c->accepted;
     if (cost_evals) *cost_evals = (int64_t)c->cost_evals;
     if (next_epoch) *next_epoch = c->epoch;

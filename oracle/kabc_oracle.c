@@ -265,26 +265,26 @@ static double cost_normal(const kor_model_t *m, stream_t *s0, const double *th) 
     const int n = m->n_draws;
     const double mu = th[0], sigma = th[1];
     double z[4];
+    double stackbuf[1024];
+    double *x = n <= 1024 ? stackbuf : (double *)malloc(sizeof(double) * (size_t)n);
     stream_t s = *s0;
     double sum = 0.0;
     for (int j = 0; j < n; j += 4) {
         uint32_t w0 = next_u32(&s), w1 = next_u32(&s), w2 = next_u32(&s), w3 = next_u32(&s);
         kor_normal_pair(w0, w1, &z[0], &z[1]);
         kor_normal_pair(w2, w3, &z[2], &z[3]);
-        for (int q = 0; q < 4 && j + q < n; ++q) sum += z[q] * sigma + mu;
-    }
-    double mean = sum / (double)n;
-    s = *s0;
-    double ss = 0.0;
-    for (int j = 0; j < n; j += 4) {
-        uint32_t w0 = next_u32(&s), w1 = next_u32(&s), w2 = next_u32(&s), w3 = next_u32(&s);
-        kor_normal_pair(w0, w1, &z[0], &z[1]);
-        kor_normal_pair(w2, w3, &z[2], &z[3]);
         for (int q = 0; q < 4 && j + q < n; ++q) {
-            double dx = (z[q] * sigma + mu) - mean;
-            ss += dx * dx;
+            x[j + q] = z[q] * sigma + mu;
+            sum += x[j + q];
         }
     }
+    double mean = sum / (double)n;
+    double ss = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double dx = x[j] - mean;
+        ss += dx * dx;
+    }
+    if (x != stackbuf) free(x);
     double sd = sqrt(ss / (double)(n - 1));
     double d1 = mean - m->target[0];
     double d2 = (sd - m->target[1]) * m->param[0];

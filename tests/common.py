@@ -3,12 +3,23 @@ import numpy as np
 
 SEED = 0x4B49535341424300
 
-# LV observations: a fixed synthetic trajectory on the 16-point grid (generated once by the oracle simulator
-# at theta = log(1, 0.005, 0.6), oracle seed 1, id 0, epoch 0 (kor_lv_trajectory); kept literal so oracle and device see the same targets)
-LV_TARGET_X = [107, 228, 113, 38, 50, 115, 348, 66, 15, 32, 97, 313, 129, 29, 38, 132]
-LV_TARGET_Y = [87, 149, 330, 209, 100, 65, 153, 484, 231, 99, 71, 116, 417, 268, 111, 62]
-GK_TARGET = [2.3943, 2.5691, 2.7479, 2.9994, 3.4156, 4.1956, 5.8946]  # octiles of g-and-k(3,1,2,0.5), c=0.8
-MA2_TARGET = [0.72, 0.2]  # E[tau1], E[tau2] at theta = (0.6, 0.2): th1 + th1 th2, th2
+import importlib.util as _u
+import os as _os
+
+# workload constants come from the product-side config table (pure Python constants, no CUDA involved)
+_spec = _u.spec_from_file_location("_kabc_workload_consts", _os.path.join(_os.path.dirname(_os.path.dirname(
+    _os.path.abspath(__file__))), "kissabc.jl_b200", "workloads.py"))
+
+
+def _consts():
+    src = open(_spec.origin).read()
+    ns = {}
+    exec(src[src.index("MA2_TARGET"):src.index("def normal")], ns)  # only the literal tables
+    return ns
+
+
+_c = _consts()
+LV_TARGET_X, LV_TARGET_Y, GK_TARGET, MA2_TARGET = _c["LV_TARGET_X"], _c["LV_TARGET_Y"], _c["GK_TARGET"], _c["MA2_TARGET"]
 
 
 def models(O, k):

@@ -250,7 +250,7 @@ def test_smc_argument_errors(kabc, ctx):
     prior = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100))
     cost = kabc.NormalMeanStd()
     cases = [(dict(min_r_ess=0.0), "min_r_ess must be > 0."), (dict(mcmc_retrys=-1), "mcmc_retrys must be >= 0."),
-             (dict(alpha=0.0), "alpha must be > 0."), (dict(r_epstol=-1.0), "r_epstol must be >= 0"),
+             (dict(alpha=0.0, min_r_ess=0.5), "alpha must be > 0."), (dict(r_epstol=-1.0), "r_epstol must be >= 0"),
              (dict(mcmc_tol=-0.1), "mcmc_tol must be >= 0"), (dict(max_stretch=1.0), "max_stretch must be > 1"),
              (dict(nparticles=6), "nparticles must be >= 7.")]
     for kw, msg in cases:
