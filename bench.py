@@ -140,7 +140,7 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    per_step = args.ref_budget or max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--log2-particles", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=0.0, help="seconds of CPU work per reference step (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -8,7 +8,7 @@ from ._capi import KissABCError, LIB_PATH, SYMBOLS, lib  # noqa: F401
 from .api import (AIS, ApproxKernelizedPosterior, AisSession, Context, Deterministic, DeviceCost, Factored,  # noqa: F401
                   GandK, LotkaVolterra, MA2, Normal, NormalMeanStd, Particles, SmcResult, SmcSession, Truncated,
                   Uniform, ais_config, default_context, sample, smc, smc_config)
-from . import _capi, workloads  # noqa: F401
+from . import _capi, dist, workloads  # noqa: F401
 
 __all__ = [
     "sample", "AIS", "ApproxKernelizedPosterior", "Factored", "smc", "Uniform", "Normal", "Truncated", "Particles",

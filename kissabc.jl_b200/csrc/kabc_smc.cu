@@ -1,36 +1,50 @@
 // kabc_smc.cu -- smc(prior, cost; ...) on device.  Restates src/smc.jl:92-206 of KissABC.jl 3.0.1:
-//   init                      :119-129   k_smc_init / k_smc_init_gk
-//   eps = quantile(Xs[alive]) :134       k_sel_begin + 6 x k_sel_pass  (two-rank radix select on FP64 keys, type-7 rule)
+//   init                      :119-129   k_smc_init / k_smc_init_prior + k_smc_init_gk
+//   eps = quantile(Xs[alive]) :134       k_sel_hist<0>, k_sel_hist<1>, k_sel_final  (exact two-rank bucket select on
+//                                        FP64 keys + Statistics.jl type-7 interpolation)
 //   alive cut, flag, ESS      :135-142   k_alive_cut
 //   cyclic-tiling resample    :145-153   k_alive_cut (decision + scan), k_resample_scatter, k_resample_gather
 //   propose                   :160-167   k_smc_propose  (+ prior-MH pre-test :172-175, builds the work list)
 //   simulate + accept         :176-189   k_smc_simulate / k_smc_simulate_gk
-//   retry / stop rules        :156-159,192-198   k_post_sweep, k_post_iter
+//   retry / stop rules        :156-159,192-198   post_sweep()/post_iter() run by the LAST block of the sweep kernel
 // Every scalar that steers control flow lives in SmcCtrl in device memory; the host only reads `stop`.
-// State is SoA FP64: th[k*N+i], X[i], lpi[i], alive[i]; two copies (ping-pong) for the resampling gather.
+// State is SoA FP64: th[k*N+i], X[i], lpi[i], alive[i]; two copies (ping-pong): every iteration gathers
+// (resample) or copies (no resample) into the other copy, so the host always knows which copy is current.
+//
+// Multi-GPU (one process per GPU): the state is replicated, the sweep is sharded.  Rank r proposes/simulates/
+// accepts particles [r N/G, (r+1) N/G); the updated shard rows and four counters are all-gathered (NCCL over
+// NVLink) after each sweep; quantile, cut and resample are computed redundantly from identical replicas, so no
+// scalar ever needs a broadcast.  Philox counters are keyed by the GLOBAL particle id: results are bit-identical
+// for any G.
 #include "kabc_host.hpp"
 #include "kabc_gk.cuh"
 #include "kabc_nccl.hpp"
 
 namespace kabc {
 
-int eval_cost_device(kabc_ctx *ctx, const DModel &m, const double *d_th, long long n, uint32_t first_id, uint32_t epoch,
-                     double *d_out, long long *d_ev);
-
-constexpr int SEL_MAXBINS = 4096;
+constexpr int SEL_LOG2_BINS = 12;
+constexpr int SEL_BINS = 1 << SEL_LOG2_BINS;
+constexpr int SEL_CAP = 4096; // candidates sorted exactly by one block
+constexpr int SEL_THREADS = 512;
 constexpr int SCAN_THREADS = 1024;
+
+struct RankPartial { // what a rank contributes to the sweep bookkeeping
+    unsigned long long accepted, work, events, minkey;
+};
 
 struct SmcCtrl {
     double eps, eps_prev, xmin, gamma;
-    unsigned long long xmin_key;
-    unsigned long long sel_prefix[2];
-    long long sel_rank[2];
-    long long n_alive; // number of alive particles (input of the next quantile)
-    long long ess;     // ESS = sum(alive) right after the cut (what the reference prints)
+    unsigned long long xmin_key; // running minimum over the alive costs (as an ordered key)
+    unsigned long long klo, khi, v0key, v1key;
+    long long below, cnt, r0, r1; // bucket-select bookkeeping
+    long long n_alive;            // number of alive particles (input of the next quantile)
+    long long ess;                // ESS = sum(alive) right after the cut (what the reference prints)
     unsigned long long accepted, cost_evals, events;
+    unsigned long long sw_accepted, sw_events, sw_minkey; // per-sweep partials of this rank
     long long iteration;
-    unsigned int work_count, ticket, ticket2, epoch;
-    int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log;
+    unsigned int work_count, cand_count, epoch;
+    unsigned int tk_hist, tk_final, tk_cut, tk_gather, tk_sim;
+    int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log, sel_done, bounds_known;
 };
 
 struct SmcParams { // launch constants
@@ -39,6 +53,7 @@ struct SmcParams { // launch constants
     double alpha, mcmc_tol, epstol, r_epstol, min_r_ess, max_stretch;
     long long mcmc_retrys;
     int max_iterations;
+    int rank, world;
 };
 
 struct SmcTrace {
@@ -52,7 +67,9 @@ struct SmcBufs {
     unsigned char *alive;
     double *thp, *lpip;
     unsigned int *work, *idxalive, *blockcnt, *hist;
+    unsigned long long *cand;
     SmcCtrl *ctrl;
+    RankPartial *partial; // [world]
     kabc_smc_log_t *log;
     long long log_cap;
     SmcTrace tr;
@@ -67,31 +84,57 @@ __device__ __forceinline__ double dunkey(unsigned long long k) {
     unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
     return __longlong_as_double((long long)b);
 }
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+// true for exactly one block: the last one to arrive (its reads see every other block's writes)
+__device__ __forceinline__ bool last_block(unsigned int *ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
 
 // ------------------------------------------------------------------ init, ref src/smc.jl:119-129
 template <int KIND, int PREC>
 __global__ void __launch_bounds__(256)
 k_smc_init(SmcBufs B, SmcParams P, DPriors pri, DModel m, RoundKeys rk, long long lo, long long hi) {
     long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= hi) return;
     const long long N = P.N;
-    Stream st(rk, ST_PRIOR, (uint32_t)i, 0u);
-    bool ok = true;
+    unsigned long long key = ~0ull, ev_u = 0;
+    if (i < hi) {
+        Stream st(rk, ST_PRIOR, (uint32_t)i, 0u);
+        bool ok = true;
 #pragma unroll 1
-    for (int k = 0; k < P.d; ++k) {
-        double x;
-        ok &= prior1_sample(pri.p[k], st, x);
-        B.th[0][(long long)k * N + i] = x;
+        for (int k = 0; k < P.d; ++k) {
+            double x;
+            ok &= prior1_sample(pri.p[k], st, x);
+            B.th[0][(long long)k * N + i] = x;
+        }
+        if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
+        long long ev;
+        double *thv = B.th[0];
+        double X = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, [&](int k) { return thv[(long long)k * N + i]; }, ev);
+        B.X[0][i] = X;
+        B.lpi[0][i] = prior_logpdf(pri, [&](int k) { return thv[(long long)k * N + i]; });
+        B.alive[i] = 1;
+        key = dkey(X);
+        ev_u = (unsigned long long)ev;
     }
-    if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
-    long long ev;
-    double *thv = B.th[0];
-    double X = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, [&](int k) { return thv[(long long)k * N + i]; }, ev);
-    B.X[0][i] = X;
-    B.lpi[0][i] = prior_logpdf(pri, [&](int k) { return thv[(long long)k * N + i]; });
-    B.alive[i] = 1;
-    unsigned long long e = warp_sum_u64((unsigned long long)ev);
-    if ((threadIdx.x & 31) == 0 && e) atomicAdd(&B.ctrl->events, e);
+    key = warp_min_u64(key);
+    ev_u = warp_sum_u64(ev_u);
+    if ((threadIdx.x & 31) == 0) {
+        if (key != ~0ull) atomicMin(&B.ctrl->sw_minkey, key);
+        if (ev_u) atomicAdd(&B.ctrl->sw_events, ev_u);
+    }
 }
 
 __global__ void k_smc_init_prior(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi) {
@@ -119,146 +162,258 @@ k_smc_init_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, long long lo, long
     for (long long i = lo + blockIdx.x; i < hi; i += gridDim.x) {
         const double *th = B.th[0];
         double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, th[i], th[N + i], th[2 * N + i], th[3 * N + i], gk_smem);
-        if (threadIdx.x == 0) B.X[0][i] = c;
+        if (threadIdx.x == 0) {
+            B.X[0][i] = c;
+            atomicMin(&B.ctrl->sw_minkey, dkey(c));
+        }
     }
 }
 
 __global__ void k_smc_reset(SmcBufs B, SmcParams P) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int q = t; q < 2 * SEL_MAXBINS; q += gridDim.x * blockDim.x) B.hist[q] = 0;
+    for (int q = t; q < SEL_BINS; q += gridDim.x * blockDim.x) B.hist[q] = 0;
     if (t == 0) {
         SmcCtrl *c = B.ctrl;
-        c->eps = dinf(); c->eps_prev = dinf(); c->xmin = 0; c->gamma = 0;
-        c->xmin_key = ~0ull;
+        memset(c, 0, sizeof(SmcCtrl));
+        c->eps = dinf(); c->eps_prev = dinf();
+        c->xmin_key = ~0ull; c->sw_minkey = ~0ull;
         c->n_alive = P.N; c->ess = P.N;
-        c->accepted = 0; c->cost_evals = (unsigned long long)P.N; c->events = 0;
-        c->iteration = 0; c->work_count = 0; c->ticket = 0; c->ticket2 = 0; c->epoch = 0;
-        c->flag = 0; c->resample = 0; c->stop = 0; c->cur = 0; c->err = 0; c->sweeps = 0; c->retry_done = 0;
-        c->resampled_log = 0;
+        c->cost_evals = (unsigned long long)P.N;
     }
+}
+
+// after the init kernels: fold this rank's partials (single GPU) or everybody's (after the all-gather)
+__global__ void k_smc_post_init(SmcBufs B, SmcParams P, int from_partials) {
+    SmcCtrl *c = B.ctrl;
+    if (from_partials) {
+        unsigned long long mk = ~0ull, ev = 0;
+        for (int r = 0; r < P.world; ++r) {
+            mk = B.partial[r].minkey < mk ? B.partial[r].minkey : mk;
+            ev += B.partial[r].events;
+        }
+        c->xmin_key = mk; c->events = ev;
+    } else {
+        c->xmin_key = c->sw_minkey; c->events = c->sw_events;
+    }
+    c->sw_minkey = ~0ull; c->sw_events = 0; c->sw_accepted = 0;
+}
+__global__ void k_smc_write_partial(SmcBufs B, SmcParams P) {
+    SmcCtrl *c = B.ctrl;
+    RankPartial p;
+    p.accepted = c->sw_accepted; p.work = c->work_count; p.events = c->sw_events; p.minkey = c->sw_minkey;
+    B.partial[P.rank] = p;
 }
 
 // ------------------------------------------------------------------ quantile, ref src/smc.jl:134 (Statistics type 7)
-__global__ void k_sel_begin(SmcBufs B, SmcParams P) {
-    SmcCtrl *c = B.ctrl;
-    c->iteration += 1;
-    c->eps_prev = c->eps;
-    const long long n = c->n_alive;
-    if (n <= 0) { c->err = KABC_ERR_DEGENERATE; return; }
-    // aleph = n*p + (1-p); j = clamp(trunc(aleph),1,n-1); gamma = clamp(aleph-j,0,1)
-    double aleph = xadd(xmul((double)n, P.alpha), xsub(1.0, P.alpha));
-    long long j = (long long)aleph;
-    if (j > n - 1) j = n - 1;
-    if (j < 1) j = 1;
-    double g = xsub(aleph, (double)j);
-    g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
-    c->gamma = g;
-    c->sel_rank[0] = (n == 1) ? 0 : j - 1; // 0-based rank of v[j]
-    c->sel_rank[1] = (n == 1) ? 0 : j;     // 0-based rank of v[j+1]
-    c->sel_prefix[0] = 0; c->sel_prefix[1] = 0;
-    c->xmin_key = ~0ull;
-    c->sweeps = 0; c->retry_done = 0; c->accepted = 0; c->resampled_log = 0;
+// Exact selection of the two adjacent order statistics v[j], v[j+1] by range narrowing: histogram the alive keys
+// inside [klo,khi] into 4096 equal-width key bins, keep the bins holding the two ranks, repeat; once at most
+// SEL_CAP keys remain they are compacted and sorted by one block.  Keys are the order-preserving u64 image of the
+// doubles, so bins, ranks and the result are exact (no floating point in the selection).
+struct SelRange {
+    unsigned long long klo, khi;
+    long long below, cnt, r0, r1;
+    int shift;
+};
+__device__ __forceinline__ int sel_shift(unsigned long long klo, unsigned long long khi) {
+    const unsigned long long range = khi - klo;
+    const int bl = range ? 64 - __clzll((long long)range) : 0;
+    return bl > SEL_LOG2_BINS ? bl - SEL_LOG2_BINS : 0;
+}
+// block-wide (SEL_THREADS threads): scan SEL_BINS counters, narrow the range to the bins holding ranks r0 and r1
+__device__ void sel_scan_narrow(const unsigned int *hist, bool hist_is_global, SelRange &R, unsigned int *s_scan,
+                                unsigned long long *s_res) {
+    constexpr int PER = SEL_BINS / SEL_THREADS;
+    unsigned int loc[PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int bin = threadIdx.x * PER + q;
+        loc[q] = hist_is_global ? __ldcg(&hist[bin]) : hist[bin];
+        sum += loc[q];
+    }
+    s_scan[threadIdx.x] = sum;
+    if (threadIdx.x < 4) s_res[threadIdx.x] = 0;
+    __syncthreads();
+    for (int o = 1; o < SEL_THREADS; o <<= 1) {
+        unsigned int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_scan[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const long long excl = (long long)s_scan[threadIdx.x] - sum;
+    const long long t0 = R.r0 - R.below, t1 = R.r1 - R.below;
+    long long cum = excl;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const long long nxt = cum + (long long)loc[q];
+        if (t0 >= cum && t0 < nxt) { s_res[0] = threadIdx.x * PER + q; s_res[1] = (unsigned long long)cum; }
+        if (t1 >= cum && t1 < nxt) { s_res[2] = threadIdx.x * PER + q; s_res[3] = (unsigned long long)nxt; }
+        cum = nxt;
+    }
+    __syncthreads();
+    const unsigned long long b0 = s_res[0], before = s_res[1], b1 = s_res[2], through = s_res[3];
+    const unsigned long long mask = R.shift ? ((1ull << R.shift) - 1ull) : 0ull;
+    const unsigned long long off_end = (b1 << R.shift) | mask;
+    const unsigned long long new_khi = off_end > R.khi - R.klo ? R.khi : R.klo + off_end;
+    R.klo = R.klo + (b0 << R.shift);
+    R.khi = new_khi;
+    R.below += (long long)before;
+    R.cnt = (long long)(through - before);
+    __syncthreads();
 }
 
-template <int SHIFT, int BITS, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(512) k_sel_pass(SmcBufs B, SmcParams P) {
-    constexpr int NB = 1 << BITS;
-    __shared__ unsigned int sh[2][NB];
-    __shared__ unsigned int s_scan[512];
-    __shared__ int s_last;
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P) {
+    __shared__ unsigned int sh[SEL_BINS];
+    __shared__ unsigned int s_scan[SEL_THREADS];
+    __shared__ unsigned long long s_res[4];
     SmcCtrl *c = B.ctrl;
     if (c->err) return;
-    for (int q = threadIdx.x; q < 2 * NB; q += blockDim.x) (&sh[0][0])[q] = 0;
+    SelRange R;
+    double gamma = 0.0;
+    if (PASS == 0) {
+        const long long n = c->n_alive;
+        if (n <= 0) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) c->err = KABC_ERR_DEGENERATE;
+            return;
+        }
+        // aleph = n*p + (1-p); j = clamp(trunc(aleph),1,n-1); gamma = clamp(aleph-j,0,1)
+        const double aleph = xadd(xmul((double)n, P.alpha), xsub(1.0, P.alpha));
+        long long j = (long long)aleph;
+        if (j > n - 1) j = n - 1;
+        if (j < 1) j = 1;
+        gamma = xsub(aleph, (double)j);
+        gamma = gamma < 0.0 ? 0.0 : (gamma > 1.0 ? 1.0 : gamma);
+        R.r0 = (n == 1) ? 0 : j - 1; // 0-based rank of v[j]
+        R.r1 = (n == 1) ? 0 : j;     // 0-based rank of v[j+1]
+        R.klo = c->xmin_key;
+        R.khi = (c->bounds_known && dfinite(c->eps)) ? dkey(c->eps) : ~0ull;
+        if (R.khi < R.klo) R.khi = ~0ull;
+        R.below = 0; R.cnt = n;
+    } else {
+        if (c->sel_done || c->cnt <= SEL_CAP) return;
+        R.klo = c->klo; R.khi = c->khi; R.below = c->below; R.cnt = c->cnt; R.r0 = c->r0; R.r1 = c->r1;
+    }
+    R.shift = sel_shift(R.klo, R.khi);
+    for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) sh[q] = 0;
     __syncthreads();
     const double *X = B.X[c->cur];
-    const unsigned long long p0 = c->sel_prefix[0], p1 = c->sel_prefix[1];
-    unsigned long long kmin = ~0ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += (long long)gridDim.x * blockDim.x) {
         if (!B.alive[i]) continue;
-        unsigned long long key = dkey(X[i]);
-        unsigned int digit = (unsigned int)(key >> SHIFT) & (NB - 1);
-        if constexpr (FIRST) {
-            kmin = key < kmin ? key : kmin;
-            atomicAdd(&sh[0][digit], 1u);
-            atomicAdd(&sh[1][digit], 1u);
-        } else {
-            constexpr int HS = SHIFT + BITS; // < 64 when !FIRST
-            if ((key >> HS) == (p0 >> HS)) atomicAdd(&sh[0][digit], 1u);
-            if ((key >> HS) == (p1 >> HS)) atomicAdd(&sh[1][digit], 1u);
-        }
-    }
-    if (FIRST) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, kmin, o);
-            kmin = other < kmin ? other : kmin;
-        }
-        if ((threadIdx.x & 31) == 0 && kmin != ~0ull) atomicMin(&c->xmin_key, kmin);
+        const unsigned long long key = dkey(X[i]);
+        if (key >= R.klo && key <= R.khi) atomicAdd(&sh[(key - R.klo) >> R.shift], 1u);
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < 2 * NB; q += blockDim.x) {
-        unsigned int v = (&sh[0][0])[q];
-        if (v) atomicAdd(&B.hist[(q / NB) * SEL_MAXBINS + (q % NB)], v);
+    for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) {
+        const unsigned int v = sh[q];
+        if (v) atomicAdd(&B.hist[q], v);
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&c->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // last block: locate, for both ranks, the digit whose cumulative count passes the rank
-    constexpr int PER = (NB + 511) / 512;
-    for (int r = 0; r < 2; ++r) {
-        const long long rank = c->sel_rank[r];
-        unsigned int loc[PER];
-        unsigned int sum = 0;
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            int bin = threadIdx.x * PER + q;
-            loc[q] = bin < NB ? __ldcg(&B.hist[r * SEL_MAXBINS + bin]) : 0u;
-            sum += loc[q];
+    if (!last_block(&c->tk_hist)) return;
+    sel_scan_narrow(B.hist, true, R, s_scan, s_res);
+    for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) B.hist[q] = 0;
+    if (threadIdx.x == 0) {
+        c->tk_hist = 0;
+        c->klo = R.klo; c->khi = R.khi; c->below = R.below; c->cnt = R.cnt; c->r0 = R.r0; c->r1 = R.r1;
+        c->sel_done = (R.shift == 0); // bins were single keys: klo/khi ARE v[j], v[j+1]
+        c->v0key = R.klo; c->v1key = R.khi;
+        if (PASS == 0) { // opens the iteration, ref :132-133
+            c->gamma = gamma;
+            c->iteration += 1;
+            c->eps_prev = c->eps;
+            c->sweeps = 0; c->retry_done = 0; c->accepted = 0; c->resampled_log = 0;
         }
-        s_scan[threadIdx.x] = sum;
-        __syncthreads();
-        for (int o = 1; o < 512; o <<= 1) { // inclusive Hillis-Steele scan
-            unsigned int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
-            __syncthreads();
-            s_scan[threadIdx.x] += v;
-            __syncthreads();
-        }
-        long long excl = (long long)s_scan[threadIdx.x] - sum;
-        if (rank >= excl && rank < excl + (long long)sum) {
-            long long cum = excl;
-#pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                if (rank >= cum && rank < cum + (long long)loc[q]) {
-                    c->sel_prefix[r] |= (unsigned long long)(threadIdx.x * PER + q) << SHIFT;
-                    c->sel_rank[r] = rank - cum;
-                }
-                cum += loc[q];
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_final(SmcBufs B, SmcParams P) {
+    __shared__ unsigned long long s_keys[SEL_CAP]; // candidates (sort path) or histogram (slow path)
+    __shared__ unsigned int s_scan[SEL_THREADS];
+    __shared__ unsigned long long s_res[4];
+    SmcCtrl *c = B.ctrl;
+    if (c->err) return;
+    const double *X = B.X[c->cur];
+    const bool compact = !c->sel_done && c->cnt <= SEL_CAP;
+    if (compact) {
+        const unsigned long long klo = c->klo, khi = c->khi;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        const long long nloop = (P.N + stride - 1) / stride;
+        for (long long it = 0; it < nloop; ++it) {
+            const long long i = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            unsigned long long key = 0;
+            bool in = false;
+            if (i < P.N && B.alive[i]) {
+                key = dkey(X[i]);
+                in = key >= klo && key <= khi;
+            }
+            const unsigned int ball = __ballot_sync(0xffffffffu, in);
+            if (ball) {
+                const unsigned int lane = threadIdx.x & 31;
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(&c->cand_count, (unsigned int)__popc(ball));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in) B.cand[base + __popc(ball & ((1u << lane) - 1u))] = key;
             }
         }
-        __syncthreads();
     }
-    for (int q = threadIdx.x; q < 2 * SEL_MAXBINS; q += blockDim.x) B.hist[q] = 0;
-    if (threadIdx.x == 0) {
-        c->ticket = 0;
-        if (FIRST) c->xmin = dunkey(c->xmin_key);
-        if (LAST) {
-            const double a = dunkey(c->sel_prefix[0]), b = dunkey(c->sel_prefix[1]), g = c->gamma;
-            double eps;
-            if (dfinite(a) && dfinite(b)) eps = xadd(a, xmul(g, xsub(b, a)));
-            else eps = xadd(xmul(xsub(1.0, g), a), xmul(g, b));
-            c->eps = eps;
-            c->flag = (eps > c->xmin) ? 0 : 1; // ref :136-141
+    if (!last_block(&c->tk_final)) return;
+    unsigned long long v0, v1;
+    if (c->sel_done) {
+        v0 = c->v0key; v1 = c->v1key;
+    } else if (compact) {
+        const int n = (int)c->cnt;
+        int npad = 2;
+        while (npad < n) npad <<= 1;
+        for (int q = threadIdx.x; q < npad; q += blockDim.x) s_keys[q] = q < n ? __ldcg(&B.cand[q]) : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= npad; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = s_keys[i], b = s_keys[l];
+                    if ((a > b) == up) { s_keys[i] = b; s_keys[l] = a; }
+                }
+                __syncthreads();
+            }
+        v0 = s_keys[c->r0 - c->below];
+        v1 = s_keys[c->r1 - c->below];
+    } else {
+        // rare slow path (massive ties / pathological spread): this block alone keeps narrowing over all N
+        SelRange R;
+        R.klo = c->klo; R.khi = c->khi; R.below = c->below; R.cnt = c->cnt; R.r0 = c->r0; R.r1 = c->r1;
+        unsigned int *sh = reinterpret_cast<unsigned int *>(s_keys);
+        for (;;) {
+            R.shift = sel_shift(R.klo, R.khi);
+            for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) sh[q] = 0;
+            __syncthreads();
+            for (long long i = threadIdx.x; i < P.N; i += blockDim.x) {
+                if (!B.alive[i]) continue;
+                const unsigned long long key = dkey(X[i]);
+                if (key >= R.klo && key <= R.khi) atomicAdd(&sh[(key - R.klo) >> R.shift], 1u);
+            }
+            __syncthreads();
+            const int shift = R.shift;
+            sel_scan_narrow(sh, false, R, s_scan, s_res);
+            if (shift == 0) break;
         }
+        v0 = R.klo; v1 = R.khi;
+    }
+    if (threadIdx.x == 0) {
+        const double a = dunkey(v0), b = dunkey(v1), g = c->gamma;
+        double eps;
+        if (dfinite(a) && dfinite(b)) eps = xadd(a, xmul(g, xsub(b, a)));
+        else eps = xadd(xmul(xsub(1.0, g), a), xmul(g, b));
+        c->eps = eps;
+        c->xmin = dunkey(c->xmin_key);
+        c->flag = (eps > c->xmin) ? 0 : 1; // ref :136-141
+        c->cand_count = 0;
+        c->tk_final = 0;
+        c->sel_done = 0;
     }
 }
 
 // ------------------------------------------------------------------ alive cut + ESS + resample decision, ref :136-147
 __global__ void __launch_bounds__(SCAN_THREADS) k_alive_cut(SmcBufs B, SmcParams P, int nblocks) {
     __shared__ unsigned int s_w[32];
-    __shared__ int s_last;
     SmcCtrl *c = B.ctrl;
     if (c->err) return;
     const double *X = B.X[c->cur];
@@ -272,14 +427,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_alive_cut(SmcBufs B, SmcParams
         B.alive[i] = (unsigned char)a;
     }
     unsigned int cnt = __syncthreads_count(a);
-    if (threadIdx.x == 0) {
-        B.blockcnt[blockIdx.x] = cnt;
-        __threadfence();
-        s_last = (atomicAdd(&c->ticket2, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (threadIdx.x == 0) B.blockcnt[blockIdx.x] = cnt;
+    if (!last_block(&c->tk_cut)) return;
     // last block: exclusive scan of the per-block counts (in place), total = ESS
     unsigned long long carry = 0;
     for (int base = 0; base < nblocks; base += blockDim.x) {
@@ -315,7 +464,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_alive_cut(SmcBufs B, SmcParams
         const long long ess = (long long)carry;
         c->ess = ess;
         c->n_alive = ess;
-        c->ticket2 = 0;
+        c->tk_cut = 0;
+        c->bounds_known = 1; // from now on every alive cost is <= eps
         // ref :145  alpha*ESS <= nparticles*min_r_ess, FP64, exactly these operands
         c->resample = xmul(P.alpha, (double)ess) <= xmul((double)P.N, P.min_r_ess);
         if (c->resample && ess == 0) c->err = KABC_ERR_DEGENERATE;
@@ -349,33 +499,36 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_resample_scatter(SmcBufs B, Sm
     }
 }
 
-// theta, X, lpi = (...)[idx], idx[k] = idxalive[k mod n_alive]; alive .= true.  ref :147-152
+// theta, X, lpi = (...)[idx], idx[k] = idxalive[k mod n_alive]; alive .= true (ref :147-152) -- or a plain copy when
+// the reference does not resample, so that the current buffer flips every iteration (the host needs no read-back)
 __global__ void __launch_bounds__(256) k_resample_gather(SmcBufs B, SmcParams P) {
     SmcCtrl *c = B.ctrl;
-    if (c->err || !c->resample) return;
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= P.N) return;
-    const int cur = c->cur;
-    const unsigned long long n = (unsigned long long)c->ess;
-    const unsigned int src = B.idxalive[(unsigned long long)k % n];
-    const long long N = P.N;
-    for (int q = 0; q < P.d; ++q) B.th[cur ^ 1][(long long)q * N + k] = B.th[cur][(long long)q * N + src];
-    B.X[cur ^ 1][k] = B.X[cur][src];
-    B.lpi[cur ^ 1][k] = B.lpi[cur][src];
-    B.alive[k] = 1;
-}
-
-// single thread between phases: commits the resample (buffer flip) and opens a sweep
-__global__ void k_pre_sweep(SmcBufs B, SmcParams P) {
-    SmcCtrl *c = B.ctrl;
     if (c->err) return;
-    if (c->resample) {
-        c->cur ^= 1;
-        c->n_alive = P.N;
-        c->resample = 0;
-        c->resampled_log = 1;
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cur = c->cur;
+    const int resample = c->resample;
+    if (k < P.N) {
+        const long long N = P.N;
+        long long src = k;
+        if (resample) {
+            const unsigned long long n = (unsigned long long)c->ess;
+            src = B.idxalive[(unsigned long long)k % n];
+            B.alive[k] = 1;
+        }
+        for (int q = 0; q < P.d; ++q) B.th[cur ^ 1][(long long)q * N + k] = B.th[cur][(long long)q * N + src];
+        B.X[cur ^ 1][k] = B.X[cur][src];
+        B.lpi[cur ^ 1][k] = B.lpi[cur][src];
     }
-    c->work_count = 0;
+    if (!last_block(&c->tk_gather)) return;
+    if (threadIdx.x == 0) {
+        c->tk_gather = 0;
+        c->cur = cur ^ 1;
+        if (resample) {
+            c->n_alive = P.N;
+            c->resample = 0;
+            c->resampled_log = 1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ propose, ref :160-167 and :172-175
@@ -403,15 +556,23 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
             const double *t = th + (long long)k * N;
             B.thp[(long long)k * N + i] = xadd(t[i], xmul(xsub(t[b], t[a]), sc));
         }
-        lprob = xlog(next_uniform(st));
+        const uint32_t wu = st.next();
         const double *thp = B.thp;
         lpip = prior_logpdf(pri, [&](int k) { return thp[(long long)k * N + i]; });
         if (lpip < 0.0 && !dfinite(lpip)) dec = 1;
         else {
+            // ref :174-175  lM = min(lpip - lpi + logcorr, 0); proceed iff log(rand) < lM.
+            // log(u) < 0 always (u < 1), so the logarithm is only evaluated when lM < 0 (or when tracing).
             const double lM = fmin(xadd(xsub(lpip, lpi[i]), 0.0), 0.0);
-            if (!(lprob < lM)) dec = 2;
+            bool pass = true;
+            if (!(lM >= 0.0) || B.trace_on) {
+                lprob = xlog(u01(wu));
+                pass = lprob < lM;
+            }
+            if (!pass) dec = 2;
             else { push = true; B.lpip[i] = lpip; }
         }
+        if (B.trace_on && lprob != lprob) lprob = xlog(u01(wu));
     }
     // warp-aggregated append to the work list
     unsigned int ball = __ballot_sync(0xffffffffu, push);
@@ -427,6 +588,66 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
         if (!B.alive[i]) for (int k = 0; k < P.d; ++k) B.thp[(long long)k * N + i] = dnan();
     }
 }
+
+// ------------------------------------------------------------------ sweep / iteration bookkeeping
+// ref :192 (`accepted >= mcmc_tol*nparticles && break`): folds the sweep's counters (this rank's, or every rank's
+// after the all-gather) into the control block
+__device__ void post_sweep(SmcBufs &B, const SmcParams &P, bool from_partials) {
+    SmcCtrl *c = B.ctrl;
+    unsigned long long acc = c->sw_accepted, work = c->work_count, ev = c->sw_events, mk = c->sw_minkey;
+    if (from_partials) {
+        acc = 0; work = 0; ev = 0; mk = ~0ull;
+        for (int r = 0; r < P.world; ++r) {
+            acc += B.partial[r].accepted; work += B.partial[r].work; ev += B.partial[r].events;
+            mk = B.partial[r].minkey < mk ? B.partial[r].minkey : mk;
+        }
+    }
+    c->accepted += acc;
+    c->cost_evals += work;
+    c->events += ev;
+    if (mk < c->xmin_key) c->xmin_key = mk;
+    c->sw_accepted = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->work_count = 0;
+    c->sweeps += 1;
+    c->epoch += 1;
+    if ((double)c->accepted >= xmul(P.mcmc_tol, (double)P.N)) c->retry_done = 1;
+}
+// closes an iteration, ref :194-198
+__device__ void post_iter(SmcBufs &B, const SmcParams &P) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err) { c->stop = -1; return; }
+    const double eps = c->eps, epsv = c->eps_prev;
+    int stop = 0;
+    if (xmul(2.0, fabs(xsub(epsv, eps))) < xmul(P.r_epstol, xadd(fabs(epsv), fabs(eps)))) stop = 1;
+    else if (eps <= P.epstol) stop = 2;
+    else if ((double)c->accepted < xmul(P.mcmc_tol, (double)P.N)) stop = 3;
+    else if (P.max_iterations > 0 && c->iteration >= P.max_iterations) stop = 4;
+    c->stop = stop;
+    const long long it = c->iteration;
+    if (it >= 1 && it <= B.log_cap) {
+        kabc_smc_log_t &L = B.log[it - 1];
+        L.iteration = it; L.eps = eps; L.n_alive = c->ess; L.flag = c->flag; L.resampled = c->resampled_log;
+        L.accepted = (long long)c->accepted; L.cost_evals = (long long)c->cost_evals; L.sweeps = c->sweeps;
+    }
+}
+// what the last block of a sweep kernel does.  mode bit0: fold + close the sweep here (single GPU);
+// bit1: also close the iteration (no retries pending); bit2: publish this rank's partials (multi GPU)
+__device__ __forceinline__ void sweep_epilogue(SmcBufs &B, const SmcParams &P, int mode) {
+    if (threadIdx.x != 0) return;
+    SmcCtrl *c = B.ctrl;
+    c->tk_sim = 0;
+    if (mode & 4) {
+        RankPartial p;
+        p.accepted = c->sw_accepted; p.work = c->work_count; p.events = c->sw_events; p.minkey = c->sw_minkey;
+        B.partial[P.rank] = p;
+    }
+    if (mode & 1) post_sweep(B, P, false);
+    if (mode & 2) post_iter(B, P);
+}
+__global__ void k_post_sweep_dist(SmcBufs B, SmcParams P, int close_iter) {
+    if (!(B.ctrl->err || B.ctrl->retry_done)) post_sweep(B, P, true);
+    if (close_iter) post_iter(B, P);
+}
+__global__ void k_post_iter(SmcBufs B, SmcParams P) { post_iter(B, P); }
 
 // ------------------------------------------------------------------ simulate + accept, ref :176-189
 __device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCtrl *c, long long i, double Xp,
@@ -444,34 +665,45 @@ __device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCt
 }
 
 template <int KIND, int PREC>
-__global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DModel m, RoundKeys rk) {
+__global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
     SmcCtrl *c = B.ctrl;
-    if (c->err || c->retry_done) return;
+    if (c->err || c->retry_done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
+        return;
+    }
     const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int nwork = c->work_count;
-    if ((w & ~31u) >= nwork) return; // whole warp idle
-    unsigned int acc = 0;
-    long long ev = 0;
-    if (w < nwork) {
-        const long long i = B.work[w];
-        const long long N = P.N;
-        const double *thp = B.thp;
-        double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, [&](int k) { return thp[(long long)k * N + i]; }, ev);
-        smc_accept(B, P, c, i, Xp, acc);
+    if ((w & ~31u) < nwork) {
+        unsigned int acc = 0;
+        long long ev = 0;
+        unsigned long long key = ~0ull;
+        if (w < nwork) {
+            const long long i = B.work[w];
+            const long long N = P.N;
+            const double *thp = B.thp;
+            double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, [&](int k) { return thp[(long long)k * N + i]; }, ev);
+            smc_accept(B, P, c, i, Xp, acc);
+            if (acc) key = dkey(Xp);
+        }
+        const unsigned int nacc = __popc(__ballot_sync(0xffffffffu, acc));
+        const unsigned long long e = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
+        if (nacc) key = warp_min_u64(key);
+        if ((threadIdx.x & 31) == 0) {
+            if (nacc) { atomicAdd(&c->sw_accepted, (unsigned long long)nacc); atomicMin(&c->sw_minkey, key); }
+            if (e) atomicAdd(&c->sw_events, e);
+        }
     }
-    unsigned int nacc = __popc(__ballot_sync(0xffffffffu, acc));
-    unsigned long long e = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
-    if ((threadIdx.x & 31) == 0) {
-        if (nacc) atomicAdd(&c->accepted, (unsigned long long)nacc);
-        if (e) atomicAdd(&c->events, e);
-    }
+    if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk) {
+__global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
     SmcCtrl *c = B.ctrl;
-    if (c->err || c->retry_done) return;
+    if (c->err || c->retry_done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
+        return;
+    }
     const unsigned int nwork = c->work_count;
     const long long N = P.N;
     for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -481,37 +713,32 @@ __global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcPa
         if (threadIdx.x == 0) {
             unsigned int acc = 0;
             smc_accept(B, P, c, i, Xp, acc);
-            if (acc) atomicAdd(&c->accepted, 1ull);
+            if (acc) { atomicAdd(&c->sw_accepted, 1ull); atomicMin(&c->sw_minkey, dkey(Xp)); }
         }
     }
+    if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
 }
 
-// closes a sweep, ref :192 (`accepted >= mcmc_tol*nparticles && break`)
-__global__ void k_post_sweep(SmcBufs B, SmcParams P) {
-    SmcCtrl *c = B.ctrl;
-    if (c->err || c->retry_done) return;
-    c->cost_evals += c->work_count;
-    c->sweeps += 1;
-    c->epoch += 1;
-    if ((double)c->accepted >= xmul(P.mcmc_tol, (double)P.N)) c->retry_done = 1;
-}
-
-// closes an iteration, ref :194-198
-__global__ void k_post_iter(SmcBufs B, SmcParams P) {
-    SmcCtrl *c = B.ctrl;
-    if (c->err) { c->stop = -1; return; }
-    const double eps = c->eps, epsv = c->eps_prev;
-    int stop = 0;
-    if (xmul(2.0, fabs(xsub(epsv, eps))) < xmul(P.r_epstol, xadd(fabs(epsv), fabs(eps)))) stop = 1;
-    else if (eps <= P.epstol) stop = 2;
-    else if ((double)c->accepted < xmul(P.mcmc_tol, (double)P.N)) stop = 3;
-    else if (P.max_iterations > 0 && c->iteration >= P.max_iterations) stop = 4;
-    c->stop = stop;
-    const long long it = c->iteration;
-    if (it >= 1 && it <= B.log_cap) {
-        kabc_smc_log_t &L = B.log[it - 1];
-        L.iteration = it; L.eps = eps; L.n_alive = c->ess; L.flag = c->flag; L.resampled = c->resampled_log;
-        L.accepted = (long long)c->accepted; L.cost_evals = (long long)c->cost_evals; L.sweeps = c->sweeps;
+// recount after kabc_smc_set_state: alive count and the running minimum
+__global__ void k_recount(SmcBufs B, long long N) {
+    __shared__ unsigned long long s_n, s_min;
+    if (threadIdx.x == 0) { s_n = 0; s_min = ~0ull; }
+    __syncthreads();
+    const double *X = B.X[B.ctrl->cur];
+    unsigned long long n = 0, mk = ~0ull;
+    for (long long i = threadIdx.x; i < N; i += blockDim.x)
+        if (B.alive[i]) {
+            n += 1;
+            const unsigned long long k = dkey(X[i]);
+            mk = k < mk ? k : mk;
+        }
+    n = warp_sum_u64(n);
+    mk = warp_min_u64(mk);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_n, n); atomicMin(&s_min, mk); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        B.ctrl->n_alive = (long long)s_n; B.ctrl->ess = (long long)s_n;
+        B.ctrl->xmin_key = s_min; B.ctrl->bounds_known = 0;
     }
 }
 
@@ -530,7 +757,9 @@ struct kabc_smc {
     DevBuf<double> th0, th1, X0, X1, lpi0, lpi1, thp, lpip;
     DevBuf<unsigned char> alive;
     DevBuf<unsigned int> work, idxalive, blockcnt, hist;
+    DevBuf<unsigned long long> cand;
     DevBuf<SmcCtrl> ctrl;
+    DevBuf<RankPartial> partial;
     DevBuf<kabc_smc_log_t> log;
     // trace
     DevBuf<long long> ta, tb;
@@ -538,6 +767,7 @@ struct kabc_smc {
     DevBuf<unsigned char> tdec;
     SmcCtrl *h_ctrl = nullptr; // pinned
     long long lo = 0, hi = 0;  // owned particle range [lo,hi) of this rank
+    int cur = 0;               // host mirror of ctrl->cur (flips once per iteration)
     bool inited = false;
     long long launches = 0;
     int nblocks_scan = 0;
@@ -558,7 +788,7 @@ static int smc_check_cfg(const kabc_smc_config_t *cfg, int d) {
     return KABC_OK;
 }
 
-#define SMC_LAUNCHED(s) do { (s)->launches += 1; (s)->ctx->launches += 1; } while (0)
+#define SMC_LAUNCHED(s, n) do { (s)->launches += (n); (s)->ctx->launches += (n); } while (0)
 
 template <int KIND>
 static void smc_launch_init_t(kabc_smc *s) {
@@ -568,18 +798,18 @@ static void smc_launch_init_t(kabc_smc *s) {
         k_smc_init<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk, s->lo, s->hi);
     else
         k_smc_init<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk, s->lo, s->hi);
-    SMC_LAUNCHED(s);
+    SMC_LAUNCHED(s, 1);
 }
 
 template <int KIND>
-static void smc_launch_sim_t(kabc_smc *s) {
+static void smc_launch_sim_t(kabc_smc *s, int mode) {
     const long long n = s->hi - s->lo;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (s->model.precision == KABC_F64)
-        k_smc_simulate<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk);
+        k_smc_simulate<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk, mode);
     else
-        k_smc_simulate<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk);
-    SMC_LAUNCHED(s);
+        k_smc_simulate<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk, mode);
+    SMC_LAUNCHED(s, 1);
 }
 
 static int smc_gk_grid(kabc_smc *s, size_t &smem) {
@@ -589,24 +819,25 @@ static int smc_gk_grid(kabc_smc *s, size_t &smem) {
     return (int)(n < cap ? n : cap);
 }
 
-// all-gather of the ranks' shards of the current state (multi-GPU only): theta planes, X, lpi
+// all-gather of the ranks' shards of state copy `cur` (theta planes, X, lpi) and of the per-rank partials
 static int smc_allgather_state(kabc_smc *s, int cur) {
     kabc_ctx *ctx = s->ctx;
-    if (ctx->world == 1) return KABC_OK;
     const long long N = s->P.N, per = N / ctx->world;
     if (int rc = nccl_group_start()) return rc;
     for (int k = 0; k < s->P.d; ++k)
         if (int rc = nccl_allgather_inplace(ctx, s->B.th[cur] + (long long)k * N, (size_t)per * 8)) return rc;
     if (int rc = nccl_allgather_inplace(ctx, s->B.X[cur], (size_t)per * 8)) return rc;
     if (int rc = nccl_allgather_inplace(ctx, s->B.lpi[cur], (size_t)per * 8)) return rc;
+    if (int rc = nccl_allgather_inplace(ctx, s->B.partial, sizeof(RankPartial))) return rc;
     if (int rc = nccl_group_end()) return rc;
     return KABC_OK;
 }
 
 static int smc_enqueue_init(kabc_smc *s) {
     kabc_ctx *ctx = s->ctx;
-    k_smc_reset<<<8, 1024, 0, ctx->stream>>>(s->B, s->P);
-    SMC_LAUNCHED(s);
+    k_smc_reset<<<4, 1024, 0, ctx->stream>>>(s->B, s->P);
+    SMC_LAUNCHED(s, 1);
+    s->cur = 0;
     switch (s->model.kind) {
     case KABC_MODEL_NORMAL_MEANSTD: smc_launch_init_t<KABC_MODEL_NORMAL_MEANSTD>(s); break;
     case KABC_MODEL_MA2_AUTOCOV: smc_launch_init_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
@@ -615,7 +846,6 @@ static int smc_enqueue_init(kabc_smc *s) {
     case KABC_MODEL_GK_OCTILE: {
         const long long n = s->hi - s->lo;
         k_smc_init_prior<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
-        SMC_LAUNCHED(s);
         size_t smem;
         int grid = smc_gk_grid(s, smem);
         if (s->model.precision == KABC_F64) {
@@ -625,54 +855,57 @@ static int smc_enqueue_init(kabc_smc *s) {
             KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_init_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_smc_init_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, s->lo, s->hi);
         }
-        SMC_LAUNCHED(s);
+        SMC_LAUNCHED(s, 2);
         break;
     }
     }
     KABC_CUDA_TRY(cudaGetLastError());
     if (ctx->world > 1) {
+        k_smc_write_partial<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
         if (int rc = smc_allgather_state(s, 0)) return rc;
         KABC_CUDA_TRY(cudaMemsetAsync(s->B.alive, 1, (size_t)s->P.N, ctx->stream));
-        // events were counted per rank
-        if (int rc = nccl_allreduce_sum_u64(ctx, &s->B.ctrl->events, 1)) return rc;
+        k_smc_post_init<<<1, 1, 0, ctx->stream>>>(s->B, s->P, 1);
+        SMC_LAUNCHED(s, 2);
+    } else {
+        k_smc_post_init<<<1, 1, 0, ctx->stream>>>(s->B, s->P, 0);
+        SMC_LAUNCHED(s, 1);
     }
+    KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
 
-// one MCMC sweep: propose -> (work list) -> simulate+accept -> bookkeeping
-static int smc_enqueue_sweep(kabc_smc *s) {
+// one MCMC sweep: propose -> (work list) -> simulate+accept (+ bookkeeping in the last block)
+static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     kabc_ctx *ctx = s->ctx;
     const long long n = s->hi - s->lo;
-    k_pre_sweep<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
-    SMC_LAUNCHED(s);
+    const bool dist = ctx->world > 1;
+    const int mode = dist ? 4 : (1 | (close_iter ? 2 : 0));
     k_smc_propose<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
-    SMC_LAUNCHED(s);
+    SMC_LAUNCHED(s, 1);
     switch (s->model.kind) {
-    case KABC_MODEL_NORMAL_MEANSTD: smc_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s); break;
-    case KABC_MODEL_MA2_AUTOCOV: smc_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
-    case KABC_MODEL_LV_SSA: smc_launch_sim_t<KABC_MODEL_LV_SSA>(s); break;
-    case KABC_MODEL_DETERMINISTIC: smc_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s); break;
+    case KABC_MODEL_NORMAL_MEANSTD: smc_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s, mode); break;
+    case KABC_MODEL_MA2_AUTOCOV: smc_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s, mode); break;
+    case KABC_MODEL_LV_SSA: smc_launch_sim_t<KABC_MODEL_LV_SSA>(s, mode); break;
+    case KABC_MODEL_DETERMINISTIC: smc_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s, mode); break;
     case KABC_MODEL_GK_OCTILE: {
         size_t smem;
         int grid = smc_gk_grid(s, smem);
         if (s->model.precision == KABC_F64) {
             KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_smc_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
+            k_smc_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
         } else {
             KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_smc_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
+            k_smc_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
         }
-        SMC_LAUNCHED(s);
+        SMC_LAUNCHED(s, 1);
         break;
     }
     }
-    if (ctx->world > 1) {
-        // the sweep only touched this rank's shard of the current buffers; `cur` is known on the host
-        // only through ctrl, so gather both candidates' current one: cur is mirrored in s->h_cur
-        return set_error(KABC_ERR_STATE, "internal: multi-GPU sweep must go through smc_enqueue_sweep_dist");
+    if (dist) {
+        if (int rc = smc_allgather_state(s, s->cur)) return rc;
+        k_post_sweep_dist<<<1, 1, 0, ctx->stream>>>(s->B, s->P, close_iter ? 1 : 0);
+        SMC_LAUNCHED(s, 1);
     }
-    k_post_sweep<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
-    SMC_LAUNCHED(s);
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
@@ -680,21 +913,17 @@ static int smc_enqueue_sweep(kabc_smc *s) {
 static int smc_enqueue_cut(kabc_smc *s) {
     kabc_ctx *ctx = s->ctx;
     const long long N = s->P.N;
-    int sel_blocks = (int)((N + 512 * 8 - 1) / (512 * 8));
+    int sel_blocks = (int)((N + SEL_THREADS * 8 - 1) / (SEL_THREADS * 8));
     if (sel_blocks > ctx->sm_count * 2) sel_blocks = ctx->sm_count * 2;
     if (sel_blocks < 1) sel_blocks = 1;
-    k_sel_begin<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
-    k_sel_pass<52, 12, true, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
-    k_sel_pass<41, 11, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
-    k_sel_pass<30, 11, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
-    k_sel_pass<20, 10, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
-    k_sel_pass<10, 10, false, false><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
-    k_sel_pass<0, 10, false, true><<<sel_blocks, 512, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_hist<0><<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_hist<1><<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    k_sel_final<<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
     k_alive_cut<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P, s->nblocks_scan);
     k_resample_scatter<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P);
     k_resample_gather<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P);
-    s->launches += 10;
-    ctx->launches += 10;
+    s->cur ^= 1;
+    SMC_LAUNCHED(s, 6);
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
@@ -714,19 +943,20 @@ static int smc_ctrl_error(kabc_smc *s) {
 }
 
 // one body of the reference's `while true` loop
-static int smc_enqueue_iteration(kabc_smc *s, bool sync_retries) {
+static int smc_enqueue_iteration(kabc_smc *s) {
     if (int rc = smc_enqueue_cut(s)) return rc;
     const long long retry_n = 1 + s->P.mcmc_retrys;
+    if (retry_n == 1) return smc_enqueue_sweep(s, true);
     for (long long r = 0; r < retry_n; ++r) {
-        if (int rc = smc_enqueue_sweep(s)) return rc;
-        if (sync_retries && r + 1 < retry_n) {
+        if (int rc = smc_enqueue_sweep(s, false)) return rc;
+        if (r + 1 < retry_n) {
             // ref :192 -- leave the retry loop as soon as enough moves were accepted
             if (int rc = smc_read_ctrl(s)) return rc;
             if (s->h_ctrl->err || s->h_ctrl->retry_done) break;
         }
     }
     k_post_iter<<<1, 1, 0, s->ctx->stream>>>(s->B, s->P);
-    SMC_LAUNCHED(s);
+    SMC_LAUNCHED(s, 1);
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
@@ -749,6 +979,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->P.N = N; s->P.d = d; s->P.alpha = cfg->alpha; s->P.mcmc_tol = cfg->mcmc_tol; s->P.epstol = cfg->epstol;
     s->P.r_epstol = cfg->r_epstol; s->P.min_r_ess = cfg->min_r_ess; s->P.max_stretch = cfg->max_stretch;
     s->P.mcmc_retrys = cfg->mcmc_retrys; s->P.max_iterations = cfg->max_iterations;
+    s->P.rank = ctx->rank; s->P.world = ctx->world;
     s->lo = N / ctx->world * ctx->rank;
     s->hi = N / ctx->world * (ctx->rank + 1);
     s->nblocks_scan = (int)((N + SCAN_THREADS - 1) / SCAN_THREADS);
@@ -758,7 +989,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     A(s->th0.alloc(nd)); A(s->th1.alloc(nd)); A(s->thp.alloc(nd));
     A(s->X0.alloc(N)); A(s->X1.alloc(N)); A(s->lpi0.alloc(N)); A(s->lpi1.alloc(N)); A(s->lpip.alloc(N));
     A(s->alive.alloc(N)); A(s->work.alloc(N)); A(s->idxalive.alloc(N)); A(s->blockcnt.alloc(s->nblocks_scan));
-    A(s->hist.alloc(2 * SEL_MAXBINS)); A(s->ctrl.alloc(1));
+    A(s->hist.alloc(SEL_BINS)); A(s->cand.alloc(SEL_CAP)); A(s->ctrl.alloc(1)); A(s->partial.alloc(ctx->world));
     const long long log_cap = 1 << 16;
     A(s->log.alloc(log_cap));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_ctrl, sizeof(SmcCtrl));
@@ -770,7 +1001,8 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->B.th[0] = s->th0.p; s->B.th[1] = s->th1.p; s->B.X[0] = s->X0.p; s->B.X[1] = s->X1.p;
     s->B.lpi[0] = s->lpi0.p; s->B.lpi[1] = s->lpi1.p; s->B.alive = s->alive.p; s->B.thp = s->thp.p;
     s->B.lpip = s->lpip.p; s->B.work = s->work.p; s->B.idxalive = s->idxalive.p; s->B.blockcnt = s->blockcnt.p;
-    s->B.hist = s->hist.p; s->B.ctrl = s->ctrl.p; s->B.log = s->log.p; s->B.log_cap = log_cap;
+    s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p; s->B.partial = s->partial.p;
+    s->B.log = s->log.p; s->B.log_cap = log_cap;
     memset(&s->B.tr, 0, sizeof s->B.tr);
     s->B.trace_on = 0;
     KABC_CUDA_TRY(cudaMemsetAsync(s->ctrl.p, 0, sizeof(SmcCtrl), ctx->stream));
@@ -790,7 +1022,6 @@ int kabc_smc_destroy(kabc_smc_t *s) {
 int kabc_smc_init(kabc_smc_t *s) {
     if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
-    if (s->ctx->world > 1) return set_error(KABC_ERR_STATE, "multi-rank smc is not wired in this build step");
     if (int rc = smc_enqueue_init(s)) return rc;
     if (int rc = smc_read_ctrl(s)) return rc;
     if (int rc = smc_ctrl_error(s)) return rc;
@@ -802,7 +1033,7 @@ int kabc_smc_iterate(kabc_smc_t *s, int *stop) {
     if (!s || !stop) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
     if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_smc_init must be called first");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
-    if (int rc = smc_enqueue_iteration(s, true)) return rc;
+    if (int rc = smc_enqueue_iteration(s)) return rc;
     if (int rc = smc_read_ctrl(s)) return rc;
     if (int rc = smc_ctrl_error(s)) return rc;
     *stop = s->h_ctrl->stop;
@@ -817,7 +1048,7 @@ int kabc_smc_iterate_n(kabc_smc_t *s, int n, int ignore_stop, int *done, float *
     KABC_CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     int it = 0;
     for (; it < n; ++it) {
-        if (int rc = smc_enqueue_iteration(s, !ignore_stop)) return rc;
+        if (int rc = smc_enqueue_iteration(s)) return rc;
         if (!ignore_stop) {
             if (int rc = smc_read_ctrl(s)) return rc;
             if (int rc = smc_ctrl_error(s)) return rc;
@@ -835,8 +1066,7 @@ int kabc_smc_iterate_n(kabc_smc_t *s, int n, int ignore_stop, int *done, float *
 int kabc_smc_get_state(kabc_smc_t *s, double *theta, double *X, double *lpi, uint8_t *alive) {
     if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
-    if (int rc = smc_read_ctrl(s)) return rc;
-    const int cur = s->h_ctrl->cur;
+    const int cur = s->cur;
     const size_t N = (size_t)s->P.N;
     cudaStream_t st = s->ctx->stream;
     if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(theta, s->B.th[cur], 8 * N * s->P.d, cudaMemcpyDeviceToHost, st));
@@ -847,33 +1077,18 @@ int kabc_smc_get_state(kabc_smc_t *s, double *theta, double *X, double *lpi, uin
     return KABC_OK;
 }
 
-__global__ void k_count_alive(SmcBufs B, long long N) {
-    __shared__ unsigned long long s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    unsigned long long n = 0;
-    for (long long i = threadIdx.x; i < N; i += blockDim.x) n += B.alive[i];
-    n = warp_sum_u64(n);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_n, n);
-    __syncthreads();
-    if (threadIdx.x == 0) { B.ctrl->n_alive = (long long)s_n; B.ctrl->ess = (long long)s_n; }
-}
-
 int kabc_smc_set_state(kabc_smc_t *s, const double *theta, const double *X, const double *lpi, const uint8_t *alive) {
     if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
-    if (int rc = smc_read_ctrl(s)) return rc;
-    const int cur = s->h_ctrl->cur;
+    const int cur = s->cur;
     const size_t N = (size_t)s->P.N;
     cudaStream_t st = s->ctx->stream;
     if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.th[cur], theta, 8 * N * s->P.d, cudaMemcpyHostToDevice, st));
     if (X) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.X[cur], X, 8 * N, cudaMemcpyHostToDevice, st));
     if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.lpi[cur], lpi, 8 * N, cudaMemcpyHostToDevice, st));
-    if (alive) {
-        KABC_CUDA_TRY(cudaMemcpyAsync(s->B.alive, alive, N, cudaMemcpyHostToDevice, st));
-        k_count_alive<<<1, 1024, 0, st>>>(s->B, s->P.N);
-        SMC_LAUNCHED(s);
-    }
+    if (alive) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.alive, alive, N, cudaMemcpyHostToDevice, st));
+    k_recount<<<1, 1024, 0, st>>>(s->B, s->P.N);
+    SMC_LAUNCHED(s, 1);
     KABC_CUDA_TRY(cudaStreamSynchronize(st));
     return KABC_OK;
 }

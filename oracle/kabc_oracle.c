@@ -515,7 +515,9 @@ struct kor_smc {
     uint8_t *tdec;
     double eps;
     int flag;
-    int64_t iteration, n_alive, accepted, cost_evals, events;
+    int64_t iteration, n_alive, accepted, cost_evals, events, sweeps;
+    double eps_prev;
+    int resampled;
     uint32_t next_epoch;
     const double *override_xp;
     kor_smc_log_t *log;
@@ -597,7 +599,7 @@ int kor_smc_init(kor_smc_t *s) {
 }
 
 /* ref: src/smc.jl:160-191 -- one synchronous MCMC sweep with epoch e */
-static void smc_sweep(kor_smc_t *s, uint32_t e) {
+static void smc_sweep(kor_smc_t *s, uint32_t e, int64_t lo, int64_t hi, int64_t *out_acc, int64_t *out_evals, int64_t *out_events) {
     const int64_t N = s->N;
     const int d = s->d;
     const double eps = s->eps;
@@ -605,7 +607,7 @@ static void smc_sweep(kor_smc_t *s, uint32_t e) {
     const double sqNp = sqrt((double)d);
     /* phase A (ref :160-167): proposals from the pre-sweep ensemble */
 #pragma omp parallel for schedule(static) num_threads(s->nthreads)
-    for (int64_t i = 0; i < N; ++i) {
+    for (int64_t i = lo; i < hi; ++i) {
         s->tdec[i] = 0;
         s->ta[i] = s->tb[i] = -1;
         s->tz[i] = s->tlprob[i] = s->tlpip[i] = s->txp[i] = NAN;
@@ -628,7 +630,7 @@ static void smc_sweep(kor_smc_t *s, uint32_t e) {
     /* phase B (ref :168-191) */
     int64_t acc = 0, evals = 0, events = 0;
 #pragma omp parallel for schedule(dynamic, 64) num_threads(s->nthreads) reduction(+ : acc, evals, events)
-    for (int64_t i = 0; i < N; ++i) {
+    for (int64_t i = lo; i < hi; ++i) {
         if (!s->alive[i]) continue;
         double thp[16];
         for (int k = 0; k < d; ++k) thp[k] = s->thp[(int64_t)k * N + i];
@@ -652,18 +654,19 @@ static void smc_sweep(kor_smc_t *s, uint32_t e) {
         s->tdec[i] = 4;
         acc += 1;
     }
-    s->accepted += acc;
-    s->cost_evals += evals;
-    s->events += events;
+    *out_acc = acc;
+    *out_evals = evals;
+    *out_events = events;
 }
 
-int kor_smc_iterate(kor_smc_t *s, int *stop) {
+/* the `while true` body in three parts so that a sharded (multi-rank) schedule can be emulated:
+ * cut (ref :132-153) ; [sweep over a shard ; commit of the summed counters]* (ref :156-193) ; finish (ref :194-198) */
+int kor_smc_cut(kor_smc_t *s) {
     const int64_t N = s->N;
     const int d = s->d;
     const kor_smc_config_t *c = &s->cfg;
-    *stop = 0;
     s->iteration += 1;
-    double epsv = s->eps;
+    s->eps_prev = s->eps;
     /* ref :134 quantile(Xs[alive], alpha) and :136 minimum(Xs[alive]) */
     int64_t na = 0;
     double *xa = s->X2;
@@ -684,7 +687,7 @@ int kor_smc_iterate(kor_smc_t *s, int *stop) {
     s->eps = eps;
     s->flag = flag;
     s->n_alive = ess;
-    int resampled = 0;
+    s->resampled = 0;
     /* ref :145-153 */
     if (c->alpha * (double)ess <= (double)N * c->min_r_ess) {
         if (ess == 0) return fail("resampling with zero alive particles");
@@ -702,31 +705,51 @@ int kor_smc_iterate(kor_smc_t *s, int *stop) {
         tmp = s->X; s->X = s->X2; s->X2 = tmp;
         tmp = s->lpi; s->lpi = s->lpi2; s->lpi2 = tmp;
         memset(s->alive, 1, (size_t)N);
-        resampled = 1;
+        s->resampled = 1;
     }
-    /* ref :156-193 */
-    s->accepted = 0;
-    int64_t sweeps = 0;
-    for (int64_t r = 0; r < 1 + c->mcmc_retrys; ++r) {
-        smc_sweep(s, s->next_epoch);
-        s->next_epoch += 1;
-        sweeps += 1;
-        if ((double)s->accepted >= c->mcmc_tol * (double)N) break;
-    }
+    s->accepted = 0; /* ref :156 */
+    s->sweeps = 0;
+    return 0;
+}
+void kor_smc_sweep_range(kor_smc_t *s, int64_t lo, int64_t hi, int64_t *acc, int64_t *evals, int64_t *events) {
+    smc_sweep(s, s->next_epoch, lo, hi, acc, evals, events);
+}
+/* returns 1 when the retry loop should stop (ref :192) */
+int kor_smc_sweep_commit(kor_smc_t *s, int64_t acc, int64_t evals, int64_t events) {
+    s->accepted += acc;
+    s->cost_evals += evals;
+    s->events += events;
+    s->next_epoch += 1;
+    s->sweeps += 1;
+    return (double)s->accepted >= s->cfg.mcmc_tol * (double)s->N;
+}
+int kor_smc_finish(kor_smc_t *s, int *stop) {
+    const kor_smc_config_t *c = &s->cfg;
+    const double eps = s->eps, epsv = s->eps_prev;
+    *stop = 0;
     if (s->nlog == s->caplog) {
         s->caplog = s->caplog ? 2 * s->caplog : 64;
         s->log = (kor_smc_log_t *)realloc(s->log, sizeof(kor_smc_log_t) * (size_t)s->caplog);
     }
     kor_smc_log_t *L = &s->log[s->nlog++];
-    L->iteration = s->iteration; L->eps = eps; L->n_alive = ess; L->flag = flag; L->resampled = resampled;
-    L->accepted = s->accepted; L->cost_evals = s->cost_evals; L->sweeps = sweeps;
-    if (c->verbose) fprintf(stderr, "(iteration, eps, ESS) = (%lld, %.17g, %lld)\n", (long long)s->iteration, eps, (long long)ess);
+    L->iteration = s->iteration; L->eps = eps; L->n_alive = s->n_alive; L->flag = s->flag; L->resampled = s->resampled;
+    L->accepted = s->accepted; L->cost_evals = s->cost_evals; L->sweeps = s->sweeps;
+    if (c->verbose) fprintf(stderr, "(iteration, eps, ESS) = (%lld, %.17g, %lld)\n", (long long)s->iteration, eps, (long long)s->n_alive);
     /* ref :194-198 */
     if (2.0 * fabs(epsv - eps) < c->r_epstol * (fabs(epsv) + fabs(eps))) *stop = 1;
     else if (eps <= c->epstol) *stop = 2;
-    else if ((double)s->accepted < c->mcmc_tol * (double)N) *stop = 3;
+    else if ((double)s->accepted < c->mcmc_tol * (double)s->N) *stop = 3;
     else if (c->max_iterations > 0 && s->iteration >= c->max_iterations) *stop = 4;
     return 0;
+}
+int kor_smc_iterate(kor_smc_t *s, int *stop) {
+    if (kor_smc_cut(s)) return 1;
+    for (int64_t r = 0; r < 1 + s->cfg.mcmc_retrys; ++r) {
+        int64_t acc, evals, events;
+        kor_smc_sweep_range(s, 0, s->N, &acc, &evals, &events);
+        if (kor_smc_sweep_commit(s, acc, evals, events)) break;
+    }
+    return kor_smc_finish(s, stop);
 }
 int kor_smc_run(kor_smc_t *s) {
     if (kor_smc_init(s)) return 1;

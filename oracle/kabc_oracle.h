@@ -123,6 +123,11 @@ int kor_smc_init(kor_smc_t *s);
 /* one pass of the `while true` body; *stop = 0 continue, 1 r_epstol, 2 epstol, 3 acceptance, 4 max_iterations */
 int kor_smc_iterate(kor_smc_t *s, int *stop);
 int kor_smc_run(kor_smc_t *s);
+/* kor_smc_iterate in parts, for emulating the sharded multi-rank schedule (tests/test_dist_gloo.py) */
+int kor_smc_cut(kor_smc_t *s);
+void kor_smc_sweep_range(kor_smc_t *s, int64_t lo, int64_t hi, int64_t *acc, int64_t *evals, int64_t *events);
+int kor_smc_sweep_commit(kor_smc_t *s, int64_t acc, int64_t evals, int64_t events);
+int kor_smc_finish(kor_smc_t *s, int *stop);
 /* replay hook: costs for the NEXT sweeps are taken from xp[i] instead of simulated (NULL = off) */
 void kor_smc_set_cost_override(kor_smc_t *s, const double *xp);
 void kor_smc_get_state(const kor_smc_t *s, double *theta_soa, double *X, double *lpi, uint8_t *alive);

@@ -115,6 +115,10 @@ def lib():
     L.kor_smc_init.argtypes = [vp]
     L.kor_smc_iterate.argtypes = [vp, C.POINTER(C.c_int)]
     L.kor_smc_run.argtypes = [vp]
+    L.kor_smc_cut.argtypes = [vp]
+    L.kor_smc_sweep_range.argtypes = [vp, C.c_int64, C.c_int64, i64p, i64p, i64p]
+    L.kor_smc_sweep_commit.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
+    L.kor_smc_finish.argtypes = [vp, C.POINTER(C.c_int)]
     L.kor_smc_set_cost_override.argtypes = [vp, dp]
     L.kor_smc_get_state.argtypes = [vp, dp, dp, dp, u8p]
     L.kor_smc_set_state.argtypes = [vp, dp, dp, dp, u8p]
@@ -245,6 +249,24 @@ class Smc:
     def run(self):
         if self.L.kor_smc_run(self.h):
             raise OracleError(self.L.kor_last_error().decode())
+
+    # kor_smc_iterate in parts (sharded-schedule emulation)
+    def cut(self):
+        if self.L.kor_smc_cut(self.h):
+            raise OracleError(self.L.kor_last_error().decode())
+
+    def sweep_range(self, lo, hi):
+        v = [C.c_int64() for _ in range(3)]
+        self.L.kor_smc_sweep_range(self.h, lo, hi, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def sweep_commit(self, acc, evals, events):
+        return bool(self.L.kor_smc_sweep_commit(self.h, acc, evals, events))
+
+    def finish(self):
+        stop = C.c_int(0)
+        self.L.kor_smc_finish(self.h, C.byref(stop))
+        return stop.value
 
     def set_cost_override(self, xp):
         if xp is None:

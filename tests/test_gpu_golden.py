@@ -1,0 +1,69 @@
+"""GPU vs the committed golden vectors (tests/golden/golden_v1.json): an anchor that does not need the oracle .so."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import SEED
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.json")
+
+
+def fh(s):
+    return float.fromhex(s)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def test_costs_match_golden(kabc, ctx, golden):
+    W = kabc.workloads
+    mk = {"normal": W.normal, "ma2": W.ma2, "gk": W.gk, "lv": W.lv}
+    for key, v in golden["costs"].items():
+        name, nd = key.rsplit("_", 1)
+        _, cost = mk[name]("f64", int(nd))
+        th = np.array([fh(x) for x in v["theta"]]).reshape(v["shape"])
+        c = ctx.eval_cost(cost, th, first_id=5, epoch=9)
+        assert [float(x).hex() for x in c] == v["cost"], key
+
+
+def test_smc_run_matches_golden(kabc, ctx, golden):
+    prior, cost = kabc.workloads.normal("f64", 100)
+    s = kabc.SmcSession(ctx, prior, cost, kabc.smc_config(nparticles=256, max_iterations=12))
+    s.init()
+    while not s.iterate():
+        pass
+    g = golden["smc_normal_256"]
+    log = s.log()
+    assert [float(r["eps"]).hex() for r in log] == g["eps"]
+    assert [r["n_alive"] for r in log] == g["n_alive"] and [r["accepted"] for r in log] == g["accepted"]
+    th, X, _, _ = s.state()
+    assert [float(x).hex() for x in th[:, :8].ravel()] == g["theta_first8"]
+    assert [float(x).hex() for x in X[:8]] == g["X_first8"]
+    assert float(th.sum()).hex() == g["theta_sum"] and s.scalars()["cost_evals"] == g["cost_evals"]
+
+
+def test_ais_run_matches_golden(kabc, ctx, golden):
+    prior, cost = kabc.workloads.normal("f64", 100)
+    post = kabc.ApproxKernelizedPosterior(prior, cost, 0.05)
+    res, cnt = kabc.sample(post, kabc.AIS(12), 40, ntransitions=5, discard_initial=3, thinning=2, ctx=ctx, return_counters=True)
+    out = np.vstack([p.particles for p in res])
+    assert [float(x).hex() for x in out.ravel()] == golden["ais_normal_12"]["samples"]
+    assert cnt["cost_evals"] == golden["ais_normal_12"]["counters"]["cost_evals"]
+    assert cnt["accepted"] == golden["ais_normal_12"]["counters"]["accepted"]
+
+
+def test_select_handles_ties_and_infinities(kabc, ctx):
+    """bucket select edge cases: all-equal costs (slow path), many +Inf, tiny populations."""
+    # deterministic cost |theta - 1.5| with a 2-point-like prior -> massive ties after resampling
+    post_prior = kabc.Uniform(1.4999999, 1.5000001)
+    res = kabc.smc(post_prior, kabc.Deterministic(1, 1.5), nparticles=5000, alpha=0.5, max_iterations=30, ctx=ctx)
+    assert np.isfinite(res.eps) and res.eps >= 0 and len(res.P) > 0
+    # smallest legal population
+    res = kabc.smc(kabc.Normal(1, 0.2), kabc.Deterministic(0, 1.5), nparticles=4, max_iterations=5, ctx=ctx)
+    assert res.C.shape == (4,)
