@@ -1,0 +1,100 @@
+# KissABCCuda.jl -- thin Julia shim over libkissabc_cuda.so (include/kissabc_cuda.h).
+# NOT executed in this repository's CI (no Julia in the build image); every call it makes is mirrored 1:1 by the
+# tested Python ctypes host (kissabc.jl_b200/api.py).  Drop next to KissABC.jl and `using KissABCCuda`.
+#
+# It adds methods to the reference's own entry points so existing scripts keep working:
+#     smc(prior, cost::DeviceCost; kw...)                                  (ref src/smc.jl:92-206)
+#     sample(ApproxKernelizedPosterior(prior, cost::DeviceCost, eps), AIS(N), Ns; kw...)   (ref src/KissABC.jl:35-94)
+module KissABCCuda
+
+using KissABC, Distributions, MonteCarloMeasurements
+import KissABC: smc, sample, AIS, ApproxKernelizedPosterior, Factored
+
+const LIB = get(ENV, "KISSABC_CUDA_LIB", joinpath(@__DIR__, "..", "libkissabc_cuda.so"))
+
+# ---- PODs, same layout as the header
+struct KabcPrior
+    kind::Int32; _pad::Int32
+    p0::Float64; p1::Float64; lo::Float64; hi::Float64
+end
+struct KabcModel
+    kind::Int32; precision::Int32; n_draws::Int32; n_target::Int32
+    target::NTuple{32,Float64}; param::NTuple{8,Float64}
+end
+struct KabcSmcConfig
+    nparticles::Int64; alpha::Float64; mcmc_retrys::Int64; mcmc_tol::Float64; epstol::Float64
+    r_epstol::Float64; min_r_ess::Float64; max_stretch::Float64; verbose::Int32; max_iterations::Int32
+end
+struct KabcAisConfig
+    nwalkers::Int64; nsamples::Int64; ntransitions::Int64; discard_initial::Int64; thinning::Int64
+    retry_sampling::Int64; scale::Float64
+end
+struct KabcSmcLog
+    iteration::Int64; eps::Float64; n_alive::Int64; flag::Int32; resampled::Int32
+    accepted::Int64; cost_evals::Int64; sweeps::Int64
+end
+
+# ---- the registered device costs that replace the `cost` closure
+abstract type DeviceCost end
+pad(v, n) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, n)
+struct NormalMeanStd <: DeviceCost; n::Int; mean::Float64; std::Float64; weight::Float64; f32::Bool; end
+NormalMeanStd(; n=1000, mean=2.0, std=0.04, weight=50.0, f32=true) = NormalMeanStd(n, mean, std, weight, f32)
+pod(c::NormalMeanStd) = KabcModel(0, c.f32, c.n, 2, pad((c.mean, c.std), 32), pad((c.weight,), 8))
+struct MA2 <: DeviceCost; n::Int; target::NTuple{2,Float64}; f32::Bool; end
+pod(c::MA2) = KabcModel(1, c.f32, c.n, 2, pad(c.target, 32), pad((), 8))
+struct GandK <: DeviceCost; n::Int; target::NTuple{7,Float64}; c::Float64; f32::Bool; end
+pod(c::GandK) = KabcModel(2, c.f32, c.n, 7, pad(c.target, 32), pad((c.c,), 8))
+struct LotkaVolterra <: DeviceCost; target::Vector{Float64}; x0::Float64; y0::Float64; T::Float64; max_events::Int; f32::Bool; end
+pod(c::LotkaVolterra) = KabcModel(3, c.f32, 0, length(c.target), pad(c.target, 32),
+                                  pad((c.x0, c.y0, c.T, length(c.target) ÷ 2, c.max_events), 8))
+
+pod(d::Uniform) = KabcPrior(0, 0, d.a, d.b, d.a, d.b)
+pod(d::Normal) = KabcPrior(1, 0, d.μ, d.σ, -Inf, Inf)
+pod(d::Truncated{<:Normal}) = KabcPrior(2, 0, d.untruncated.μ, d.untruncated.σ, d.lower, d.upper)
+pods(p::Factored) = KabcPrior[pod(q) for q in p.p]
+pods(p::UnivariateDistribution) = KabcPrior[pod(p)]
+
+lasterror() = unsafe_string(ccall((:kabc_last_error, LIB), Cstring, ()))
+check(rc) = rc == 0 || error(lasterror())       # the reference raises ErrorException: same here
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(; device=0, seed=UInt64(0x4B49535341424300))
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:kabc_ctx_create, LIB), Cint, (Cint, UInt64, Ref{Ptr{Cvoid}}), device, seed, r))
+        c = new(r[]); finalizer(x -> ccall((:kabc_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c); c
+    end
+end
+const DEFAULT = Ref{Union{Nothing,Context}}(nothing)
+ctx() = (DEFAULT[] === nothing && (DEFAULT[] = Context()); DEFAULT[])
+
+bundle(θ::Matrix{Float64}) = (P = [Particles(θ[:, k]) for k in 1:size(θ, 2)]; length(P) == 1 ? P[1] : P)
+
+function smc(prior::Distribution, cost::DeviceCost; nparticles::Int=100, alpha=0.95, mcmc_retrys::Int=0,
+             mcmc_tol=0.015, epstol=0.0, r_epstol=(1 - alpha)^1.5 / 50, min_r_ess=alpha^2, max_stretch=2.0,
+             verbose::Bool=false, parallel::Bool=false, context::Context=ctx())
+    pr = pods(prior); d = length(pr); N = nparticles
+    cfg = KabcSmcConfig(N, alpha, mcmc_retrys, mcmc_tol, epstol, r_epstol, min_r_ess, max_stretch, verbose, 0)
+    θ = Matrix{Float64}(undef, N, d); alive = Vector{UInt8}(undef, N); C = Vector{Float64}(undef, N)
+    ϵ = Ref(0.0); it = Ref{Int64}(0); ev = Ref{Int64}(0); log = Vector{KabcSmcLog}(undef, 1 << 16)
+    check(ccall((:kabc_smc_run, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{KabcPrior}, Cint, Ref{KabcModel}, Ref{KabcSmcConfig}, Ptr{Float64}, Ptr{UInt8},
+                 Ptr{Float64}, Ref{Float64}, Ref{Int64}, Ref{Int64}, Ptr{KabcSmcLog}, Int64),
+                context.h, pr, d, pod(cost), cfg, θ, alive, C, ϵ, it, ev, log, length(log)))
+    verbose && foreach(r -> println("(iteration, ϵ, ESS) = ", (r.iteration, r.eps, r.n_alive)), log[1:it[]])
+    (P = bundle(θ[alive .== 1, :]), C = C, ϵ = ϵ[])            # ref src/smc.jl:200-205
+end
+
+function sample(model::ApproxKernelizedPosterior{<:Any,<:DeviceCost}, spl::AIS, Ns::Integer; ntransitions::Int=1,
+                discard_initial::Int=0, thinning::Int=1, retry_sampling::Int=100, context::Context=ctx(), kwargs...)
+    pr = pods(model.prior); d = length(pr)
+    cfg = KabcAisConfig(spl.nparticles, Ns, ntransitions, discard_initial, thinning, retry_sampling, model.scale)
+    out = Matrix{Float64}(undef, Ns, d); ev = Ref{Int64}(0); acc = Ref{Int64}(0)
+    check(ccall((:kabc_ais_run, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{KabcPrior}, Cint, Ref{KabcModel}, Ref{KabcAisConfig}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+                context.h, pr, d, pod(model.cost), cfg, out, ev, acc))
+    bundle(out)                                                  # ref src/KissABC.jl:82-94
+end
+
+export DeviceCost, NormalMeanStd, MA2, GandK, LotkaVolterra, Context
+end # module
