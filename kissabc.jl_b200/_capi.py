@@ -64,7 +64,7 @@ SYMBOLS = [
     "kabc_ctx_create_dist", "kabc_ctx_destroy", "kabc_ctx_info", "kabc_prior_logpdf", "kabc_prior_sample",
     "kabc_eval_cost", "kabc_eval_cost_device", "kabc_smc_run", "kabc_smc_create", "kabc_smc_destroy",
     "kabc_smc_init", "kabc_smc_iterate", "kabc_smc_iterate_n", "kabc_smc_get_state", "kabc_smc_set_state",
-    "kabc_smc_get_scalars", "kabc_smc_get_log", "kabc_smc_kernel_launches", "kabc_smc_trace_enable",
+    "kabc_smc_get_scalars", "kabc_smc_get_log", "kabc_smc_kernel_launches", "kabc_smc_profile_iteration", "kabc_smc_trace_enable",
     "kabc_smc_get_trace", "kabc_ais_run", "kabc_ais_create", "kabc_ais_destroy", "kabc_ais_init",
     "kabc_ais_sweep", "kabc_ais_get_state", "kabc_ais_set_state", "kabc_ais_get_counters",
     "kabc_ais_kernel_launches", "kabc_ais_trace_enable", "kabc_ais_get_trace", "kabc_microbench",
@@ -110,6 +110,7 @@ def lib():
     L.kabc_smc_get_log.restype = C.c_int64
     L.kabc_smc_kernel_launches.argtypes = [vp]
     L.kabc_smc_kernel_launches.restype = C.c_int64
+    L.kabc_smc_profile_iteration.argtypes = [vp, fp, C.c_int, ip]
     L.kabc_smc_trace_enable.argtypes = [vp, C.c_int]
     L.kabc_smc_get_trace.argtypes = [vp, i64p, i64p, dp, dp, dp, dp, u8p, dp]
     L.kabc_ais_run.argtypes = [vp, C.POINTER(PriorT), C.c_int, C.POINTER(ModelT), C.POINTER(AisConfigT), dp, i64p, i64p]

@@ -365,6 +365,15 @@ class SmcSession:
     def kernel_launches(self) -> int:
         return int(self.L.kabc_smc_kernel_launches(self.h))
 
+    def profile_iteration(self) -> dict:
+        """one iteration with CUDA events between its kernels: warm per-kernel microseconds"""
+        buf = (C.c_float * 16)()
+        n = C.c_int()
+        K.check(self.L.kabc_smc_profile_iteration(self.h, buf, 16, C.byref(n)))
+        names = ["sel_hist0", "sel_hist1", "sel_final", "alive_cut", "resample_scatter", "resample_gather", "propose",
+                 "simulate", "allgather_post"]
+        return {names[i]: float(buf[i]) for i in range(n.value)}
+
     def trace_enable(self, on=True):
         K.check(self.L.kabc_smc_trace_enable(self.h, int(on)))
 

@@ -303,6 +303,47 @@ __global__ void __launch_bounds__(256) k_microbench(RoundKeys rk, int iters, flo
         }
         double s = s0 + s1;
         if (s == 12345.678) sink_d[0] = s;
+    } else if (KIND == 12) { // Philox + the four u32->f32 conversions only (isolates I2FP)
+        float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int it = 0; it < iters; ++it) {
+            uint32_t w0, w1, w2, w3;
+            philox4x32_10(rk, (uint32_t)it, tid, 0u, 12u, w0, w1, w2, w3);
+            s0 += __uint2float_rn(w0); s1 += __uint2float_rn(w1); s2 += __uint2float_rn(w2); s3 += __uint2float_rn(w3);
+        }
+        float s = (s0 + s1) + (s2 + s3);
+        if (s == 12345.678f) sink_f[0] = s;
+    } else if (KIND == 13) { // Box-Muller with mantissa-trick conversions (no I2FP): 23-bit uniforms
+        float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int it = 0; it < iters; ++it) {
+            uint32_t w[4];
+            philox4x32_10(rk, (uint32_t)it, tid, 0u, 13u, w[0], w[1], w[2], w[3]);
+            float z[4];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float f1 = __uint_as_float(0x3f800000u | (w[2 * q] >> 9));     // [1,2)
+                float f2 = __uint_as_float(0x3f800000u | (w[2 * q + 1] >> 9)); // [1,2)
+                float u1 = __fsub_rn(2.0f, f1);                                // (0,1]
+                float ang = __fmaf_rn(f2, 6.2831853071795865f, -6.2831853071795865f);
+                float r = mufu_sqrt(__fmul_rn(mufu_lg2(u1), -1.3862943611198906f));
+                z[2 * q] = __fmul_rn(r, mufu_cos(ang));
+                z[2 * q + 1] = __fmul_rn(r, mufu_sin(ang));
+            }
+            s0 += z[0]; s1 += z[1]; s2 += z[2]; s3 += z[3];
+        }
+        float s = (s0 + s1) + (s2 + s3);
+        if (s == 12345.678f) sink_f[0] = s;
+    } else if (KIND == 14) { // Box-Muller, I2FP kept, no accumulation FADD chain differences: MUFU count halved (lg2+sqrt only)
+        float s0 = 0, s1 = 0;
+        for (int it = 0; it < iters; ++it) {
+            uint32_t w0, w1, w2, w3;
+            philox4x32_10(rk, (uint32_t)it, tid, 0u, 14u, w0, w1, w2, w3);
+            float u1 = __fmaf_rn(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+            float u2 = __fmaf_rn(__uint2float_rn(w2), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+            s0 += mufu_sqrt(__fmul_rn(mufu_lg2(u1), -1.3862943611198906f)) * __uint_as_float(0x3f800000u | (w1 >> 9));
+            s1 += mufu_sqrt(__fmul_rn(mufu_lg2(u2), -1.3862943611198906f)) * __uint_as_float(0x3f800000u | (w3 >> 9));
+        }
+        float s = s0 + s1;
+        if (s == 12345.678f) sink_f[0] = s;
     }
 }
 
@@ -453,7 +494,7 @@ int kabc_eval_cost(kabc_ctx_t *ctx, const kabc_model_t *model, int d, const doub
 }
 
 int kabc_microbench(kabc_ctx_t *ctx, int kind, double *out_rate, float *out_ms) {
-    if (!ctx || kind < 0 || kind > 11) return set_error(KABC_ERR_INVALID_ARG, "bad argument");
+    if (!ctx || kind < 0 || kind > 14) return set_error(KABC_ERR_INVALID_ARG, "bad argument");
     KABC_CUDA_TRY(cudaSetDevice(ctx->device));
     DevBuf<float> sf;
     DevBuf<double> sd;
@@ -466,13 +507,14 @@ int kabc_microbench(kabc_ctx_t *ctx, int kind, double *out_rate, float *out_ms) 
     if (kind == 9) { iters = 1024; ops_per_iter = 4.0; }
     if (kind == 10) { iters = 1024; ops_per_iter = 4.0; }
     if (kind == 11) { iters = 64; ops_per_iter = 4.0; }
+    if (kind >= 12) { iters = 1024; ops_per_iter = 4.0; }
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         KABC_CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
         switch (kind) {
 #define KABC_MB(K) case K: k_microbench<K><<<blocks, threads, 0, ctx->stream>>>(ctx->rk, iters, sf.p, sd.p); break;
             KABC_MB(0) KABC_MB(1) KABC_MB(2) KABC_MB(3) KABC_MB(4) KABC_MB(5) KABC_MB(6) KABC_MB(7) KABC_MB(8) KABC_MB(9)
-            KABC_MB(10) KABC_MB(11)
+            KABC_MB(10) KABC_MB(11) KABC_MB(12) KABC_MB(13) KABC_MB(14)
 #undef KABC_MB
         }
         KABC_CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -62,8 +62,15 @@ struct SmcTrace {
     unsigned char *dec;
 };
 
+constexpr int KABC_MAX_PEERS = 16;
+
 struct SmcBufs {
+    // the six state arrays live in ONE slab per rank: copy c at slab + c*(d+2)*N = [th (d*N) | X (N) | lpi (N)]
     double *th[2], *X[2], *lpi[2];
+    // peer-memory replicas (multi GPU): peer[r] is rank r's slab mapped into this process (cudaIpc over NVLink);
+    // n_peers == 0 -> no direct pushes (single GPU, or the NCCL all-gather fallback)
+    double *peer[KABC_MAX_PEERS];
+    int n_peers;
     unsigned char *alive;
     double *thp, *lpip;
     unsigned int *work, *idxalive, *blockcnt, *hist;
@@ -656,10 +663,25 @@ __device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCt
     const int cur = c->cur;
     const bool reject = c->flag ? (Xp > c->eps) : (Xp >= c->eps);
     if (!reject) {
+        const double lp = B.lpip[i];
         for (int k = 0; k < P.d; ++k) B.th[cur][(long long)k * N + i] = B.thp[(long long)k * N + i];
         B.X[cur][i] = Xp;
-        B.lpi[cur][i] = B.lpip[i];
+        B.lpi[cur][i] = lp;
         acc = 1;
+        // multi GPU: push the accepted row straight into every peer's replica (NVLink stores, overlapped with the
+        // other warps' simulation); the per-sweep NCCL all-gather of the 32-byte partials is the barrier after which
+        // the replicas are read again
+        if (B.n_peers > 0) {
+            const long long base = (long long)cur * (P.d + 2) * N;
+            for (int r = 0; r < B.n_peers; ++r) {
+                if (r == P.rank) continue;
+                double *q = B.peer[r] + base;
+                for (int k = 0; k < P.d; ++k) q[(long long)k * N + i] = B.thp[(long long)k * N + i];
+                q[(long long)P.d * N + i] = Xp;
+                q[(long long)(P.d + 1) * N + i] = lp;
+            }
+            __threadfence_system();
+        }
     }
     if (B.trace_on) { B.tr.xp[i] = Xp; B.tr.dec[i] = reject ? 3 : 4; }
 }
@@ -754,7 +776,9 @@ struct kabc_smc {
     SmcParams P;
     kabc_smc_config_t cfg;
     SmcBufs B;
-    DevBuf<double> th0, th1, X0, X1, lpi0, lpi1, thp, lpip;
+    DevBuf<double> slab, thp, lpip; // slab = both copies of [th | X | lpi]
+    std::vector<void *> peer_maps;  // cudaIpcOpenMemHandle mappings to close
+    bool p2p = false;               // accepted rows are pushed into the peers' slabs (else: NCCL all-gather)
     DevBuf<unsigned char> alive;
     DevBuf<unsigned int> work, idxalive, blockcnt, hist;
     DevBuf<unsigned long long> cand;
@@ -771,6 +795,15 @@ struct kabc_smc {
     bool inited = false;
     long long launches = 0;
     int nblocks_scan = 0;
+    // optional warm per-kernel timing of one iteration (kabc_smc_profile_iteration)
+    std::vector<cudaEvent_t> *prof = nullptr;
+    void mark() {
+        if (!prof) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        prof->push_back(e);
+    }
 };
 
 static int smc_check_cfg(const kabc_smc_config_t *cfg, int d) {
@@ -819,17 +852,69 @@ static int smc_gk_grid(kabc_smc *s, size_t &smem) {
     return (int)(n < cap ? n : cap);
 }
 
-// all-gather of the ranks' shards of state copy `cur` (theta planes, X, lpi) and of the per-rank partials
-static int smc_allgather_state(kabc_smc *s, int cur) {
+// all-gather of the per-rank partials and -- unless the rows were already pushed through peer memory -- of the
+// ranks' shards of state copy `cur` (theta planes, X, lpi)
+static int smc_allgather_state(kabc_smc *s, int cur, bool rows) {
     kabc_ctx *ctx = s->ctx;
     const long long N = s->P.N, per = N / ctx->world;
     if (int rc = nccl_group_start()) return rc;
-    for (int k = 0; k < s->P.d; ++k)
-        if (int rc = nccl_allgather_inplace(ctx, s->B.th[cur] + (long long)k * N, (size_t)per * 8)) return rc;
-    if (int rc = nccl_allgather_inplace(ctx, s->B.X[cur], (size_t)per * 8)) return rc;
-    if (int rc = nccl_allgather_inplace(ctx, s->B.lpi[cur], (size_t)per * 8)) return rc;
+    if (rows) {
+        for (int k = 0; k < s->P.d; ++k)
+            if (int rc = nccl_allgather_inplace(ctx, s->B.th[cur] + (long long)k * N, (size_t)per * 8)) return rc;
+        if (int rc = nccl_allgather_inplace(ctx, s->B.X[cur], (size_t)per * 8)) return rc;
+        if (int rc = nccl_allgather_inplace(ctx, s->B.lpi[cur], (size_t)per * 8)) return rc;
+    }
     if (int rc = nccl_allgather_inplace(ctx, s->B.partial, sizeof(RankPartial))) return rc;
     if (int rc = nccl_group_end()) return rc;
+    return KABC_OK;
+}
+
+// Map every peer's state slab into this process (cudaIpc; NVLink P2P).  The 64-byte handles travel through the
+// NCCL communicator the context already owns, so the host language needs no extra plumbing.  On any failure the
+// handle stays in the all-gather mode (s->p2p = false): same results, more traffic.
+static int smc_attach_peers(kabc_smc *s) {
+    kabc_ctx *ctx = s->ctx;
+    const int world = ctx->world;
+    s->p2p = false;
+    s->B.n_peers = 0;
+    if (world == 1 || world > KABC_MAX_PEERS) return KABC_OK;
+    const char *env = getenv("KABC_NO_P2P");
+    const bool want = !(env && env[0] == '1');
+    std::vector<cudaIpcMemHandle_t> handles(world);
+    memset(handles.data(), 0, sizeof(cudaIpcMemHandle_t) * world);
+    int ok = want ? 1 : 0;
+    if (ok && cudaIpcGetMemHandle(&handles[ctx->rank], s->slab.p) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    DevBuf<unsigned char> dh;
+    DevBuf<unsigned long long> dok;
+    KABC_CUDA_TRY(dh.alloc(sizeof(cudaIpcMemHandle_t) * world));
+    KABC_CUDA_TRY(dok.alloc(1));
+    KABC_CUDA_TRY(cudaMemcpyAsync(dh.p + sizeof(cudaIpcMemHandle_t) * ctx->rank, &handles[ctx->rank], sizeof(cudaIpcMemHandle_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = nccl_allgather_inplace(ctx, dh.p, sizeof(cudaIpcMemHandle_t))) return rc;
+    KABC_CUDA_TRY(cudaMemcpyAsync(handles.data(), dh.p, sizeof(cudaIpcMemHandle_t) * world, cudaMemcpyDeviceToHost, ctx->stream));
+    KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<void *> maps(world, nullptr);
+    for (int r = 0; ok && r < world; ++r) {
+        if (r == ctx->rank) { maps[r] = s->slab.p; continue; }
+        if (cudaIpcOpenMemHandle(&maps[r], handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // every rank must take the same path: agree through a sum
+    unsigned long long okv = (unsigned long long)ok;
+    KABC_CUDA_TRY(cudaMemcpyAsync(dok.p, &okv, 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = nccl_allreduce_sum_u64(ctx, dok.p, 1)) return rc;
+    KABC_CUDA_TRY(cudaMemcpyAsync(&okv, dok.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if ((int)okv == world) {
+        for (int r = 0; r < world; ++r) {
+            s->B.peer[r] = (double *)maps[r];
+            if (r != ctx->rank) s->peer_maps.push_back(maps[r]);
+        }
+        s->B.n_peers = world;
+        s->p2p = true;
+    } else {
+        for (int r = 0; r < world; ++r)
+            if (r != ctx->rank && maps[r]) cudaIpcCloseMemHandle(maps[r]);
+    }
     return KABC_OK;
 }
 
@@ -862,7 +947,7 @@ static int smc_enqueue_init(kabc_smc *s) {
     KABC_CUDA_TRY(cudaGetLastError());
     if (ctx->world > 1) {
         k_smc_write_partial<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
-        if (int rc = smc_allgather_state(s, 0)) return rc;
+        if (int rc = smc_allgather_state(s, 0, true)) return rc;
         KABC_CUDA_TRY(cudaMemsetAsync(s->B.alive, 1, (size_t)s->P.N, ctx->stream));
         k_smc_post_init<<<1, 1, 0, ctx->stream>>>(s->B, s->P, 1);
         SMC_LAUNCHED(s, 2);
@@ -882,6 +967,12 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     const int mode = dist ? 4 : (1 | (close_iter ? 2 : 0));
     k_smc_propose<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
     SMC_LAUNCHED(s, 1);
+    if (s->p2p) {
+        // barrier: every rank has finished writing (resample gather) and reading (propose) the current copy before
+        // any peer starts pushing accepted rows into it
+        if (int rc = nccl_allgather_inplace(ctx, s->B.partial, sizeof(RankPartial))) return rc;
+    }
+    s->mark();
     switch (s->model.kind) {
     case KABC_MODEL_NORMAL_MEANSTD: smc_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s, mode); break;
     case KABC_MODEL_MA2_AUTOCOV: smc_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s, mode); break;
@@ -901,10 +992,12 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
         break;
     }
     }
+    s->mark();
     if (dist) {
-        if (int rc = smc_allgather_state(s, s->cur)) return rc;
+        if (int rc = smc_allgather_state(s, s->cur, !s->p2p)) return rc;
         k_post_sweep_dist<<<1, 1, 0, ctx->stream>>>(s->B, s->P, close_iter ? 1 : 0);
         SMC_LAUNCHED(s, 1);
+        s->mark();
     }
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
@@ -916,12 +1009,19 @@ static int smc_enqueue_cut(kabc_smc *s) {
     int sel_blocks = (int)((N + SEL_THREADS * 8 - 1) / (SEL_THREADS * 8));
     if (sel_blocks > ctx->sm_count * 2) sel_blocks = ctx->sm_count * 2;
     if (sel_blocks < 1) sel_blocks = 1;
+    s->mark();
     k_sel_hist<0><<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    s->mark();
     k_sel_hist<1><<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    s->mark();
     k_sel_final<<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    s->mark();
     k_alive_cut<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P, s->nblocks_scan);
+    s->mark();
     k_resample_scatter<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    s->mark();
     k_resample_gather<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P);
+    s->mark();
     s->cur ^= 1;
     SMC_LAUNCHED(s, 6);
     KABC_CUDA_TRY(cudaGetLastError());
@@ -986,8 +1086,8 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     const size_t nd = (size_t)N * d;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    A(s->th0.alloc(nd)); A(s->th1.alloc(nd)); A(s->thp.alloc(nd));
-    A(s->X0.alloc(N)); A(s->X1.alloc(N)); A(s->lpi0.alloc(N)); A(s->lpi1.alloc(N)); A(s->lpip.alloc(N));
+    const size_t copy_elems = nd + 2 * (size_t)N; // [th | X | lpi]
+    A(s->slab.alloc(2 * copy_elems)); A(s->thp.alloc(nd)); A(s->lpip.alloc(N));
     A(s->alive.alloc(N)); A(s->work.alloc(N)); A(s->idxalive.alloc(N)); A(s->blockcnt.alloc(s->nblocks_scan));
     A(s->hist.alloc(SEL_BINS)); A(s->cand.alloc(SEL_CAP)); A(s->ctrl.alloc(1)); A(s->partial.alloc(ctx->world));
     const long long log_cap = 1 << 16;
@@ -998,14 +1098,26 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
         return set_error(KABC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
     memset(s->h_ctrl, 0, sizeof(SmcCtrl));
-    s->B.th[0] = s->th0.p; s->B.th[1] = s->th1.p; s->B.X[0] = s->X0.p; s->B.X[1] = s->X1.p;
-    s->B.lpi[0] = s->lpi0.p; s->B.lpi[1] = s->lpi1.p; s->B.alive = s->alive.p; s->B.thp = s->thp.p;
+    for (int c = 0; c < 2; ++c) {
+        s->B.th[c] = s->slab.p + (size_t)c * copy_elems;
+        s->B.X[c] = s->B.th[c] + nd;
+        s->B.lpi[c] = s->B.X[c] + N;
+    }
+    memset(s->B.peer, 0, sizeof s->B.peer);
+    s->B.n_peers = 0;
+    s->B.alive = s->alive.p; s->B.thp = s->thp.p;
     s->B.lpip = s->lpip.p; s->B.work = s->work.p; s->B.idxalive = s->idxalive.p; s->B.blockcnt = s->blockcnt.p;
     s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p; s->B.partial = s->partial.p;
     s->B.log = s->log.p; s->B.log_cap = log_cap;
     memset(&s->B.tr, 0, sizeof s->B.tr);
     s->B.trace_on = 0;
     KABC_CUDA_TRY(cudaMemsetAsync(s->ctrl.p, 0, sizeof(SmcCtrl), ctx->stream));
+    if (int rc = smc_attach_peers(s)) {
+        std::string keep = g_last_error;
+        kabc_smc_destroy(s);
+        g_last_error = keep;
+        return rc;
+    }
     *out = s;
     return KABC_OK;
 }
@@ -1014,6 +1126,7 @@ int kabc_smc_destroy(kabc_smc_t *s) {
     if (!s) return KABC_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    for (void *m : s->peer_maps) cudaIpcCloseMemHandle(m);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     delete s;
     return KABC_OK;
@@ -1061,6 +1174,27 @@ int kabc_smc_iterate_n(kabc_smc_t *s, int n, int ignore_stop, int *done, float *
     if (done) *done = it;
     if (out_ms) KABC_CUDA_TRY(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
     return KABC_OK;
+}
+
+int kabc_smc_profile_iteration(kabc_smc_t *s, float *out_us, int cap, int *out_n) {
+    if (!s || !out_us || !out_n) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
+    if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_smc_init must be called first");
+    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    std::vector<cudaEvent_t> evs;
+    s->prof = &evs;
+    int rc = smc_enqueue_iteration(s);
+    s->prof = nullptr;
+    if (!rc) rc = smc_read_ctrl(s);
+    int n = 0;
+    for (size_t q = 1; q < evs.size(); ++q) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evs[q - 1], evs[q]);
+        if (n < cap) out_us[n++] = ms * 1e3f;
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    *out_n = n;
+    if (rc) return rc;
+    return smc_ctrl_error(s);
 }
 
 int kabc_smc_get_state(kabc_smc_t *s, double *theta, double *X, double *lpi, uint8_t *alive) {
