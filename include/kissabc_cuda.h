@@ -169,7 +169,7 @@ int kabc_smc_get_scalars(kabc_smc_t *smc, double *eps, int32_t *flag, int64_t *i
 int64_t kabc_smc_get_log(kabc_smc_t *smc, kabc_smc_log_t *log, int64_t cap);
 int64_t kabc_smc_kernel_launches(kabc_smc_t *smc);
 /* one iteration with CUDA events between its kernels: warm per-kernel times in microseconds, in launch order
- * (hist0, hist1, final, cut, scatter, gather, propose, simulate [, all-gather+post]) */
+ * (hist0, hist1, final, cut, scatter, gather+propose, simulate [, barrier+post]) */
 int kabc_smc_profile_iteration(kabc_smc_t *smc, float *out_us, int cap, int *out_n);
 /* replay hooks: record, for the next sweeps, the variates and decisions each particle used so that the CPU
  * oracle can replay them through the reference logic (north_star "Philox uniforms replayed").

@@ -370,8 +370,8 @@ class SmcSession:
         buf = (C.c_float * 16)()
         n = C.c_int()
         K.check(self.L.kabc_smc_profile_iteration(self.h, buf, 16, C.byref(n)))
-        names = ["sel_hist0", "sel_hist1", "sel_final", "alive_cut", "resample_scatter", "resample_gather", "propose",
-                 "simulate", "allgather_post"]
+        names = ["sel_hist0", "sel_hist1", "sel_final", "alive_cut", "resample_scatter", "gather_propose",
+                 "simulate", "barrier_post"]
         return {names[i]: float(buf[i]) for i in range(n.value)}
 
     def trace_enable(self, on=True):

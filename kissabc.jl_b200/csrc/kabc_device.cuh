@@ -82,6 +82,22 @@ __device__ __forceinline__ bool dfinite(double x) {
     return ((unsigned long long)__double_as_longlong(x) & 0x7FF0000000000000ull) != 0x7FF0000000000000ull;
 }
 
+// Polynomial coefficients live in constant memory so that DFMA reads them as constant-bank operands (as 64-bit
+// immediates they cost two MOVs each).  The initialisers are folded by the host compiler with IEEE division, i.e.
+// they are the same correctly rounded doubles the oracle's literals are.
+static __constant__ double KC_LOG[11] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0,
+                                         1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
+static __constant__ double KC_EXP[13] = {1.0 / 87178291200.0, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0,
+                                         1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+                                         1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+static __constant__ double KC_SIN[9] = {-1.0 / 121645100408832000.0, 1.0 / 355687428096000.0, -1.0 / 1307674368000.0,
+                                        1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0,
+                                        -1.0 / 6.0};
+static __constant__ double KC_COS[9] = {1.0 / 6402373705728000.0, -1.0 / 20922789888000.0, 1.0 / 87178291200.0,
+                                        -1.0 / 479001600.0, 1.0 / 3628800.0, -1.0 / 40320.0, 1.0 / 720.0, -1.0 / 24.0, 0.5};
+static __constant__ double KC_MISC[6] = {6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4426950408889634,
+                                         6.283185307179586, 1.4142135623730951, 2.3283064365386962890625e-10};
+
 static __device__ __noinline__ double xlog(double x) {
     if (x != x) return x;
     if (x < 0.0) return dnan();
@@ -96,46 +112,28 @@ static __device__ __noinline__ double xlog(double x) {
     }
     e += (int)(b >> 52) - 1023;
     double m = __longlong_as_double((long long)((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
-    if (m > 1.4142135623730951) { m = xmul(m, 0.5); e += 1; }
+    if (m > KC_MISC[4]) { m = xmul(m, 0.5); e += 1; }
     double s = xdiv(xsub(m, 1.0), xadd(m, 1.0));
     double s2 = xmul(s, s);
-    double p = 1.0 / 23.0;
-    p = xfma(p, s2, 1.0 / 21.0);
-    p = xfma(p, s2, 1.0 / 19.0);
-    p = xfma(p, s2, 1.0 / 17.0);
-    p = xfma(p, s2, 1.0 / 15.0);
-    p = xfma(p, s2, 1.0 / 13.0);
-    p = xfma(p, s2, 1.0 / 11.0);
-    p = xfma(p, s2, 1.0 / 9.0);
-    p = xfma(p, s2, 1.0 / 7.0);
-    p = xfma(p, s2, 1.0 / 5.0);
-    p = xfma(p, s2, 1.0 / 3.0);
+    double p = KC_LOG[0];
+#pragma unroll
+    for (int q = 1; q < 11; ++q) p = xfma(p, s2, KC_LOG[q]);
     double t = xmul(xmul(s, s2), p);
     double r = xadd(xmul(2.0, s), xmul(2.0, t));
     double ef = (double)e;
-    return xadd(xmul(ef, 6.93147180369123816490e-01), xadd(r, xmul(ef, 1.90821492927058770002e-10)));
+    return xadd(xmul(ef, KC_MISC[0]), xadd(r, xmul(ef, KC_MISC[1])));
 }
 
 static __device__ __noinline__ double xexp(double x) {
     if (x != x) return x;
     if (x > 709.78) return dinf();
     if (x < -745.2) return 0.0;
-    double k = floor(xadd(xmul(x, 1.4426950408889634), 0.5));
-    double r = xfma(-k, 6.93147180369123816490e-01, x);
-    r = xfma(-k, 1.90821492927058770002e-10, r);
-    double p = 1.0 / 87178291200.0;
-    p = xfma(p, r, 1.0 / 6227020800.0);
-    p = xfma(p, r, 1.0 / 479001600.0);
-    p = xfma(p, r, 1.0 / 39916800.0);
-    p = xfma(p, r, 1.0 / 3628800.0);
-    p = xfma(p, r, 1.0 / 362880.0);
-    p = xfma(p, r, 1.0 / 40320.0);
-    p = xfma(p, r, 1.0 / 5040.0);
-    p = xfma(p, r, 1.0 / 720.0);
-    p = xfma(p, r, 1.0 / 120.0);
-    p = xfma(p, r, 1.0 / 24.0);
-    p = xfma(p, r, 1.0 / 6.0);
-    p = xfma(p, r, 0.5);
+    double k = floor(xadd(xmul(x, KC_MISC[2]), 0.5));
+    double r = xfma(-k, KC_MISC[0], x);
+    r = xfma(-k, KC_MISC[1], r);
+    double p = KC_EXP[0];
+#pragma unroll
+    for (int q = 1; q < 13; ++q) p = xfma(p, r, KC_EXP[q]);
     p = xfma(p, r, 1.0);
     p = xfma(p, r, 1.0);
     int ki = (int)k;
@@ -148,34 +146,22 @@ static __device__ __noinline__ double xexp(double x) {
 __device__ __forceinline__ void xsincos2pi(double u, double &sn, double &cs) {
     double q = floor(xadd(xmul(4.0, u), 0.5));
     double t = xsub(u, xmul(0.25, q));
-    double phi = xmul(t, 6.283185307179586);
+    double phi = xmul(t, KC_MISC[3]);
     double p2 = xmul(phi, phi);
-    double ps = -1.0 / 121645100408832000.0;
-    ps = xfma(ps, p2, 1.0 / 355687428096000.0);
-    ps = xfma(ps, p2, -1.0 / 1307674368000.0);
-    ps = xfma(ps, p2, 1.0 / 6227020800.0);
-    ps = xfma(ps, p2, -1.0 / 39916800.0);
-    ps = xfma(ps, p2, 1.0 / 362880.0);
-    ps = xfma(ps, p2, -1.0 / 5040.0);
-    ps = xfma(ps, p2, 1.0 / 120.0);
-    ps = xfma(ps, p2, -1.0 / 6.0);
+    double ps = KC_SIN[0], pc = KC_COS[0];
+#pragma unroll
+    for (int j = 1; j < 9; ++j) {
+        ps = xfma(ps, p2, KC_SIN[j]);
+        pc = xfma(pc, p2, KC_COS[j]);
+    }
     double s = xfma(xmul(phi, p2), ps, phi);
-    double pc = 1.0 / 6402373705728000.0;
-    pc = xfma(pc, p2, -1.0 / 20922789888000.0);
-    pc = xfma(pc, p2, 1.0 / 87178291200.0);
-    pc = xfma(pc, p2, -1.0 / 479001600.0);
-    pc = xfma(pc, p2, 1.0 / 3628800.0);
-    pc = xfma(pc, p2, -1.0 / 40320.0);
-    pc = xfma(pc, p2, 1.0 / 720.0);
-    pc = xfma(pc, p2, -1.0 / 24.0);
-    pc = xfma(pc, p2, 0.5);
     double c = xfma(-p2, pc, 1.0);
     int qi = ((int)q) & 3;
     sn = qi == 0 ? s : (qi == 1 ? c : (qi == 2 ? -s : -c));
     cs = qi == 0 ? c : (qi == 1 ? -s : (qi == 2 ? -c : s));
 }
 
-__device__ __forceinline__ double u01(uint32_t w) { return xmul(xadd((double)w, 0.5), 2.3283064365386962890625e-10); }
+__device__ __forceinline__ double u01(uint32_t w) { return xmul(xadd((double)w, 0.5), KC_MISC[5]); }
 __device__ __forceinline__ uint32_t index_of(uint32_t w, uint32_t n) { return __umulhi(w, n); }
 
 __device__ __forceinline__ void normal_pair64(uint32_t w0, uint32_t w1, double &z0, double &z1) {

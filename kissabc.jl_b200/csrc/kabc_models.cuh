@@ -55,12 +55,13 @@ __device__ __forceinline__ double cost_normal_f64(const DModel &m, const RoundKe
     return xsqrt(xadd(xmul(d1, d1), xmul(d2, d2)));
 }
 
-// FP32 draws; shifted one-pass sums of (x - mu) = sigma*z (exact algebra, well conditioned in FP32).
+// FP32 draws.  mean(x) = mu + sigma*mean(z) and std(x) = sigma*std(z) exactly (x = mu + sigma*z), so the kernel
+// accumulates the one-pass sums of z and z^2 in FP32 (well conditioned: z is centred, unit scale) and applies mu and
+// sigma once, in FP64, at the end.
 __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
                                                   uint32_t epoch, double mu, double sigma) {
     const int n = m.n_draws;
     const int nbf = n >> 2; // full blocks
-    const float sg = (float)sigma;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
     for (int b = 0; b < nbf; ++b) {
@@ -71,9 +72,8 @@ __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKe
         normal_pair32(w2, w3, z[2], z[3]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float dx = __fmul_rn(sg, z[q]);
-            s1[q] = __fadd_rn(s1[q], dx);
-            s2[q] = __fmaf_rn(dx, dx, s2[q]);
+            s1[q] = __fadd_rn(s1[q], z[q]);
+            s2[q] = __fmaf_rn(z[q], z[q], s2[q]);
         }
     }
     if (n & 3) {
@@ -85,18 +85,17 @@ __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKe
 #pragma unroll
         for (int q = 0; q < 3; ++q)
             if (q < (n & 3)) {
-                float dx = __fmul_rn(sg, z[q]);
-                s1[q] = __fadd_rn(s1[q], dx);
-                s2[q] = __fmaf_rn(dx, dx, s2[q]);
+                s1[q] = __fadd_rn(s1[q], z[q]);
+                s2[q] = __fmaf_rn(z[q], z[q], s2[q]);
             }
     }
     const double S1 = ((double)s1[0] + (double)s1[1]) + ((double)s1[2] + (double)s1[3]);
     const double S2 = ((double)s2[0] + (double)s2[1]) + ((double)s2[2] + (double)s2[3]);
     const double dn = (double)n;
-    const double mean = mu + S1 / dn;
+    const double mean = mu + sigma * (S1 / dn);
     double var = (S2 - S1 * S1 / dn) / (double)(n - 1);
     if (var < 0.0) var = 0.0;
-    const double sd = sqrt(var);
+    const double sd = fabs(sigma) * sqrt(var);
     const double d1 = mean - m.target[0];
     const double d2 = (sd - m.target[1]) * m.param[0];
     return sqrt(d1 * d1 + d2 * d2);

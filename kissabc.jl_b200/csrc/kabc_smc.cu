@@ -26,7 +26,7 @@ constexpr int SEL_LOG2_BINS = 12;
 constexpr int SEL_BINS = 1 << SEL_LOG2_BINS;
 constexpr int SEL_CAP = 4096; // candidates sorted exactly by one block
 constexpr int SEL_THREADS = 512;
-constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_THREADS = 1024; // particles per block of the cut / scatter kernels
 
 struct RankPartial { // what a rank contributes to the sweep bookkeeping
     unsigned long long accepted, work, events, minkey;
@@ -37,6 +37,7 @@ struct SmcCtrl {
     unsigned long long xmin_key; // running minimum over the alive costs (as an ordered key)
     unsigned long long klo, khi, v0key, v1key;
     long long below, cnt, r0, r1; // bucket-select bookkeeping
+    unsigned long long sel_below;  // alive keys under the guessed lower bound of pass 0
     long long n_alive;            // number of alive particles (input of the next quantile)
     long long ess;                // ESS = sum(alive) right after the cut (what the reference prints)
     unsigned long long accepted, cost_evals, events;
@@ -268,6 +269,23 @@ __device__ void sel_scan_narrow(const unsigned int *hist, bool hist_is_global, S
     __syncthreads();
 }
 
+// 4 consecutive particles per thread: one uchar4 + two double2 loads
+__device__ __forceinline__ void load4(const unsigned char *alive, const double *X, long long base, long long N,
+                                      unsigned int (&a)[4], double (&x)[4]) {
+    if (base + 3 < N && (reinterpret_cast<unsigned long long>(X) & 15ull) == 0) {
+        const uchar4 av = *reinterpret_cast<const uchar4 *>(alive + base);
+        const double2 x0 = *reinterpret_cast<const double2 *>(X + base), x1 = *reinterpret_cast<const double2 *>(X + base + 2);
+        a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+        x[0] = x0.x; x[1] = x0.y; x[2] = x1.x; x[3] = x1.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            a[q] = (base + q < N) ? alive[base + q] : 0u;
+            x[q] = (base + q < N) ? X[base + q] : 0.0;
+        }
+    }
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P) {
     __shared__ unsigned int sh[SEL_BINS];
@@ -277,6 +295,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P
     if (c->err) return;
     SelRange R;
     double gamma = 0.0;
+    unsigned long long klo_true = 0;
     if (PASS == 0) {
         const long long n = c->n_alive;
         if (n <= 0) {
@@ -292,9 +311,17 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P
         gamma = gamma < 0.0 ? 0.0 : (gamma > 1.0 ? 1.0 : gamma);
         R.r0 = (n == 1) ? 0 : j - 1; // 0-based rank of v[j]
         R.r1 = (n == 1) ? 0 : j;     // 0-based rank of v[j+1]
-        R.klo = c->xmin_key;
-        R.khi = (c->bounds_known && dfinite(c->eps)) ? dkey(c->eps) : ~0ull;
-        if (R.khi < R.klo) R.khi = ~0ull;
+        klo_true = c->xmin_key;
+        R.klo = klo_true;
+        R.khi = ~0ull;
+        if (c->bounds_known && dfinite(c->eps)) {
+            R.khi = dkey(c->eps);
+            // guess: the new quantile sits in the top binade of the alive costs (it does for any alpha that is not
+            // tiny); keys under the guess are only counted.  A wrong guess is detected below and costs one more pass.
+            const unsigned long long g = dkey(xmul(c->eps, 0.5));
+            if (c->eps > 0.0 && g > R.klo && g < R.khi) R.klo = g;
+        }
+        if (R.khi < R.klo) { R.khi = ~0ull; R.klo = klo_true; }
         R.below = 0; R.cnt = n;
     } else {
         if (c->sel_done || c->cnt <= SEL_CAP) return;
@@ -304,10 +331,23 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P
     for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) sh[q] = 0;
     __syncthreads();
     const double *X = B.X[c->cur];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += (long long)gridDim.x * blockDim.x) {
-        if (!B.alive[i]) continue;
-        const unsigned long long key = dkey(X[i]);
-        if (key >= R.klo && key <= R.khi) atomicAdd(&sh[(key - R.klo) >> R.shift], 1u);
+    unsigned long long nbelow = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < P.N; base += stride) {
+        unsigned int a[4];
+        double x[4];
+        load4(B.alive, X, base, P.N, a, x);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!a[q]) continue;
+            const unsigned long long key = dkey(x[q]);
+            if (key >= R.klo && key <= R.khi) atomicAdd(&sh[(key - R.klo) >> R.shift], 1u);
+            else if (PASS == 0 && key < R.klo) nbelow += 1;
+        }
+    }
+    if (PASS == 0) {
+        nbelow = warp_sum_u64(nbelow);
+        if ((threadIdx.x & 31) == 0 && nbelow) atomicAdd(&c->sel_below, nbelow);
     }
     __syncthreads();
     for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) {
@@ -315,10 +355,21 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P
         if (v) atomicAdd(&B.hist[q], v);
     }
     if (!last_block(&c->tk_hist)) return;
-    sel_scan_narrow(B.hist, true, R, s_scan, s_res);
+    bool guess_failed = false;
+    if (PASS == 0) {
+        const long long below = (long long)c->sel_below;
+        if (R.r0 < below) { // a rank lies under the guessed bound: hand the whole range [true min, khi] to the next pass
+            guess_failed = true;
+            R.klo = klo_true; R.below = 0; R.cnt = c->n_alive; R.shift = 1;
+        } else {
+            R.below = below;
+        }
+    }
+    if (!guess_failed) sel_scan_narrow(B.hist, true, R, s_scan, s_res);
     for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) B.hist[q] = 0;
     if (threadIdx.x == 0) {
         c->tk_hist = 0;
+        c->sel_below = 0;
         c->klo = R.klo; c->khi = R.khi; c->below = R.below; c->cnt = R.cnt; c->r0 = R.r0; c->r1 = R.r1;
         c->sel_done = (R.shift == 0); // bins were single keys: klo/khi ARE v[j], v[j+1]
         c->v0key = R.klo; c->v1key = R.khi;
@@ -341,23 +392,34 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_final(SmcBufs B, SmcParams 
     const bool compact = !c->sel_done && c->cnt <= SEL_CAP;
     if (compact) {
         const unsigned long long klo = c->klo, khi = c->khi;
-        const long long stride = (long long)gridDim.x * blockDim.x;
+        const long long stride = (long long)gridDim.x * blockDim.x * 4;
         const long long nloop = (P.N + stride - 1) / stride;
         for (long long it = 0; it < nloop; ++it) {
-            const long long i = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-            unsigned long long key = 0;
-            bool in = false;
-            if (i < P.N && B.alive[i]) {
-                key = dkey(X[i]);
-                in = key >= klo && key <= khi;
+            const long long base = it * stride + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+            unsigned int a[4] = {0u, 0u, 0u, 0u};
+            double x[4] = {0.0, 0.0, 0.0, 0.0};
+            if (base < P.N) load4(B.alive, X, base, P.N, a, x);
+            unsigned long long keys[4];
+            bool ins[4], any = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                keys[q] = dkey(x[q]);
+                ins[q] = a[q] && keys[q] >= klo && keys[q] <= khi;
+                any |= ins[q];
             }
-            const unsigned int ball = __ballot_sync(0xffffffffu, in);
-            if (ball) {
-                const unsigned int lane = threadIdx.x & 31;
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(&c->cand_count, (unsigned int)__popc(ball));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (in) B.cand[base + __popc(ball & ((1u << lane) - 1u))] = key;
+            if (__ballot_sync(0xffffffffu, any) == 0) continue; // candidates are rare (<= 4096 of N)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned long long key = keys[q];
+                const bool in = ins[q];
+                const unsigned int ball = __ballot_sync(0xffffffffu, in);
+                if (ball) {
+                    const unsigned int lane = threadIdx.x & 31;
+                    unsigned int pos = 0;
+                    if (lane == 0) pos = atomicAdd(&c->cand_count, (unsigned int)__popc(ball));
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                    if (in) B.cand[pos + __popc(ball & ((1u << lane) - 1u))] = key;
+                }
             }
         }
     }
@@ -419,167 +481,208 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_final(SmcBufs B, SmcParams 
 }
 
 // ------------------------------------------------------------------ alive cut + ESS + resample decision, ref :136-147
-__global__ void __launch_bounds__(SCAN_THREADS) k_alive_cut(SmcBufs B, SmcParams P, int nblocks) {
-    __shared__ unsigned int s_w[32];
-    SmcCtrl *c = B.ctrl;
-    if (c->err) return;
-    const double *X = B.X[c->cur];
-    const double eps = c->eps;
-    const int flag = c->flag;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int a = 0;
-    if (i < P.N) {
-        double x = X[i];
-        a = flag ? (x <= eps) : (x < eps);
-        B.alive[i] = (unsigned char)a;
-    }
-    unsigned int cnt = __syncthreads_count(a);
-    if (threadIdx.x == 0) B.blockcnt[blockIdx.x] = cnt;
-    if (!last_block(&c->tk_cut)) return;
-    // last block: exclusive scan of the per-block counts (in place), total = ESS
-    unsigned long long carry = 0;
-    for (int base = 0; base < nblocks; base += blockDim.x) {
-        int q = base + threadIdx.x;
-        unsigned int v = q < nblocks ? __ldcg(&B.blockcnt[q]) : 0u;
-        unsigned int incl = v;
+// block b owns particles [1024 b, 1024 b + 1024): 256 threads x 4 consecutive particles
+constexpr int CUT_THREADS = 256;
+__device__ __forceinline__ unsigned int block_excl_scan_256(unsigned int v, unsigned int *s_w, unsigned int &total) {
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int incl = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += t;
-        }
-        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            unsigned int w = s_w[threadIdx.x], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (threadIdx.x >= o) wi += t;
-            }
-            s_w[threadIdx.x] = wi - w; // exclusive warp offsets
-        }
-        __syncthreads();
-        unsigned int excl = incl - v + s_w[threadIdx.x >> 5];
-        if (q < nblocks) B.blockcnt[q] = (unsigned int)(carry + excl);
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_w[0] = excl + v;
-        __syncthreads();
-        carry += s_w[0];
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    if (threadIdx.x == 0) {
-        const long long ess = (long long)carry;
-        c->ess = ess;
-        c->n_alive = ess;
-        c->tk_cut = 0;
-        c->bounds_known = 1; // from now on every alive cost is <= eps
-        // ref :145  alpha*ESS <= nparticles*min_r_ess, FP64, exactly these operands
-        c->resample = xmul(P.alpha, (double)ess) <= xmul((double)P.N, P.min_r_ess);
-        if (c->resample && ess == 0) c->err = KABC_ERR_DEGENERATE;
-    }
-}
-
-// idxalive = (1:N)[alive], ref :146
-__global__ void __launch_bounds__(SCAN_THREADS) k_resample_scatter(SmcBufs B, SmcParams P) {
-    __shared__ unsigned int s_w[32];
-    SmcCtrl *c = B.ctrl;
-    if (c->err || !c->resample) return;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int a = (i < P.N) ? B.alive[i] : 0u;
-    unsigned int ball = __ballot_sync(0xffffffffu, a);
-    unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) s_w[warp] = __popc(ball);
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
     if (threadIdx.x < 32) {
-        unsigned int w = s_w[threadIdx.x], wi = w;
+        unsigned int w = threadIdx.x < (CUT_THREADS / 32) ? s_w[threadIdx.x] : 0u, wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
             if (threadIdx.x >= o) wi += t;
         }
-        s_w[threadIdx.x] = wi - w;
+        s_w[threadIdx.x] = wi - w;          // exclusive warp offsets
+        if (threadIdx.x == 31) s_w[32] = wi; // block total
     }
     __syncthreads();
-    if (a) {
-        unsigned int pos = B.blockcnt[blockIdx.x] + s_w[warp] + __popc(ball & ((1u << lane) - 1u));
-        B.idxalive[pos] = (unsigned int)i;
-    }
+    total = s_w[32];
+    const unsigned int r = incl - v + s_w[warp];
+    __syncthreads();
+    return r;
 }
 
-// theta, X, lpi = (...)[idx], idx[k] = idxalive[k mod n_alive]; alive .= true (ref :147-152) -- or a plain copy when
-// the reference does not resample, so that the current buffer flips every iteration (the host needs no read-back)
-__global__ void __launch_bounds__(256) k_resample_gather(SmcBufs B, SmcParams P) {
+__global__ void __launch_bounds__(CUT_THREADS) k_alive_cut(SmcBufs B, SmcParams P, int nblocks) {
+    __shared__ unsigned int s_w[33];
     SmcCtrl *c = B.ctrl;
     if (c->err) return;
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int cur = c->cur;
-    const int resample = c->resample;
-    if (k < P.N) {
-        const long long N = P.N;
-        long long src = k;
-        if (resample) {
-            const unsigned long long n = (unsigned long long)c->ess;
-            src = B.idxalive[(unsigned long long)k % n];
-            B.alive[k] = 1;
-        }
-        for (int q = 0; q < P.d; ++q) B.th[cur ^ 1][(long long)q * N + k] = B.th[cur][(long long)q * N + src];
-        B.X[cur ^ 1][k] = B.X[cur][src];
-        B.lpi[cur ^ 1][k] = B.lpi[cur][src];
+    const double *X = B.X[c->cur];
+    const double eps = c->eps;
+    const int flag = c->flag;
+    const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
+    unsigned int cnt = 0;
+    if (base + 3 < P.N && (reinterpret_cast<unsigned long long>(X) & 15ull) == 0) {
+        const double2 x0 = *reinterpret_cast<const double2 *>(X + base), x1 = *reinterpret_cast<const double2 *>(X + base + 2);
+        uchar4 a;
+        a.x = flag ? (x0.x <= eps) : (x0.x < eps); a.y = flag ? (x0.y <= eps) : (x0.y < eps);
+        a.z = flag ? (x1.x <= eps) : (x1.x < eps); a.w = flag ? (x1.y <= eps) : (x1.y < eps);
+        *reinterpret_cast<uchar4 *>(B.alive + base) = a;
+        cnt = a.x + a.y + a.z + a.w;
+    } else {
+        for (int q = 0; q < 4; ++q)
+            if (base + q < P.N) {
+                const double x = X[base + q];
+                const unsigned int a = flag ? (x <= eps) : (x < eps);
+                B.alive[base + q] = (unsigned char)a;
+                cnt += a;
+            }
     }
-    if (!last_block(&c->tk_gather)) return;
+    unsigned int total;
+    block_excl_scan_256(cnt, s_w, total);
+    if (threadIdx.x == 0) B.blockcnt[blockIdx.x] = total;
+    if (!last_block(&c->tk_cut)) return;
+    // last block: exclusive scan of the per-block counts (in place), total = ESS
+    unsigned long long carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += CUT_THREADS) {
+        const int q = b0 + threadIdx.x;
+        const unsigned int v = q < nblocks ? __ldcg(&B.blockcnt[q]) : 0u;
+        unsigned int chunk;
+        const unsigned int excl = block_excl_scan_256(v, s_w, chunk);
+        if (q < nblocks) B.blockcnt[q] = (unsigned int)(carry + excl);
+        carry += chunk;
+    }
     if (threadIdx.x == 0) {
-        c->tk_gather = 0;
-        c->cur = cur ^ 1;
-        if (resample) {
-            c->n_alive = P.N;
-            c->resample = 0;
-            c->resampled_log = 1;
-        }
+        const long long ess = (long long)carry;
+        c->ess = ess;
+        c->tk_cut = 0;
+        c->bounds_known = 1; // from now on every alive cost is <= eps
+        // ref :145  alpha*ESS <= nparticles*min_r_ess, FP64, exactly these operands
+        c->resample = xmul(P.alpha, (double)ess) <= xmul((double)P.N, P.min_r_ess);
+        if (c->resample && ess == 0) c->err = KABC_ERR_DEGENERATE;
+        c->n_alive = c->resample ? P.N : ess; // ref :151-152: after resampling everything is alive
+        if (c->resample) c->resampled_log = 1;
     }
 }
 
-// ------------------------------------------------------------------ propose, ref :160-167 and :172-175
+// idxalive = (1:N)[alive], ref :146; `alive .= true` (ref :152) is applied here as well
+__global__ void __launch_bounds__(CUT_THREADS) k_resample_scatter(SmcBufs B, SmcParams P) {
+    __shared__ unsigned int s_w[33];
+    SmcCtrl *c = B.ctrl;
+    if (c->err || !c->resample) return;
+    const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
+    unsigned int a[4] = {0u, 0u, 0u, 0u};
+    if (base + 3 < P.N) {
+        const uchar4 av = *reinterpret_cast<const uchar4 *>(B.alive + base);
+        a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+        *reinterpret_cast<uchar4 *>(B.alive + base) = make_uchar4(1, 1, 1, 1);
+    } else {
+        for (int q = 0; q < 4; ++q)
+            if (base + q < P.N) { a[q] = B.alive[base + q]; B.alive[base + q] = 1; }
+    }
+    unsigned int total;
+    unsigned int pos = B.blockcnt[blockIdx.x] + block_excl_scan_256(a[0] + a[1] + a[2] + a[3], s_w, total);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (a[q]) B.idxalive[pos++] = (unsigned int)(base + q);
+}
+
+// One row of the population, pushed into every peer replica of copy `dst` (multi GPU, peer memory over NVLink).
+// Every row of a copy has exactly ONE writer in the whole job -- its owner rank -- so the pushes need no ordering
+// against anything but the end-of-sweep barrier.
+template <int DM>
+__device__ __forceinline__ void push_row(const SmcBufs &B, const SmcParams &P, int dst, long long i, const double (&th_row)[DM],
+                                         double X, double lp) {
+    const long long N = P.N;
+    const long long base = (long long)dst * (P.d + 2) * N;
+    for (int r = 0; r < B.n_peers; ++r) {
+        if (r == P.rank) continue;
+        double *q = B.peer[r] + base;
+#pragma unroll
+        for (int k = 0; k < DM; ++k)
+            if (k < P.d) q[(long long)k * N + i] = th_row[k];
+        q[(long long)P.d * N + i] = X;
+        q[(long long)(P.d + 1) * N + i] = lp;
+    }
+}
+
+// ------------------------------------------------------------------ resample gather + propose, ref :147-152, :160-167, :172-175
+// Reads the complete copy S = cur (rows through the resampling map idx[k] = idxalive[k mod n], ref :146-147, or the
+// identity when the reference does not resample) and writes copy D = cur^1: every owned particle's row is
+// materialised in D here (the physical gather of the reference, done by the owner only); particles that go on to the
+// simulator are appended to the work list and finalised by the sweep kernel, the others are final here and are
+// pushed to the peers.  Partner rows are read from S through the same map, so no rank ever needs another rank's D rows.
+template <int DM> // DM >= d: compile-time bound of the parameter loops (rows stay in registers)
 __global__ void __launch_bounds__(256)
-k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi) {
+k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi, double sqrt_np) {
     SmcCtrl *c = B.ctrl;
     if (c->err || c->retry_done) return;
     long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N = P.N;
-    const double *th = B.th[c->cur];
-    const double *lpi = B.lpi[c->cur];
+    const int S = c->cur, D = S ^ 1;
+    const double *th = B.th[S];
+    const int resample = c->resample;
+    const unsigned int n_src = (unsigned int)c->ess;
     const uint32_t epoch = c->epoch;
     bool push = false;
     int dec = 0;
     long long a = -1, b = -1;
     double z = dnan(), lprob = dnan(), lpip = dnan();
-    if (i < hi && B.alive[i]) {
-        Stream st(rk, ST_PROPOSE, (uint32_t)i, epoch);
-        a = i; b = i;
-        while (a == i) a = (long long)index_of(st.next(), (uint32_t)N);
-        while (b == i || b == a) b = (long long)index_of(st.next(), (uint32_t)N);
-        z = next_normal(st);
-        const double sc = xdiv(xmul(P.max_stretch, z), xsqrt((double)P.d));
-        for (int k = 0; k < P.d; ++k) {
-            const double *t = th + (long long)k * N;
-            B.thp[(long long)k * N + i] = xadd(t[i], xmul(xsub(t[b], t[a]), sc));
-        }
-        const uint32_t wu = st.next();
-        const double *thp = B.thp;
-        lpip = prior_logpdf(pri, [&](int k) { return thp[(long long)k * N + i]; });
-        if (lpip < 0.0 && !dfinite(lpip)) dec = 1;
-        else {
-            // ref :174-175  lM = min(lpip - lpi + logcorr, 0); proceed iff log(rand) < lM.
-            // log(u) < 0 always (u < 1), so the logarithm is only evaluated when lM < 0 (or when tracing).
-            const double lM = fmin(xadd(xsub(lpip, lpi[i]), 0.0), 0.0);
-            bool pass = true;
-            if (!(lM >= 0.0) || B.trace_on) {
-                lprob = xlog(u01(wu));
-                pass = lprob < lM;
+    if (i < hi) {
+        // the particle's own row after the (possible) resampling
+        const long long ri = resample ? (long long)B.idxalive[(unsigned int)i % n_src] : i;
+        const bool alive_i = resample ? true : (B.alive[i] != 0);
+        double row[DM];
+#pragma unroll
+        for (int k = 0; k < DM; ++k) {
+            row[k] = 0.0;
+            if (k < P.d) {
+                row[k] = th[(long long)k * N + ri];
+                B.th[D][(long long)k * N + i] = row[k];
             }
-            if (!pass) dec = 2;
-            else { push = true; B.lpip[i] = lpip; }
         }
-        if (B.trace_on && lprob != lprob) lprob = xlog(u01(wu));
+        const double Xi = B.X[S][ri], lpi_i = B.lpi[S][ri];
+        B.X[D][i] = Xi;
+        B.lpi[D][i] = lpi_i;
+        if (alive_i) {
+            Stream st(rk, ST_PROPOSE, (uint32_t)i, epoch);
+            a = i; b = i;
+            while (a == i) a = (long long)index_of(st.next(), (uint32_t)N);
+            while (b == i || b == a) b = (long long)index_of(st.next(), (uint32_t)N);
+            const long long ra = resample ? (long long)B.idxalive[(unsigned int)a % n_src] : a;
+            const long long rb = resample ? (long long)B.idxalive[(unsigned int)b % n_src] : b;
+            z = next_normal(st);
+            const double sc = xdiv(xmul(P.max_stretch, z), sqrt_np);
+#pragma unroll
+            for (int k = 0; k < DM; ++k) {
+                if (k < P.d) {
+                    const double *t = th + (long long)k * N;
+                    B.thp[(long long)k * N + i] = xadd(row[k], xmul(xsub(t[rb], t[ra]), sc));
+                }
+            }
+            const uint32_t wu = st.next();
+            const double *thp = B.thp;
+            lpip = prior_logpdf(pri, [&](int k) { return thp[(long long)k * N + i]; });
+            if (lpip < 0.0 && !dfinite(lpip)) dec = 1;
+            else {
+                // ref :174-175  lM = min(lpip - lpi + logcorr, 0); proceed iff log(rand) < lM.
+                // log(u) < 0 always (u < 1), so the logarithm is only evaluated when lM < 0 (or when tracing).
+                const double lM = fmin(xadd(xsub(lpip, lpi_i), 0.0), 0.0);
+                bool pass = true;
+                if (!(lM >= 0.0) || B.trace_on) {
+                    lprob = xlog(u01(wu));
+                    pass = lprob < lM;
+                }
+                if (!pass) dec = 2;
+                else { push = true; B.lpip[i] = lpip; }
+            }
+            if (B.trace_on && lprob != lprob) lprob = xlog(u01(wu));
+        }
+        if (!push && B.n_peers > 0) {
+            push_row<DM>(B, P, D, i, row, Xi, lpi_i);
+        }
+        if (B.trace_on) {
+            B.tr.a[i] = a; B.tr.b[i] = b; B.tr.z[i] = z; B.tr.lprob[i] = lprob; B.tr.lpip[i] = lpip;
+            B.tr.dec[i] = (unsigned char)dec; B.tr.xp[i] = dnan();
+            if (!alive_i) for (int k = 0; k < P.d; ++k) B.thp[(long long)k * N + i] = dnan();
+        }
     }
     // warp-aggregated append to the work list
     unsigned int ball = __ballot_sync(0xffffffffu, push);
@@ -588,11 +691,6 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
         if (lane == 0) base = atomicAdd(&c->work_count, (unsigned int)__popc(ball));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (push) B.work[base + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
-    }
-    if (B.trace_on && i < hi) {
-        B.tr.a[i] = a; B.tr.b[i] = b; B.tr.z[i] = z; B.tr.lprob[i] = lprob; B.tr.lpip[i] = lpip;
-        B.tr.dec[i] = (unsigned char)dec; B.tr.xp[i] = dnan();
-        if (!B.alive[i]) for (int k = 0; k < P.d; ++k) B.thp[(long long)k * N + i] = dnan();
     }
 }
 
@@ -616,6 +714,8 @@ __device__ void post_sweep(SmcBufs &B, const SmcParams &P, bool from_partials) {
     c->sw_accepted = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->work_count = 0;
     c->sweeps += 1;
     c->epoch += 1;
+    c->cur ^= 1;      // copy D is now complete on every rank
+    c->resample = 0;  // a retry sweep of the same iteration reads D as it is (identity map)
     if ((double)c->accepted >= xmul(P.mcmc_tol, (double)P.N)) c->retry_done = 1;
 }
 // closes an iteration, ref :194-198
@@ -657,31 +757,39 @@ __global__ void k_post_sweep_dist(SmcBufs B, SmcParams P, int close_iter) {
 __global__ void k_post_iter(SmcBufs B, SmcParams P) { post_iter(B, P); }
 
 // ------------------------------------------------------------------ simulate + accept, ref :176-189
+template <int DM>
 __device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCtrl *c, long long i, double Xp,
                                            unsigned int &acc) {
     const long long N = P.N;
-    const int cur = c->cur;
+    const int D = c->cur ^ 1; // the copy this sweep writes (the row was pre-filled by k_smc_propose)
     const bool reject = c->flag ? (Xp > c->eps) : (Xp >= c->eps);
+    double row[DM], Xf = 0.0, lpf = 0.0;
+#pragma unroll
+    for (int k = 0; k < DM; ++k) row[k] = 0.0;
     if (!reject) {
-        const double lp = B.lpip[i];
-        for (int k = 0; k < P.d; ++k) B.th[cur][(long long)k * N + i] = B.thp[(long long)k * N + i];
-        B.X[cur][i] = Xp;
-        B.lpi[cur][i] = lp;
-        acc = 1;
-        // multi GPU: push the accepted row straight into every peer's replica (NVLink stores, overlapped with the
-        // other warps' simulation); the per-sweep NCCL all-gather of the 32-byte partials is the barrier after which
-        // the replicas are read again
-        if (B.n_peers > 0) {
-            const long long base = (long long)cur * (P.d + 2) * N;
-            for (int r = 0; r < B.n_peers; ++r) {
-                if (r == P.rank) continue;
-                double *q = B.peer[r] + base;
-                for (int k = 0; k < P.d; ++k) q[(long long)k * N + i] = B.thp[(long long)k * N + i];
-                q[(long long)P.d * N + i] = Xp;
-                q[(long long)(P.d + 1) * N + i] = lp;
+        lpf = B.lpip[i];
+        Xf = Xp;
+#pragma unroll
+        for (int k = 0; k < DM; ++k)
+            if (k < P.d) {
+                row[k] = B.thp[(long long)k * N + i];
+                B.th[D][(long long)k * N + i] = row[k];
             }
-            __threadfence_system();
-        }
+        B.X[D][i] = Xf;
+        B.lpi[D][i] = lpf;
+        acc = 1;
+    } else if (B.n_peers > 0) {
+#pragma unroll
+        for (int k = 0; k < DM; ++k)
+            if (k < P.d) row[k] = B.th[D][(long long)k * N + i];
+        Xf = B.X[D][i];
+        lpf = B.lpi[D][i];
+    }
+    // multi GPU: the final row (moved or not) goes straight into every peer's replica: NVLink stores that overlap
+    // with the other warps' simulation.  Kernel completion flushes them; the NCCL all-gather of the 32-byte partials
+    // that closes the sweep is the barrier after which the replicas are read again.
+    if (B.n_peers > 0) {
+        push_row<DM>(B, P, D, i, row, Xf, lpf);
     }
     if (B.trace_on) { B.tr.xp[i] = Xp; B.tr.dec[i] = reject ? 3 : 4; }
 }
@@ -704,7 +812,8 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
             const long long N = P.N;
             const double *thp = B.thp;
             double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, [&](int k) { return thp[(long long)k * N + i]; }, ev);
-            smc_accept(B, P, c, i, Xp, acc);
+            constexpr int DM = KIND == KABC_MODEL_LV_SSA ? 3 : (KIND == KABC_MODEL_DETERMINISTIC ? KABC_MAX_DIM : 2);
+            smc_accept<DM>(B, P, c, i, Xp, acc);
             if (acc) key = dkey(Xp);
         }
         const unsigned int nacc = __popc(__ballot_sync(0xffffffffu, acc));
@@ -734,7 +843,7 @@ __global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcPa
         double Xp = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, thp[i], thp[N + i], thp[2 * N + i], thp[3 * N + i], gk_smem);
         if (threadIdx.x == 0) {
             unsigned int acc = 0;
-            smc_accept(B, P, c, i, Xp, acc);
+            smc_accept<4>(B, P, c, i, Xp, acc);
             if (acc) { atomicAdd(&c->sw_accepted, 1ull); atomicMin(&c->sw_minkey, dkey(Xp)); }
         }
     }
@@ -965,13 +1074,14 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     const long long n = s->hi - s->lo;
     const bool dist = ctx->world > 1;
     const int mode = dist ? 4 : (1 | (close_iter ? 2 : 0));
-    k_smc_propose<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
-    SMC_LAUNCHED(s, 1);
-    if (s->p2p) {
-        // barrier: every rank has finished writing (resample gather) and reading (propose) the current copy before
-        // any peer starts pushing accepted rows into it
-        if (int rc = nccl_allgather_inplace(ctx, s->B.partial, sizeof(RankPartial))) return rc;
+    {
+        const unsigned pb = (unsigned)((n + 255) / 256);
+        const double sq = sqrt((double)s->P.d);
+        if (s->P.d <= 2) k_smc_propose<2><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi, sq);
+        else if (s->P.d <= 4) k_smc_propose<4><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi, sq);
+        else k_smc_propose<KABC_MAX_DIM><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi, sq);
     }
+    SMC_LAUNCHED(s, 1);
     s->mark();
     switch (s->model.kind) {
     case KABC_MODEL_NORMAL_MEANSTD: smc_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s, mode); break;
@@ -994,11 +1104,13 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     }
     s->mark();
     if (dist) {
-        if (int rc = smc_allgather_state(s, s->cur, !s->p2p)) return rc;
+        // barrier + counters; without peer memory also the rows this rank wrote into copy D
+        if (int rc = smc_allgather_state(s, s->cur ^ 1, !s->p2p)) return rc;
         k_post_sweep_dist<<<1, 1, 0, ctx->stream>>>(s->B, s->P, close_iter ? 1 : 0);
         SMC_LAUNCHED(s, 1);
         s->mark();
     }
+    s->cur ^= 1; // host mirror of ctrl->cur: every executed sweep writes the other copy
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
@@ -1006,7 +1118,7 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
 static int smc_enqueue_cut(kabc_smc *s) {
     kabc_ctx *ctx = s->ctx;
     const long long N = s->P.N;
-    int sel_blocks = (int)((N + SEL_THREADS * 8 - 1) / (SEL_THREADS * 8));
+    int sel_blocks = (int)((N + SEL_THREADS * 16 - 1) / (SEL_THREADS * 16));
     if (sel_blocks > ctx->sm_count * 2) sel_blocks = ctx->sm_count * 2;
     if (sel_blocks < 1) sel_blocks = 1;
     s->mark();
@@ -1016,14 +1128,11 @@ static int smc_enqueue_cut(kabc_smc *s) {
     s->mark();
     k_sel_final<<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
     s->mark();
-    k_alive_cut<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P, s->nblocks_scan);
+    k_alive_cut<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P, s->nblocks_scan);
     s->mark();
-    k_resample_scatter<<<s->nblocks_scan, SCAN_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    k_resample_scatter<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P);
     s->mark();
-    k_resample_gather<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P);
-    s->mark();
-    s->cur ^= 1;
-    SMC_LAUNCHED(s, 6);
+    SMC_LAUNCHED(s, 5);
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
