@@ -178,38 +178,45 @@ __device__ __forceinline__ double cost_ma2_f32(const DModel &m, const RoundKeys 
 
 // ------------------------------------------------------------------ Lotka-Volterra, Gillespie direct method
 // theta = log rates; param = {X0, Y0, T, G, max_events}; target = [X(t_1..t_G), Y(t_1..t_G)], t_g = g T/G.
+// The simulator is a resumable state machine (one SSA event per step()) so that the sweep kernel can re-fill a lane
+// with a new particle as soon as its trajectory ends (event counts differ by orders of magnitude across the prior).
 template <bool F32>
-__device__ __forceinline__ double cost_lv(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
-                                          uint32_t epoch, double l1, double l2, double l3, long long &events) {
-    const double c1 = xexp(l1), c2 = xexp(l2), c3 = xexp(l3);
-    double X = m.param[0], Y = m.param[1];
-    const double T = m.param[2];
-    const int G = (int)m.param[3];
-    const long long max_events = (long long)m.param[4];
-    const double dt = xdiv(T, (double)G);
-    double t = 0.0, acc = 0.0;
-    int g = 0;
-    long long ev = 0;
-    uint32_t blk = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-    int have = 0; // unread word pairs left in the current Philox block
-    double ret = 0.0;
-    bool capped = false;
-    while (g < G) {
+struct LvSim {
+    double c1, c2, c3, X, Y, t, acc, dt;
+    long long ev, max_events;
+    uint32_t blk, w2, w3, id, epoch, tag;
+    int g, G, have;
+    bool capped;
+
+    __device__ __forceinline__ void init(const DModel &m, uint32_t tag_, uint32_t id_, uint32_t epoch_, double l1, double l2,
+                                         double l3) {
+        c1 = xexp(l1); c2 = xexp(l2); c3 = xexp(l3);
+        X = m.param[0]; Y = m.param[1];
+        G = (int)m.param[3];
+        max_events = (long long)m.param[4];
+        dt = xdiv(m.param[2], (double)G);
+        t = 0.0; acc = 0.0; g = 0; ev = 0; blk = 0; w2 = 0; w3 = 0; have = 0; capped = false;
+        id = id_; epoch = epoch_; tag = tag_;
+    }
+    // one Gillespie event (or the final recording of the grid); returns true when the trajectory is finished
+    __device__ __forceinline__ bool step(const DModel &m, const RoundKeys &rk) {
+        if (g >= G) return true;
         const double a1 = xmul(c1, X), a2 = xmul(xmul(c2, X), Y), a3 = xmul(c3, Y);
         const double a0 = xadd(xadd(a1, a2), a3);
         double tn;
         uint32_t u0 = 0, u1 = 0;
         if (a0 > 0.0) {
-            if (ev >= max_events) { capped = true; break; }
+            if (ev >= max_events) { capped = true; return true; }
             if (have == 0) {
+                uint32_t w0, w1;
                 philox4x32_10(rk, blk, id, epoch, tag, w0, w1, w2, w3);
                 blk += 1;
-                have = 2;
+                have = 1;
                 u0 = w0; u1 = w1;
             } else {
+                have = 0;
                 u0 = w2; u1 = w3;
             }
-            have -= 1;
             double lg;
             if (F32) {
                 float uf = __fmaf_rn(__uint2float_rn(u0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
@@ -221,23 +228,32 @@ __device__ __forceinline__ double cost_lv(const DModel &m, const RoundKeys &rk, 
         } else {
             tn = dinf();
         }
-        while (g < G && xmul((double)(g + 1), dt) <= tn) {
+        while (g < G && xmul((double)(g + 1), dt) <= tn) { // record the pre-event state
             const double dx = xsub(X, m.target[g]), dy = xsub(Y, m.target[G + g]);
             acc = xadd(acc, xmul(dx, dx));
             acc = xadd(acc, xmul(dy, dy));
             ++g;
         }
-        if (g >= G) break;
+        if (g >= G) return true;
         const double r = xmul(u01(u1), a0);
         if (r < a1) X = xadd(X, 1.0);
         else if (r < xadd(a1, a2)) { X = xsub(X, 1.0); Y = xadd(Y, 1.0); }
         else Y = xsub(Y, 1.0);
         t = tn;
         ++ev;
+        return false;
     }
-    events = ev;
-    ret = capped ? dinf() : xsqrt(xdiv(acc, (double)(2 * G)));
-    return ret;
+    __device__ __forceinline__ double result() const { return capped ? dinf() : xsqrt(xdiv(acc, (double)(2 * G))); }
+};
+
+template <bool F32>
+__device__ __forceinline__ double cost_lv(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                          uint32_t epoch, double l1, double l2, double l3, long long &events) {
+    LvSim<F32> sim;
+    sim.init(m, tag, id, epoch, l1, l2, l3);
+    while (!sim.step(m, rk)) {}
+    events = sim.ev;
+    return sim.result();
 }
 
 // ------------------------------------------------------------------ deterministic costs of the reference's tests

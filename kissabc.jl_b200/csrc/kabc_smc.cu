@@ -43,7 +43,7 @@ struct SmcCtrl {
     unsigned long long accepted, cost_evals, events;
     unsigned long long sw_accepted, sw_events, sw_minkey; // per-sweep partials of this rank
     long long iteration;
-    unsigned int work_count, cand_count, epoch;
+    unsigned int work_count, cand_count, epoch, lv_head;
     unsigned int tk_hist, tk_final, tk_cut, tk_gather, tk_sim;
     int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log, sel_done, bounds_known;
 };
@@ -711,7 +711,7 @@ __device__ void post_sweep(SmcBufs &B, const SmcParams &P, bool from_partials) {
     c->cost_evals += work;
     c->events += ev;
     if (mk < c->xmin_key) c->xmin_key = mk;
-    c->sw_accepted = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->work_count = 0;
+    c->sw_accepted = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->work_count = 0; c->lv_head = 0;
     c->sweeps += 1;
     c->epoch += 1;
     c->cur ^= 1;      // copy D is now complete on every rank
@@ -823,6 +823,69 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
             if (nacc) { atomicAdd(&c->sw_accepted, (unsigned long long)nacc); atomicMin(&c->sw_minkey, key); }
             if (e) atomicAdd(&c->sw_events, e);
         }
+    }
+    if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
+}
+
+// Lotka-Volterra sweep: persistent lanes.  Event counts per trajectory differ by orders of magnitude, so a lane whose
+// trajectory ended immediately pulls the next work item (warp-aggregated atomic on the work-list head) instead of
+// idling until the slowest lane of its warp finishes.  Per-particle arithmetic is unchanged (LvSim), so results do
+// not depend on the schedule.
+constexpr int LV_CHUNK = 32; // events between refill checks
+template <int PREC>
+__global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
+    SmcCtrl *c = B.ctrl;
+    if (c->err || c->retry_done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
+        return;
+    }
+    const unsigned int nwork = c->work_count;
+    const long long N = P.N;
+    const uint32_t epoch = c->epoch;
+    const unsigned int lane = threadIdx.x & 31;
+    LvSim<PREC != KABC_F64> sim;
+    long long i = -1;
+    bool have = false, exhausted = false;
+    unsigned int nacc = 0;
+    unsigned long long events = 0, key = ~0ull;
+    for (;;) {
+        const unsigned int need = __ballot_sync(0xffffffffu, !have && !exhausted);
+        if (need) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&c->lv_head, (unsigned int)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!have && !exhausted) {
+                const unsigned int w = base + __popc(need & ((1u << lane) - 1u));
+                if (w < nwork) {
+                    i = B.work[w];
+                    sim.init(m, ST_COST, (uint32_t)i, epoch, B.thp[i], B.thp[N + i], B.thp[2 * N + i]);
+                    have = true;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__ballot_sync(0xffffffffu, have)) break;
+        bool fin = false;
+        for (int e = 0; e < LV_CHUNK; ++e) {
+            if (have && !fin) fin = sim.step(m, rk);
+            if (!__ballot_sync(0xffffffffu, have && !fin)) break;
+        }
+        if (have && fin) {
+            unsigned int acc = 0;
+            const double Xp = sim.result();
+            smc_accept<3>(B, P, c, i, Xp, acc);
+            if (acc) { nacc += 1; const unsigned long long k2 = dkey(Xp); key = k2 < key ? k2 : key; }
+            events += (unsigned long long)sim.ev;
+            have = false;
+        }
+    }
+    nacc = (unsigned int)warp_sum_u64(nacc);
+    events = warp_sum_u64(events);
+    key = warp_min_u64(key);
+    if (lane == 0) {
+        if (nacc) { atomicAdd(&c->sw_accepted, (unsigned long long)nacc); atomicMin(&c->sw_minkey, key); }
+        if (events) atomicAdd(&c->sw_events, events);
     }
     if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
 }
@@ -1086,7 +1149,16 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     switch (s->model.kind) {
     case KABC_MODEL_NORMAL_MEANSTD: smc_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s, mode); break;
     case KABC_MODEL_MA2_AUTOCOV: smc_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s, mode); break;
-    case KABC_MODEL_LV_SSA: smc_launch_sim_t<KABC_MODEL_LV_SSA>(s, mode); break;
+    case KABC_MODEL_LV_SSA: {
+        long long nb = (n + 255) / 256, cap = (long long)ctx->sm_count * 8;
+        const unsigned blocks = (unsigned)(nb < cap ? nb : cap);
+        if (s->model.precision == KABC_F64)
+            k_smc_simulate_lv<KABC_F64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
+        else
+            k_smc_simulate_lv<KABC_F32_ACC64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
+        SMC_LAUNCHED(s, 1);
+        break;
+    }
     case KABC_MODEL_DETERMINISTIC: smc_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s, mode); break;
     case KABC_MODEL_GK_OCTILE: {
         size_t smem;
