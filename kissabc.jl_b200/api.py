@@ -408,7 +408,7 @@ def smc(prior, cost: DeviceCost, *, nparticles=100, alpha=0.95, mcmc_retrys=0, m
     d, N = len(prior), int(nparticles)
     th = np.empty((d, max(N, 1))); alive = np.empty(max(N, 1), dtype=np.uint8); X = np.empty(max(N, 1))
     eps, it, evals = C.c_double(), C.c_int64(), C.c_int64()
-    cap = 1 << 16
+    cap = 1 << 13
     logbuf = (K.SmcLogT * cap)()
     m = cost._pod()
     K.check(ctx.L.kabc_smc_run(ctx.h, prior._pods(), d, C.byref(m), C.byref(cfg), K.dptr(th), K.u8ptr(alive),

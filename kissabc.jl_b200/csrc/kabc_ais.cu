@@ -388,8 +388,8 @@ int kabc_ais_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     const size_t nd = (size_t)N * d;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    A(s->th.alloc(nd)); A(s->thp.alloc(nd)); A(s->lp.alloc(N)); A(s->ll.alloc(N)); A(s->lpp.alloc(N));
-    A(s->corr.alloc(N)); A(s->work.alloc(N)); A(s->ctrl.alloc(1));
+    A(s->th.alloc(ctx, nd)); A(s->thp.alloc(ctx, nd)); A(s->lp.alloc(ctx, N)); A(s->ll.alloc(ctx, N)); A(s->lpp.alloc(ctx, N));
+    A(s->corr.alloc(ctx, N)); A(s->work.alloc(ctx, N)); A(s->ctrl.alloc(ctx, 1));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_ctrl, sizeof(AisCtrl));
     if (e != cudaSuccess) {
         delete s;

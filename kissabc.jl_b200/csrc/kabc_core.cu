@@ -401,6 +401,8 @@ int kabc_ctx_destroy(kabc_ctx_t *ctx) {
     if (!ctx) return KABC_OK;
     cudaSetDevice(ctx->device);
     if (ctx->comm) nccl_comm_destroy(ctx);
+    for (auto &e : ctx->cache) cudaFree(e.p); // handles must be destroyed before their context
+    ctx->cache.clear();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -37,6 +37,36 @@ struct kabc_ctx {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     long long launches = 0;
+    // Device-buffer cache: smc/ais handles are created and destroyed once per user call (smc(...), sample(...)); cudaMalloc
+    // and above all cudaFree of a few hundred MB cost far more than an smc run, so freed buffers are kept for the next handle.
+    struct CacheEntry { void *p; size_t bytes; bool in_use; };
+    std::vector<CacheEntry> cache;
+    cudaError_t acquire(void **out, size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (auto &e : cache)
+            if (!e.in_use && e.bytes == bytes) { e.in_use = true; *out = e.p; return cudaSuccess; }
+        cudaError_t rc = cudaMalloc(out, bytes);
+        if (rc != cudaSuccess) { // out of memory: drop every idle buffer and retry
+            cudaGetLastError();
+            trim();
+            rc = cudaMalloc(out, bytes);
+        }
+        if (rc == cudaSuccess) cache.push_back({*out, bytes, true});
+        return rc;
+    }
+    void release(void *p) {
+        for (auto &e : cache)
+            if (e.p == p) { e.in_use = false; return; }
+        cudaFree(p);
+    }
+    void trim() {
+        std::vector<CacheEntry> keep;
+        for (auto &e : cache) {
+            if (e.in_use) keep.push_back(e);
+            else cudaFree(e.p);
+        }
+        cache.swap(keep);
+    }
 };
 
 namespace kabc {
@@ -50,6 +80,7 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    kabc_ctx *owner = nullptr; // non-null: the buffer comes from (and returns to) the context's cache
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -60,10 +91,22 @@ struct DevBuf {
         if (count == 0) return cudaSuccess;
         return cudaMalloc((void **)&p, count * sizeof(T));
     }
+    cudaError_t alloc(kabc_ctx *ctx, size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        cudaError_t rc = ctx->acquire((void **)&p, count * sizeof(T));
+        if (rc == cudaSuccess) owner = ctx;
+        return rc;
+    }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (owner) owner->release(p);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
+        owner = nullptr;
     }
 };
 

@@ -63,7 +63,12 @@ __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKe
     const int n = m.n_draws;
     const int nbf = n >> 2; // full blocks
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+#ifndef KABC_NORMAL_UNROLL
+#define KABC_NORMAL_UNROLL 4
+#endif
+#define KABC_STR2(x) #x
+#define KABC_STR(x) KABC_STR2(x)
+    _Pragma(KABC_STR(unroll KABC_NORMAL_UNROLL))
     for (int b = 0; b < nbf; ++b) {
         uint32_t w0, w1, w2, w3;
         philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);

@@ -16,6 +16,7 @@
 // NVLink) after each sweep; quantile, cut and resample are computed redundantly from identical replicas, so no
 // scalar ever needs a broadcast.  Philox counters are keyed by the GLOBAL particle id: results are bit-identical
 // for any G.
+#include <ctime>
 #include "kabc_host.hpp"
 #include "kabc_gk.cuh"
 #include "kabc_nccl.hpp"
@@ -46,6 +47,7 @@ struct SmcCtrl {
     unsigned int work_count, cand_count, epoch, lv_head;
     unsigned int tk_hist, tk_final, tk_cut, tk_gather, tk_sim;
     int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log, sel_done, bounds_known;
+    int honor_stop; // kabc_smc_run enqueues one iteration ahead: once `stop` is set the queued kernels do nothing
 };
 
 struct SmcParams { // launch constants
@@ -83,6 +85,9 @@ struct SmcBufs {
     SmcTrace tr;
     int trace_on;
 };
+
+// an iteration queued behind a stop (or after an error) must leave the state untouched
+__device__ __forceinline__ bool smc_skip(const SmcCtrl *c) { return c->err || (c->honor_stop && c->stop); }
 
 __device__ __forceinline__ unsigned long long dkey(double x) {
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P
     __shared__ unsigned int s_scan[SEL_THREADS];
     __shared__ unsigned long long s_res[4];
     SmcCtrl *c = B.ctrl;
-    if (c->err) return;
+    if (smc_skip(c)) return;
     SelRange R;
     double gamma = 0.0;
     unsigned long long klo_true = 0;
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_final(SmcBufs B, SmcParams 
     __shared__ unsigned int s_scan[SEL_THREADS];
     __shared__ unsigned long long s_res[4];
     SmcCtrl *c = B.ctrl;
-    if (c->err) return;
+    if (smc_skip(c)) return;
     const double *X = B.X[c->cur];
     const bool compact = !c->sel_done && c->cnt <= SEL_CAP;
     if (compact) {
@@ -513,7 +518,7 @@ __device__ __forceinline__ unsigned int block_excl_scan_256(unsigned int v, unsi
 __global__ void __launch_bounds__(CUT_THREADS) k_alive_cut(SmcBufs B, SmcParams P, int nblocks) {
     __shared__ unsigned int s_w[33];
     SmcCtrl *c = B.ctrl;
-    if (c->err) return;
+    if (smc_skip(c)) return;
     const double *X = B.X[c->cur];
     const double eps = c->eps;
     const int flag = c->flag;
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(CUT_THREADS) k_alive_cut(SmcBufs B, SmcParams 
 __global__ void __launch_bounds__(CUT_THREADS) k_resample_scatter(SmcBufs B, SmcParams P) {
     __shared__ unsigned int s_w[33];
     SmcCtrl *c = B.ctrl;
-    if (c->err || !c->resample) return;
+    if (smc_skip(c) || !c->resample) return;
     const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
     unsigned int a[4] = {0u, 0u, 0u, 0u};
     if (base + 3 < P.N) {
@@ -613,7 +618,7 @@ template <int DM> // DM >= d: compile-time bound of the parameter loops (rows st
 __global__ void __launch_bounds__(256)
 k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi, double sqrt_np) {
     SmcCtrl *c = B.ctrl;
-    if (c->err || c->retry_done) return;
+    if (smc_skip(c) || c->retry_done) return;
     long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N = P.N;
     const int S = c->cur, D = S ^ 1;
@@ -751,10 +756,12 @@ __device__ __forceinline__ void sweep_epilogue(SmcBufs &B, const SmcParams &P, i
     if (mode & 2) post_iter(B, P);
 }
 __global__ void k_post_sweep_dist(SmcBufs B, SmcParams P, int close_iter) {
+    if (B.ctrl->honor_stop && B.ctrl->stop) return;
     if (!(B.ctrl->err || B.ctrl->retry_done)) post_sweep(B, P, true);
     if (close_iter) post_iter(B, P);
 }
 __global__ void k_post_iter(SmcBufs B, SmcParams P) { post_iter(B, P); }
+__global__ void k_set_honor_stop(SmcBufs B, int v) { B.ctrl->honor_stop = v; }
 
 // ------------------------------------------------------------------ simulate + accept, ref :176-189
 template <int DM>
@@ -797,7 +804,8 @@ __device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCt
 template <int KIND, int PREC>
 __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
     SmcCtrl *c = B.ctrl;
-    if (c->err || c->retry_done) {
+    if (smc_skip(c)) return;
+    if (c->retry_done) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
         return;
     }
@@ -835,7 +843,8 @@ constexpr int LV_CHUNK = 32; // events between refill checks
 template <int PREC>
 __global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
     SmcCtrl *c = B.ctrl;
-    if (c->err || c->retry_done) {
+    if (smc_skip(c)) return;
+    if (c->retry_done) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
         return;
     }
@@ -894,7 +903,8 @@ template <int PREC>
 __global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
     SmcCtrl *c = B.ctrl;
-    if (c->err || c->retry_done) {
+    if (smc_skip(c)) return;
+    if (c->retry_done) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
         return;
     }
@@ -1268,11 +1278,13 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     const size_t copy_elems = nd + 2 * (size_t)N; // [th | X | lpi]
-    A(s->slab.alloc(2 * copy_elems)); A(s->thp.alloc(nd)); A(s->lpip.alloc(N));
-    A(s->alive.alloc(N)); A(s->work.alloc(N)); A(s->idxalive.alloc(N)); A(s->blockcnt.alloc(s->nblocks_scan));
-    A(s->hist.alloc(SEL_BINS)); A(s->cand.alloc(SEL_CAP)); A(s->ctrl.alloc(1)); A(s->partial.alloc(ctx->world));
-    const long long log_cap = 1 << 16;
-    A(s->log.alloc(log_cap));
+    if (ctx->world > 1) A(s->slab.alloc(2 * copy_elems)); // peer-mapped slabs are not recycled
+    else A(s->slab.alloc(ctx, 2 * copy_elems));
+    A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, N));
+    A(s->alive.alloc(ctx, N)); A(s->work.alloc(ctx, N)); A(s->idxalive.alloc(ctx, N)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
+    A(s->hist.alloc(ctx, SEL_BINS)); A(s->cand.alloc(ctx, SEL_CAP)); A(s->ctrl.alloc(ctx, 1)); A(s->partial.alloc(ctx, ctx->world));
+    const long long log_cap = 1 << 14;
+    A(s->log.alloc(ctx, log_cap));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_ctrl, sizeof(SmcCtrl));
     if (e != cudaSuccess) {
         delete s;
@@ -1480,10 +1492,58 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
                  const kabc_smc_config_t *cfg, double *out_theta, uint8_t *out_alive, double *out_cost, double *out_eps,
                  int64_t *out_iterations, int64_t *out_cost_evals, kabc_smc_log_t *log, int64_t log_cap) {
     kabc_smc *s = nullptr;
+    const bool dbg = getenv("KABC_DEBUG_TIMING") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    const double t0 = now();
     if (int rc = kabc_smc_create(ctx, prior, d, model, cfg, &s)) return rc;
+    const double t1 = now();
     int rc = kabc_smc_init(s);
-    int stop = 0;
-    while (!rc && !stop) rc = kabc_smc_iterate(s, &stop);
+    const double t2 = now();
+    if (!rc && s->P.mcmc_retrys > 0) {
+        // the retry loop needs the host between sweeps anyway (ref :192): plain stepping
+        int stop = 0;
+        while (!rc && !stop) rc = kabc_smc_iterate(s, &stop);
+    } else if (!rc) {
+        // One iteration is always queued AHEAD of the one whose `stop` flag the host is waiting for, so kernel
+        // launches and the flag read-back overlap with device work.  The look-ahead iteration does nothing on the
+        // device when `stop` was set (smc_skip), and the host then takes its buffer flip back.
+        cudaStream_t st = ctx->stream;
+        SmcCtrl *slots = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaError_t e = cudaMallocHost((void **)&slots, 2 * sizeof(SmcCtrl));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+        if (e != cudaSuccess) rc = set_error(KABC_ERR_CUDA, "pipeline setup failed: %s", cudaGetErrorString(e));
+        if (!rc) {
+            k_set_honor_stop<<<1, 1, 0, st>>>(s->B, 1);
+            SMC_LAUNCHED(s, 1);
+        }
+        auto enqueue = [&](int slot) -> int {
+            if (int r2 = smc_enqueue_iteration(s)) return r2;
+            if (cudaMemcpyAsync(&slots[slot], s->B.ctrl, sizeof(SmcCtrl), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaEventRecord(ev[slot], st) != cudaSuccess)
+                return set_error(KABC_ERR_CUDA, "pipeline enqueue failed");
+            return KABC_OK;
+        };
+        if (!rc) rc = enqueue(0);
+        for (int k = 0; !rc; ++k) {
+            rc = enqueue((k + 1) & 1);
+            if (rc) break;
+            if (cudaEventSynchronize(ev[k & 1]) != cudaSuccess) { rc = set_error(KABC_ERR_CUDA, "event wait failed"); break; }
+            const SmcCtrl &c = slots[k & 1];
+            if (c.err || c.stop) {
+                cudaEventSynchronize(ev[(k + 1) & 1]); // the look-ahead iteration was skipped on the device
+                s->cur ^= 1;                             // ... so its host-side buffer flip is undone
+                break;
+            }
+        }
+        if (!rc) rc = smc_read_ctrl(s);
+        if (!rc) rc = smc_ctrl_error(s);
+        if (ev[0]) cudaEventDestroy(ev[0]);
+        if (ev[1]) cudaEventDestroy(ev[1]);
+        if (slots) cudaFreeHost(slots);
+    }
+    const double t3 = now();
     if (!rc) rc = kabc_smc_get_state(s, out_theta, out_cost, nullptr, out_alive);
     if (!rc) {
         if (out_eps) *out_eps = s->h_ctrl->eps;
@@ -1491,9 +1551,13 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
         if (out_cost_evals) *out_cost_evals = (int64_t)s->h_ctrl->cost_evals;
         if (log && log_cap > 0 && kabc_smc_get_log(s, log, log_cap) < 0) rc = set_error(KABC_ERR_CUDA, "log copy failed");
     }
+    const double t4 = now();
     std::string keep = g_last_error;
     kabc_smc_destroy(s);
     g_last_error = keep;
+    if (dbg)
+        fprintf(stderr, "[kabc_smc_run] create %.1f ms, init %.1f ms, iterate %.1f ms, copy-out %.1f ms, destroy %.1f ms\n",
+                1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (now() - t4));
     return rc;
 }
 
