@@ -74,6 +74,7 @@ struct SmcBufs {
     // n_peers == 0 -> no direct pushes (single GPU, or the NCCL all-gather fallback)
     double *peer[KABC_MAX_PEERS];
     int n_peers;
+    int shard_rows; // 1: only X is replicated; theta/lpi rows are read from their owner's slab in k_smc_propose
     unsigned char *alive;
     double *thp, *lpip;
     unsigned int *work, *idxalive, *blockcnt, *hist;
@@ -600,10 +601,11 @@ __device__ __forceinline__ void push_row(const SmcBufs &B, const SmcParams &P, i
     for (int r = 0; r < B.n_peers; ++r) {
         if (r == P.rank) continue;
         double *q = B.peer[r] + base;
+        q[(long long)P.d * N + i] = X;
+        if (B.shard_rows) continue;
 #pragma unroll
         for (int k = 0; k < DM; ++k)
             if (k < P.d) q[(long long)k * N + i] = th_row[k];
-        q[(long long)P.d * N + i] = X;
         q[(long long)(P.d + 1) * N + i] = lp;
     }
 }
@@ -634,16 +636,22 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
         // the particle's own row after the (possible) resampling
         const long long ri = resample ? (long long)B.idxalive[(unsigned int)i % n_src] : i;
         const bool alive_i = resample ? true : (B.alive[i] != 0);
+        // where row r of copy S lives: the local replica, or (sharded rows) the slab of the rank that owns r
+        const long long per = N / P.world, sbase = (long long)S * (P.d + 2) * N;
+        auto src_of = [&](long long r) -> const double * {
+            return B.shard_rows ? B.peer[(int)(r / per)] + sbase : th;
+        };
         double row[DM];
+        const double *own = src_of(ri);
 #pragma unroll
         for (int k = 0; k < DM; ++k) {
             row[k] = 0.0;
             if (k < P.d) {
-                row[k] = th[(long long)k * N + ri];
+                row[k] = own[(long long)k * N + ri];
                 B.th[D][(long long)k * N + i] = row[k];
             }
         }
-        const double Xi = B.X[S][ri], lpi_i = B.lpi[S][ri];
+        const double Xi = B.X[S][ri], lpi_i = own[(long long)(P.d + 1) * N + ri];
         B.X[D][i] = Xi;
         B.lpi[D][i] = lpi_i;
         if (alive_i) {
@@ -655,12 +663,11 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
             const long long rb = resample ? (long long)B.idxalive[(unsigned int)b % n_src] : b;
             z = next_normal(st);
             const double sc = xdiv(xmul(P.max_stretch, z), sqrt_np);
+            const double *pa = src_of(ra), *pb = src_of(rb);
 #pragma unroll
             for (int k = 0; k < DM; ++k) {
-                if (k < P.d) {
-                    const double *t = th + (long long)k * N;
-                    B.thp[(long long)k * N + i] = xadd(row[k], xmul(xsub(t[rb], t[ra]), sc));
-                }
+                if (k < P.d)
+                    B.thp[(long long)k * N + i] = xadd(row[k], xmul(xsub(pb[(long long)k * N + rb], pa[(long long)k * N + ra]), sc));
             }
             const uint32_t wu = st.next();
             const double *thp = B.thp;
@@ -1093,6 +1100,10 @@ static int smc_attach_peers(kabc_smc *s) {
         }
         s->B.n_peers = world;
         s->p2p = true;
+        // measured on 4 x B200: fine-grained remote partner reads cost more than replicating the rows
+        // (propose 311 us vs 165 us at 2^22 particles), so full-row replication is the default
+        const char *e2 = getenv("KABC_SHARD_ROWS");
+        s->B.shard_rows = (e2 && e2[0] == '1') ? 1 : 0;
     } else {
         for (int r = 0; r < world; ++r)
             if (r != ctx->rank && maps[r]) cudaIpcCloseMemHandle(maps[r]);
@@ -1298,6 +1309,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     }
     memset(s->B.peer, 0, sizeof s->B.peer);
     s->B.n_peers = 0;
+    s->B.shard_rows = 0;
     s->B.alive = s->alive.p; s->B.thp = s->thp.p;
     s->B.lpip = s->lpip.p; s->B.work = s->work.p; s->B.idxalive = s->idxalive.p; s->B.blockcnt = s->blockcnt.p;
     s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p; s->B.partial = s->partial.p;
@@ -1394,6 +1406,10 @@ int kabc_smc_get_state(kabc_smc_t *s, double *theta, double *X, double *lpi, uin
     if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
     const int cur = s->cur;
+    if (s->B.shard_rows && s->inited) {
+        // theta / lpi rows are only valid on their owner: assemble the full state (collective: every rank calls this)
+        if (int rc = smc_allgather_state(s, cur, true)) return rc;
+    }
     const size_t N = (size_t)s->P.N;
     cudaStream_t st = s->ctx->stream;
     if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(theta, s->B.th[cur], 8 * N * s->P.d, cudaMemcpyDeviceToHost, st));
