@@ -617,7 +617,7 @@ __device__ __forceinline__ void push_row(const SmcBufs &B, const SmcParams &P, i
 // simulator are appended to the work list and finalised by the sweep kernel, the others are final here and are
 // pushed to the peers.  Partner rows are read from S through the same map, so no rank ever needs another rank's D rows.
 template <int DM> // DM >= d: compile-time bound of the parameter loops (rows stay in registers)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5) // 48 registers: the kernel is latency-bound on its gathers, occupancy matters
 k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi, double sqrt_np) {
     SmcCtrl *c = B.ctrl;
     if (smc_skip(c) || c->retry_done) return;
