@@ -42,6 +42,14 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def traffic_bytes(name, prec):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/ncu_top_kernels_r1.txt); None for workloads without a capture."""
+    if name == "normal_smc" and prec == "f32":
+        return 41.03e6 + 13.58e6
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -52,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -161,7 +169,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="normal_smc", choices=list(W_INSTR))
@@ -256,6 +264,43 @@ def main():
     # with the replicated-state design every rank reports the same global counter
     value = evals / (ms_total * 1e-3)
 
+    # ---- end to end through the public API (host buffers in, host buffers out).  smc: a whole run to the target
+    # epsilon, every rank calls it (the call is collective), timed on the host as the max over ranks.
+    e2e = None
+    if not args.no_e2e and not is_ais:
+        import ctypes as C
+        eps_t = EPS_TARGET[name]
+        kw = dict(nparticles=N, ctx=ctx)
+        if eps_t is not None:
+            kw["epstol"] = eps_t
+        else:
+            kw["max_iterations"] = 30
+        sess.close()  # give the buffers back to the context cache
+        k.smc(prior, cost, **kw)  # warm the call path (allocations, lazy module load)
+        barrier()
+        t0 = time.perf_counter()
+        res = k.smc(prior, cost, **kw)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = d * C.sizeof(k._capi.PriorT) + C.sizeof(k._capi.ModelT) + C.sizeof(k._capi.SmcConfigT)
+        d2h = N * (8 * d + 1 + 8) + 56 * res.iterations
+        e2e = {"value": res.cost_evals / dt, "unit": "cost evals/s", "h2d_bytes_per_step": h2d / max(res.iterations, 1),
+               "d2h_bytes_per_step": d2h / max(res.iterations, 1),
+               "call": "kissabc_jl_b200.smc(prior, cost, nparticles=N, epstol=target) on every rank",
+               "iterations": res.iterations, "cost_evals": res.cost_evals, "eps": res.eps, "time_s": dt, "eps_target": eps_t}
+    elif not args.no_e2e and world == 1 and is_ais:
+        sess.close()
+        post = k.ApproxKernelizedPosterior(prior, cost, 0.5)
+        t0 = time.perf_counter()
+        _, cnt = k.sample(post, k.AIS(N), N, ntransitions=2, ctx=ctx, return_counters=True)
+        dt = time.perf_counter() - t0
+        e2e = {"value": cnt["cost_evals"] / dt, "unit": "cost evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": N * 8 * d,
+               "call": "kissabc_jl_b200.sample(ApproxKernelizedPosterior(...), AIS(N), N, ntransitions=2)", "time_s": dt}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -272,7 +317,7 @@ def main():
     roofline = {
         "bound": "issue", "kernel": "k_ais_simulate*" if is_ais else "k_smc_simulate<model,precision>",
         "achieved": achieved_instr / 1e12, "peak": r_issue / 1e12, "unit": "T thread-instr/s (SM issue slots: SMs x 4 x 32 x f_clk at the sampled clock)",
-        "frac": achieved_instr / r_issue, "traffic": None,
+        "frac": achieved_instr / r_issue, "traffic": traffic_bytes(name, args.precision),
         "w_instr_per_unit": W_INSTR[name], "unit_of_work": "SSA event" if name == "lv_smc" else "cost eval",
         "hbm": {"achieved": hbm_bytes / (ms_total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
                 "frac": hbm_bytes / (ms_total * 1e-3) / 1e9 / (peaks["hbm_gbs"] * world), "peak_source": peak_src,
@@ -292,33 +337,11 @@ def main():
     if name == "lv_smc":
         out["ssa_events_per_s"] = events / (ms_total * 1e-3)
 
-    # ---- end to end through the public API (host buffers in, host buffers out), whole smc run to the target epsilon
-    if not args.no_e2e and world == 1 and not is_ais:
-        eps_t = EPS_TARGET[name]
-        kw = dict(nparticles=N, ctx=ctx)
-        if eps_t is not None:
-            kw["epstol"] = eps_t
-        else:
-            kw["max_iterations"] = 30
-        k.smc(prior, cost, **dict(kw, nparticles=1 << 12))  # warm the call path
-        t0 = time.perf_counter()
-        res = k.smc(prior, cost, **kw)
-        dt = time.perf_counter() - t0
-        import ctypes as C
-        h2d = d * C.sizeof(k._capi.PriorT) + C.sizeof(k._capi.ModelT) + C.sizeof(k._capi.SmcConfigT)
-        d2h = N * (8 * d + 1 + 8) + 56 * res.iterations
-        out["e2e"] = {"value": res.cost_evals / dt, "unit": "cost evals/s", "h2d_bytes_per_step": h2d / max(res.iterations, 1),
-                      "d2h_bytes_per_step": d2h / max(res.iterations, 1), "call": "kissabc_jl_b200.smc(prior, cost, nparticles=N, epstol=target)",
-                      "iterations": res.iterations, "cost_evals": res.cost_evals, "eps": res.eps}
-        out["smc_time_to_eps_s"] = dt
-        out["eps_target"] = eps_t
-    elif not args.no_e2e and world == 1 and is_ais:
-        post = k.ApproxKernelizedPosterior(prior, cost, 0.5)
-        t0 = time.perf_counter()
-        _, cnt = k.sample(post, k.AIS(N), N, ntransitions=2, ctx=ctx, return_counters=True)
-        dt = time.perf_counter() - t0
-        out["e2e"] = {"value": cnt["cost_evals"] / dt, "unit": "cost evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": N * 8 * d,
-                      "call": "kissabc_jl_b200.sample(ApproxKernelizedPosterior(...), AIS(N), N, ntransitions=2)"}
+    if e2e is not None:
+        out["e2e"] = e2e
+        if "eps_target" in e2e:
+            out["smc_time_to_eps_s"] = e2e["time_s"]
+            out["eps_target"] = e2e["eps_target"]
 
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(name)
