@@ -184,13 +184,20 @@ k_ais_propose(AisBufs B, AisParams P, DPriors pri, RoundKeys rk, long long lo, l
             B.tr.lpp[i] = lpp; B.tr.llp[i] = lpp; B.tr.e[i] = dnan(); B.tr.dec[i] = 0;
         }
     }
-    unsigned int ball = __ballot_sync(0xffffffffu, push);
-    unsigned int lane = threadIdx.x & 31, base = 0;
-    if (ball) {
-        if (lane == 0) base = atomicAdd(&ctl->work_count, (unsigned int)__popc(ball));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (push) B.work[base + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
+    // block-aggregated append to the work list: one global atomic per CTA
+    __shared__ unsigned int s_cnt[8], s_base;
+    const unsigned int ball = __ballot_sync(0xffffffffu, push);
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = __popc(ball);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
+        s_base = tot ? atomicAdd(&ctl->work_count, tot) : 0u;
     }
+    __syncthreads();
+    if (push) B.work[s_base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
 }
 
 // ref src/types.jl:62-75 + src/transition.jl:76-79

@@ -696,14 +696,21 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
             if (!alive_i) for (int k = 0; k < P.d; ++k) B.thp[(long long)k * N + i] = dnan();
         }
     }
-    // warp-aggregated append to the work list
-    unsigned int ball = __ballot_sync(0xffffffffu, push);
-    unsigned int lane = threadIdx.x & 31, base = 0;
-    if (ball) {
-        if (lane == 0) base = atomicAdd(&c->work_count, (unsigned int)__popc(ball));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (push) B.work[base + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
+    // block-aggregated append to the work list: ONE global atomic per CTA (a per-warp atomic on the single counter
+    // serialises 32768 requests in L2 and was the top stall of this kernel)
+    __shared__ unsigned int s_cnt[8], s_base;
+    const unsigned int ball = __ballot_sync(0xffffffffu, push);
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = __popc(ball);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
+        s_base = tot ? atomicAdd(&c->work_count, tot) : 0u;
     }
+    __syncthreads();
+    if (push) B.work[s_base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
 }
 
 // ------------------------------------------------------------------ sweep / iteration bookkeeping
@@ -818,6 +825,8 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
     }
     const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int nwork = c->work_count;
+    unsigned int nacc_w = 0;
+    unsigned long long e_w = 0, key_w = ~0ull;
     if ((w & ~31u) < nwork) {
         unsigned int acc = 0;
         long long ev = 0;
@@ -831,13 +840,23 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
             smc_accept<DM>(B, P, c, i, Xp, acc);
             if (acc) key = dkey(Xp);
         }
-        const unsigned int nacc = __popc(__ballot_sync(0xffffffffu, acc));
-        const unsigned long long e = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
-        if (nacc) key = warp_min_u64(key);
-        if ((threadIdx.x & 31) == 0) {
-            if (nacc) { atomicAdd(&c->sw_accepted, (unsigned long long)nacc); atomicMin(&c->sw_minkey, key); }
-            if (e) atomicAdd(&c->sw_events, e);
-        }
+        nacc_w = __popc(__ballot_sync(0xffffffffu, acc));
+        e_w = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
+        if (nacc_w) key_w = warp_min_u64(key);
+    }
+    // block-level fold of the sweep counters: one set of global atomics per CTA
+    __shared__ unsigned int s_acc;
+    __shared__ unsigned long long s_ev, s_key;
+    if (threadIdx.x == 0) { s_acc = 0; s_ev = 0; s_key = ~0ull; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        if (nacc_w) { atomicAdd(&s_acc, nacc_w); atomicMin(&s_key, key_w); }
+        if (e_w) atomicAdd(&s_ev, e_w);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_acc) { atomicAdd(&c->sw_accepted, (unsigned long long)s_acc); atomicMin(&c->sw_minkey, s_key); }
+        if (s_ev) atomicAdd(&c->sw_events, s_ev);
     }
     if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
 }
