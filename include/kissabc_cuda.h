@@ -99,7 +99,9 @@ typedef struct {
     int64_t discard_initial; /* 0 */
     int64_t thinning;        /* 1 */
     int64_t retry_sampling;  /* 100 */
-    double scale;
+    double scale;            /* target_average_cost (posterior 0) or max_cost (posterior 1) */
+    int32_t posterior;       /* 0 = ApproxKernelizedPosterior (src/types.jl:40-75), 1 = ApproxPosterior (src/types.jl:76-104) */
+    int32_t _pad;
 } kabc_ais_config_t;
 
 /* one record per smc iteration: what `verbose && @show iteration, eps, ESS` prints (src/smc.jl:143) + counters */

@@ -41,7 +41,7 @@ class SmcConfigT(C.Structure):
 class AisConfigT(C.Structure):
     _fields_ = [("nwalkers", C.c_int64), ("nsamples", C.c_int64), ("ntransitions", C.c_int64),
                 ("discard_initial", C.c_int64), ("thinning", C.c_int64), ("retry_sampling", C.c_int64),
-                ("scale", C.c_double)]
+                ("scale", C.c_double), ("posterior", C.c_int32), ("_pad", C.c_int32)]
 
 
 class SmcLogT(C.Structure):

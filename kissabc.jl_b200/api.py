@@ -439,9 +439,18 @@ class ApproxKernelizedPosterior:
     scale: float
 
 
-def ais_config(nwalkers, nsamples, ntransitions=1, discard_initial=0, thinning=1, retry_sampling=100, scale=1.0):
+@dataclass(frozen=True)
+class ApproxPosterior:
+    """ApproxPosterior(prior, cost, max_cost), ref src/types.jl:76-104: uniform errors in [-max_cost, max_cost]."""
+    prior: object
+    cost: DeviceCost
+    maxcost: float
+
+
+def ais_config(nwalkers, nsamples, ntransitions=1, discard_initial=0, thinning=1, retry_sampling=100, scale=1.0,
+               posterior=0):
     return K.AisConfigT(int(nwalkers), int(nsamples), int(ntransitions), int(discard_initial), int(thinning),
-                        int(retry_sampling), float(scale))
+                        int(retry_sampling), float(scale), int(posterior), 0)
 
 
 class AisSession:
@@ -505,19 +514,21 @@ class AisSession:
         return dict(move=move, a=a, b=b, c=c, corr=corr, theta_p=thp, lp_p=lpp, ll_p=llp, e=e, decision=dec)
 
 
-def sample(model: ApproxKernelizedPosterior, sampler: AIS, nsamples: int, *, ntransitions=1, discard_initial=0,
+def sample(model, sampler: AIS, nsamples: int, *, ntransitions=1, discard_initial=0,
            thinning=1, retry_sampling=100, progress=False, ctx: Optional[Context] = None, return_counters=False):
     """sample(model, AIS(N), Ns; ntransitions, discard_initial, thinning, retry_sampling), ref
     src/KissABC.jl:35-94 + AbstractMCMC.sample.  Returns one Particles per parameter (a scalar Particles if d = 1)."""
     del progress
-    if not isinstance(model, ApproxKernelizedPosterior):
-        raise KissABCError(K.ERR_INVALID_ARG, "the device path registers ApproxKernelizedPosterior only")
+    if not isinstance(model, (ApproxKernelizedPosterior, ApproxPosterior)):
+        raise KissABCError(K.ERR_INVALID_ARG, "the device path registers ApproxKernelizedPosterior and ApproxPosterior")
     if not isinstance(model.cost, DeviceCost):
         raise KissABCError(K.ERR_INVALID_ARG, "the device path needs a registered DeviceCost, not a closure")
     ctx = ctx or default_context()
     prior = _as_factored(model.prior)
     d = len(prior)
-    cfg = ais_config(sampler.nparticles, nsamples, ntransitions, discard_initial, thinning, retry_sampling, model.scale)
+    hard = isinstance(model, ApproxPosterior)
+    cfg = ais_config(sampler.nparticles, nsamples, ntransitions, discard_initial, thinning, retry_sampling,
+                     model.maxcost if hard else model.scale, posterior=1 if hard else 0)
     out = np.empty((d, max(int(nsamples), 1)))
     evals, acc = C.c_int64(), C.c_int64()
     m = model.cost._pod()

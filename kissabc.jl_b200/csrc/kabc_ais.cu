@@ -27,7 +27,8 @@ struct AisCtrl {
 struct AisParams {
     long long N;
     int d;
-    double scale;
+    double scale;        // kernel scale (posterior 0) or max_cost (posterior 1)
+    int posterior;       // 0 ApproxKernelizedPosterior, 1 ApproxPosterior
     long long retry_cap; // per-walker attempt cap = budget + 1
 };
 
@@ -51,6 +52,15 @@ __device__ __forceinline__ double kernel_ll(double cost, double scale) {
     double q = xdiv(cost, scale);
     return xmul(-0.5, xmul(q, q));
 }
+// second slot of the walker's log-density: the kernelized log-likelihood, or -- ApproxPosterior, ref
+// src/types.jl:84-91 -- the cost itself
+__device__ __forceinline__ double second_slot(const AisParams &P, double cost) {
+    return P.posterior == 1 ? cost : kernel_ll(cost, P.scale);
+}
+// ref src/types.jl:60 and :93-94
+__device__ __forceinline__ bool ld_valid(const AisParams &P, double lp, double ll) {
+    return P.posterior == 1 ? (dfinite(ll) && dfinite(lp)) : dfinite(xadd(lp, ll));
+}
 
 // ------------------------------------------------------------------ init with retry, ref src/KissABC.jl:50-61
 template <int KIND, int PREC>
@@ -71,15 +81,15 @@ k_ais_init(AisBufs B, AisParams P, DPriors pri, DModel m, RoundKeys rk) {
         }
         const double *th = B.th;
         lp = prior_logpdf(pri, [&](int k) { return th[(long long)k * N + i]; });
-        ll = lp;
+        ll = P.posterior == 1 ? -lp : lp;
         if (dfinite(lp)) {
             long long ev;
             double c = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, (uint32_t)i, (uint32_t)t,
                                                [&](int k) { return th[(long long)k * N + i]; }, ev);
-            ll = kernel_ll(c, P.scale);
+            ll = second_slot(P, c);
             evals += 1;
         }
-        if (dfinite(xadd(lp, ll)) || t >= P.retry_cap) break;
+        if (ld_valid(P, lp, ll) || t >= P.retry_cap) break;
     }
     B.lp[i] = lp;
     B.ll[i] = ll;
@@ -101,13 +111,13 @@ k_ais_init_gk(AisBufs B, AisParams P, DPriors pri, DModel m, RoundKeys rk) {
             Stream st(rk, ST_PRIOR, (uint32_t)i, (uint32_t)t);
             for (int k = 0; k < 4; ++k) ok &= prior1_sample(pri.p[k], st, x[k]);
             lp = prior_logpdf(pri, [&](int k) { return x[k]; });
-            ll = lp;
+            ll = P.posterior == 1 ? -lp : lp;
             if (dfinite(lp)) {
                 double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, (uint32_t)t, x[0], x[1], x[2], x[3], gk_smem);
-                ll = kernel_ll(c, P.scale);
+                ll = second_slot(P, c);
                 evals += 1;
             }
-            if (dfinite(xadd(lp, ll)) || t >= P.retry_cap) break;
+            if (ld_valid(P, lp, ll) || t >= P.retry_cap) break;
         }
         if (threadIdx.x == 0) {
             for (int k = 0; k < 4; ++k) B.th[(long long)k * N + i] = x[k];
@@ -181,7 +191,7 @@ k_ais_propose(AisBufs B, AisParams P, DPriors pri, RoundKeys rk, long long lo, l
         push = dfinite(lpp);
         if (B.trace_on) {
             B.tr.move[i] = (unsigned char)move; B.tr.a[i] = a; B.tr.b[i] = b; B.tr.c[i] = c; B.tr.corr[i] = corr;
-            B.tr.lpp[i] = lpp; B.tr.llp[i] = lpp; B.tr.e[i] = dnan(); B.tr.dec[i] = 0;
+            B.tr.lpp[i] = lpp; B.tr.llp[i] = P.posterior == 1 ? -lpp : lpp; B.tr.e[i] = dnan(); B.tr.dec[i] = 0;
         }
     }
     // block-aggregated append to the work list: one global atomic per CTA
@@ -205,14 +215,20 @@ __device__ __forceinline__ unsigned int ais_accept(AisBufs &B, const AisParams &
                                                    uint32_t epoch, double cost) {
     const long long N = P.N;
     const double lpp = B.lpp[i];
-    const double llp = kernel_ll(cost, P.scale);
+    const double llp = second_slot(P, cost);
     int dec = 0;
     double e = dnan();
-    if (dfinite(xadd(lpp, llp))) {
+    if (ld_valid(P, lpp, llp)) {
         Stream sa(rk, ST_ACCEPT, (uint32_t)i, epoch);
         e = next_exp(sa);
-        const double lW = xsub(xadd(B.corr[i], xadd(lpp, llp)), xadd(B.lp[i], B.ll[i]));
-        dec = (-e <= lW) ? 2 : 1;
+        if (P.posterior == 1) { // ref src/types.jl:101-103: (-randexp <= lW) && lW2 >= 0
+            const double lW = xsub(xadd(B.corr[i], lpp), B.lp[i]);
+            const double lW2 = xsub(fmax(P.scale, B.ll[i]), llp);
+            dec = ((-e <= lW) && lW2 >= 0.0) ? 2 : 1;
+        } else {                // ref src/types.jl:73-74
+            const double lW = xsub(xadd(B.corr[i], xadd(lpp, llp)), xadd(B.lp[i], B.ll[i]));
+            dec = (-e <= lW) ? 2 : 1;
+        }
     }
     if (dec == 2) {
         for (int k = 0; k < P.d; ++k) B.th[(long long)k * N + i] = B.thp[(long long)k * N + i];
@@ -383,7 +399,8 @@ int kabc_ais_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
         return set_error(KABC_ERR_INVALID_ARG, "nparticles = %lld is insufficient, set number of particles in AIS(.) atleast to %d",
                          (long long)cfg->nwalkers, d + 5);
     if (cfg->nwalkers > 0x7FFFFFFFll) return set_error(KABC_ERR_INVALID_ARG, "nwalkers must be < 2^31");
-    if (!(cfg->scale > 0)) return set_error(KABC_ERR_INVALID_ARG, "kernel scale (target_average_cost) must be > 0");
+    if (cfg->posterior != 0 && cfg->posterior != 1) return set_error(KABC_ERR_INVALID_ARG, "posterior must be 0 (kernelized) or 1 (hard threshold)");
+    if (cfg->posterior == 0 && !(cfg->scale > 0)) return set_error(KABC_ERR_INVALID_ARG, "kernel scale (target_average_cost) must be > 0");
     if (cfg->nsamples < 0 || cfg->ntransitions < 1 || cfg->discard_initial < 0 || cfg->thinning < 1 || cfg->retry_sampling < 0)
         return set_error(KABC_ERR_INVALID_ARG, "bad AIS configuration");
     if (int rc = ingest_model(model, d, m)) return rc;
@@ -391,7 +408,7 @@ int kabc_ais_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     kabc_ais *s = new kabc_ais();
     s->ctx = ctx; s->pri = pri; s->model = m; s->cfg = *cfg;
     const long long N = cfg->nwalkers;
-    s->P.N = N; s->P.d = d; s->P.scale = cfg->scale; s->P.retry_cap = cfg->retry_sampling * N + 1;
+    s->P.N = N; s->P.d = d; s->P.scale = cfg->scale; s->P.posterior = cfg->posterior; s->P.retry_cap = cfg->retry_sampling * N + 1;
     const size_t nd = (size_t)N * d;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };

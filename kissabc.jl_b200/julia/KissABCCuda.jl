@@ -27,7 +27,7 @@ struct KabcSmcConfig
 end
 struct KabcAisConfig
     nwalkers::Int64; nsamples::Int64; ntransitions::Int64; discard_initial::Int64; thinning::Int64
-    retry_sampling::Int64; scale::Float64
+    retry_sampling::Int64; scale::Float64; posterior::Int32; _pad::Int32
 end
 struct KabcSmcLog
     iteration::Int64; eps::Float64; n_alive::Int64; flag::Int32; resampled::Int32
@@ -88,12 +88,24 @@ end
 function sample(model::ApproxKernelizedPosterior{<:Any,<:DeviceCost}, spl::AIS, Ns::Integer; ntransitions::Int=1,
                 discard_initial::Int=0, thinning::Int=1, retry_sampling::Int=100, context::Context=ctx(), kwargs...)
     pr = pods(model.prior); d = length(pr)
-    cfg = KabcAisConfig(spl.nparticles, Ns, ntransitions, discard_initial, thinning, retry_sampling, model.scale)
+    cfg = KabcAisConfig(spl.nparticles, Ns, ntransitions, discard_initial, thinning, retry_sampling, model.scale, 0, 0)
     out = Matrix{Float64}(undef, Ns, d); ev = Ref{Int64}(0); acc = Ref{Int64}(0)
     check(ccall((:kabc_ais_run, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{KabcPrior}, Cint, Ref{KabcModel}, Ref{KabcAisConfig}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
                 context.h, pr, d, pod(model.cost), cfg, out, ev, acc))
     bundle(out)                                                  # ref src/KissABC.jl:82-94
+end
+
+# hard-threshold posterior, ref src/types.jl:76-104: same entry point, posterior = 1, scale = maxcost
+function sample(model::KissABC.ApproxPosterior{<:Any,<:DeviceCost}, spl::AIS, Ns::Integer; ntransitions::Int=1,
+                discard_initial::Int=0, thinning::Int=1, retry_sampling::Int=100, context::Context=ctx(), kwargs...)
+    pr = pods(model.prior); d = length(pr)
+    cfg = KabcAisConfig(spl.nparticles, Ns, ntransitions, discard_initial, thinning, retry_sampling, model.maxcost, 1, 0)
+    out = Matrix{Float64}(undef, Ns, d); ev = Ref{Int64}(0); acc = Ref{Int64}(0)
+    check(ccall((:kabc_ais_run, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{KabcPrior}, Cint, Ref{KabcModel}, Ref{KabcAisConfig}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+                context.h, pr, d, pod(model.cost), cfg, out, ev, acc))
+    bundle(out)
 end
 
 export DeviceCost, NormalMeanStd, MA2, GandK, LotkaVolterra, Context

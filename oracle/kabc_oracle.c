@@ -846,19 +846,28 @@ void kor_ais_destroy(kor_ais_t *s) {
     free(s->tb); free(s->tc); free(s->tcorr); free(s->tlpp); free(s->tllp); free(s->te); free(s);
 }
 
-/* ref: src/types.jl:51-58 -- (logprior, loglikelihood) of the kernelized posterior */
+/* ref: src/types.jl:51-58 -- (logprior, loglikelihood) of the kernelized posterior (cfg.posterior == 0);
+ * ref: src/types.jl:84-91 -- (logprior, cost) of the hard-threshold ApproxPosterior (cfg.posterior == 1): the second
+ * slot then holds the cost itself (-logprior when the prior is not finite). */
 static void ais_loglike(kor_ais_t *s, const double *x, uint32_t tag, uint32_t id, uint32_t epoch, double *lp,
                         double *ll, int *evals) {
     double p = kor_prior_logpdf(s->prior, s->d, x);
-    double l = p;
+    double l = s->cfg.posterior == 1 ? -p : p;
     if (isfinite(p)) {
         double c = cost_dispatch(&s->model, s->seed, tag, s->d, x, id, epoch);
-        double q = c / s->cfg.scale;
-        l = -0.5 * (q * q);
+        if (s->cfg.posterior == 1) l = c;
+        else {
+            double q = c / s->cfg.scale;
+            l = -0.5 * (q * q);
+        }
         *evals += 1;
     }
     *lp = p;
     *ll = l;
+}
+/* ref: src/types.jl:60 and :93-94 */
+static int ais_valid(const kor_ais_t *s, double lp, double ll) {
+    return s->cfg.posterior == 1 ? (isfinite(ll) && isfinite(lp)) : isfinite(lp + ll);
 }
 
 /* ref: src/KissABC.jl:50-61.  attempt t of walker i uses epoch t of the PRIOR / COST_INIT streams */
@@ -877,7 +886,7 @@ int kor_ais_init(kor_ais_t *s) {
         for (;; ++t) {
             bad |= kor_prior_sample(s->seed, s->prior, d, (uint32_t)i, (uint32_t)t, th);
             ais_loglike(s, th, ST_COST_INIT, (uint32_t)i, (uint32_t)t, &lp, &ll, &evals);
-            if (isfinite(lp + ll) || t >= cap) break;
+            if (ais_valid(s, lp, ll) || t >= cap) break;
         }
         retries += t;
         evals_total += evals;
@@ -956,13 +965,19 @@ static int ais_transition_from(kor_ais_t *s, const double *src, int64_t i, int64
     /* ref: src/types.jl:69-74 */
     int dec;
     double e = NAN;
-    if (!isfinite(lpp + llp)) dec = 0;
+    if (!ais_valid(s, lpp, llp)) dec = 0;
     else {
         stream_t sa;
         stream_init(&sa, s->seed, ST_ACCEPT, (uint32_t)i, epoch);
         e = next_exp(&sa);
-        double lW = (corr + (lpp + llp)) - (s->lp[i] + s->ll[i]);
-        dec = (-e <= lW) ? 2 : 1;
+        if (s->cfg.posterior == 1) { /* ref: src/types.jl:101-103 */
+            double lW = (corr + lpp) - s->lp[i];
+            double lW2 = fmax(s->cfg.scale, s->ll[i]) - llp;
+            dec = ((-e <= lW) && lW2 >= 0) ? 2 : 1;
+        } else {                     /* ref: src/types.jl:73-74 */
+            double lW = (corr + (lpp + llp)) - (s->lp[i] + s->ll[i]);
+            dec = (-e <= lW) ? 2 : 1;
+        }
     }
     s->tmove[i] = (uint8_t)move; s->ta[i] = a; s->tb[i] = b; s->tc[i] = c; s->tcorr[i] = corr;
     for (int k = 0; k < d; ++k) s->thp[(int64_t)k * N + i] = p[k];

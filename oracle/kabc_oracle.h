@@ -71,7 +71,9 @@ typedef struct {
     int64_t discard_initial;
     int64_t thinning;
     int64_t retry_sampling;
-    double scale;
+    double scale;      /* kernel scale (posterior 0) or max_cost (posterior 1) */
+    int32_t posterior; /* 0 ApproxKernelizedPosterior, 1 ApproxPosterior (hard threshold) */
+    int32_t _pad;
 } kor_ais_config_t;
 
 /* per-iteration log record (same layout as kabc_smc_log_t) */

@@ -39,7 +39,7 @@ class SmcConfig(C.Structure):
 class AisConfig(C.Structure):
     _fields_ = [("nwalkers", C.c_int64), ("nsamples", C.c_int64), ("ntransitions", C.c_int64),
                 ("discard_initial", C.c_int64), ("thinning", C.c_int64), ("retry_sampling", C.c_int64),
-                ("scale", C.c_double)]
+                ("scale", C.c_double), ("posterior", C.c_int32), ("_pad", C.c_int32)]
 
 
 class SmcLog(C.Structure):
@@ -194,9 +194,10 @@ def smc_config(nparticles=100, alpha=0.95, mcmc_retrys=0, mcmc_tol=0.015, epstol
                      float(r_epstol), float(min_r_ess), float(max_stretch), int(verbose), int(max_iterations))
 
 
-def ais_config(nwalkers, nsamples, ntransitions=1, discard_initial=0, thinning=1, retry_sampling=100, scale=1.0):
+def ais_config(nwalkers, nsamples, ntransitions=1, discard_initial=0, thinning=1, retry_sampling=100, scale=1.0,
+               posterior=0):
     return AisConfig(int(nwalkers), int(nsamples), int(ntransitions), int(discard_initial), int(thinning),
-                     int(retry_sampling), float(scale))
+                     int(retry_sampling), float(scale), int(posterior), 0)
 
 
 def philox(ctr, key):

@@ -38,7 +38,7 @@ def test_version_and_loud_failure_without_gpu(kabc):
 def test_pod_layouts_match_header(kabc):
     K = kabc._capi
     assert C.sizeof(K.PriorT) == 40 and C.sizeof(K.ModelT) == 16 + 32 * 8 + 8 * 8
-    assert C.sizeof(K.SmcConfigT) == 72 and C.sizeof(K.AisConfigT) == 56 and C.sizeof(K.SmcLogT) == 56
+    assert C.sizeof(K.SmcConfigT) == 72 and C.sizeof(K.AisConfigT) == 64 and C.sizeof(K.SmcLogT) == 56
     from oracle import oracle as O
     for a, b in [(K.PriorT, O.Prior), (K.ModelT, O.Model), (K.SmcConfigT, O.SmcConfig), (K.AisConfigT, O.AisConfig), (K.SmcLogT, O.SmcLog)]:
         assert [(n, t) for n, t in a._fields_] == [(n, t) for n, t in b._fields_]

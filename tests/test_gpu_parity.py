@@ -303,6 +303,30 @@ def test_ais_sweeps_f64_bit_exact(oracle, kabc, ctx, name, N, scale, ndraws):
     assert da.counters()["accepted"] > 0
 
 
+@pytest.mark.parametrize("name,N,maxcost,ndraws", [("normal", 40, 0.3, 100), ("ma2", 300, 0.5, 100)])
+def test_ais_hard_threshold_posterior_bit_exact(oracle, kabc, ctx, name, N, maxcost, ndraws):
+    """ApproxPosterior (ref src/types.jl:76-104): (logprior, cost) state, accept = (-randexp <= lW) && max(maxcost,old)-new >= 0."""
+    cfg = dict(nwalkers=N, nsamples=1, scale=maxcost, posterior=1)
+    oa, da = _ais_pair(oracle, kabc, ctx, name, "f64", cfg, ndraws)
+    da.trace_enable(True)
+    oa.init(); da.init()
+    for a, b, what in zip(oa.state(), da.state(), ("theta", "lp", "cost")):
+        assert_bits_equal(b, a, f"hard-threshold init {what}")
+    cost0 = da.state()[2].copy()
+    assert (cost0 >= 0).all()                  # the second slot is the cost itself
+    for sw in range(20):
+        oa.sweep(); da.sweep(1)
+        for a, b, what in zip(oa.state(), da.state(), ("theta", "lp", "cost")):
+            assert_bits_equal(b, a, f"hard-threshold sweep {sw} {what}")
+        to, td = oa.trace(), da.trace()
+        assert (to["decision"] == td["decision"]).all()
+        assert_bits_equal(td["ll_p"], to["ll_p"], "proposal cost")
+        assert oa.counters() == da.counters()
+    th, lp, cost = da.state()
+    # a walker only ever moves to cost <= max(maxcost, its current cost)
+    assert da.counters()["accepted"] > 0 and (cost <= np.maximum(maxcost, cost0)).all() and cost.mean() < cost0.mean()
+
+
 def test_ais_run_matches_oracle_and_readme(oracle, kabc, ctx):
     """sample(ApproxKernelizedPosterior(prior,cost,0.005), AIS(10), 1000, ntransitions=100) -- config 1 -- through
     the one-call C ABI: bit-exact against the oracle's red/black run, and README.md:64-66 posterior."""
@@ -350,6 +374,8 @@ def test_deterministic_cost_reference_tests(kabc, ctx):
     s = kabc.sample(post, kabc.AIS(12), 500, discard_initial=1000, ctx=ctx)
     sim = kabc.Particles(s.particles ** 2 + 1)
     assert abs(sim.mean() - 1.5) < 0.01
-    post = kabc.ApproxKernelizedPosterior(kabc.Uniform(-10, 10), kabc.Deterministic(1, 1.5), 0.01)
-    s = kabc.sample(post, kabc.AIS(20), 500, discard_initial=2000, ntransitions=5, ctx=ctx)
-    assert abs(s.mean() - 1.5) < 0.02
+    # ref test/runtests.jl:177-182 verbatim: plan = ApproxPosterior(Normal(0,1), x -> abs(x-1.5), 0.01); AIS(20), 100
+    # samples, discard_initial = 2000; @test res ≈ 1.5 (MonteCarloMeasurements: |mean - 1.5| / std < 2)
+    plan = kabc.ApproxPosterior(kabc.Normal(0, 1), kabc.Deterministic(1, 1.5), 0.01)
+    s = kabc.sample(plan, kabc.AIS(20), 100, discard_initial=2000, ctx=ctx)
+    assert s.approx(1.5) and abs(s.mean() - 1.5) < 0.01 and (np.abs(s.particles - 1.5) <= 0.01 + 1e-12).all()

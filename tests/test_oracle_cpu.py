@@ -376,6 +376,19 @@ def test_ais_reference_schedule_counts_and_readme_posterior(oracle):
     assert abs(mu.mean() - 2.0) < 0.004 and abs(sg.mean() - 0.04) < 0.0005 and 0.0005 < sg.std() < 0.0016
 
 
+def test_ais_hard_threshold_issue10(oracle):
+    """ref test/runtests.jl:177-182: ApproxPosterior(Normal(0,1), x -> abs(x-1.5), 0.01), AIS(20), 100 samples,
+    discard_initial = 2000 -> res ≈ 1.5; every retained sample obeys the hard threshold."""
+    pri = oracle.make_priors([("normal", 0, 1)])
+    m = oracle.make_model(oracle.DETERMINISTIC, 0, (1.5,), (1.0,))
+    a = oracle.Ais(SEED, pri, m, oracle.ais_config(20, 100, discard_initial=2000, scale=0.01, posterior=1))
+    out = a.run_sequential()[0]
+    assert abs(out.mean() - 1.5) / out.std(ddof=1) < 2 and (np.abs(out - 1.5) <= 0.01).all()
+    b = oracle.Ais(SEED, pri, m, oracle.ais_config(20, 100, discard_initial=2000, scale=0.01, posterior=1))
+    out = b.run_parallel()[0]
+    assert abs(out.mean() - 1.5) / out.std(ddof=1) < 2 and (np.abs(out - 1.5) <= 0.01).all()
+
+
 def test_ais_errors(oracle):
     M = models(oracle, None)["normal"]
     with pytest.raises(oracle.OracleError, match="is insufficient"):
