@@ -39,13 +39,24 @@ enum kabc_status {
     KABC_ERR_STATE = 6         /* handle used out of order */
 };
 
-/* ---- prior: Factored(Uniform(a,b), Normal(mu,sigma), Truncated(Normal(mu,sigma),lo,hi), ...)
- *      replaces src/priors.jl:10-49 + the Distributions.jl univariate laws it delegates to ---- */
-enum kabc_prior_kind { KABC_PRIOR_UNIFORM = 0, KABC_PRIOR_NORMAL = 1, KABC_PRIOR_TRUNC_NORMAL = 2 };
+/* ---- prior: Factored(Uniform(a,b), Normal(mu,sigma), Truncated(Normal(mu,sigma),lo,hi), Beta(a,b),
+ *      NegativeBinomial(r,p), DiscreteUniform(a,b), ...)
+ *      replaces src/priors.jl:10-49 + the Distributions.jl univariate laws it delegates to.  Components of a discrete law
+ *      (NegativeBinomial, DiscreteUniform) follow push_p, src/types.jl:28-32: the particle keeps its real value, the prior
+ *      density and the cost see round(Int, .), and so do the returned samples ---- */
+enum kabc_prior_kind {
+    KABC_PRIOR_UNIFORM = 0,
+    KABC_PRIOR_NORMAL = 1,
+    KABC_PRIOR_TRUNC_NORMAL = 2,
+    KABC_PRIOR_BETA = 3,            /* test/runtests.jl:51, examples/example_n2.jl:28 */
+    KABC_PRIOR_NEG_BINOMIAL = 4,    /* test/runtests.jl:50 */
+    KABC_PRIOR_DISCRETE_UNIFORM = 5 /* test/runtests.jl:106 */
+};
 typedef struct {
     int32_t kind;
     int32_t _pad;
-    double p0, p1; /* Uniform: a,b.  Normal / Truncated(Normal): mu, sigma */
+    double p0, p1; /* Uniform: a,b.  Normal / Truncated(Normal): mu, sigma.  Beta: alpha, beta.  NegativeBinomial: r, p.
+                      DiscreteUniform: a, b (integers) */
     double lo, hi; /* Truncated: support bounds (ignored otherwise) */
 } kabc_prior_t;
 #define KABC_MAX_DIM 16
@@ -57,7 +68,10 @@ enum kabc_model_kind {
     KABC_MODEL_MA2_AUTOCOV = 1,    /* MA(2), n obs; || (tau1,tau2) - target ||_2; +Inf outside the triangle */
     KABC_MODEL_GK_OCTILE = 2,      /* g-and-k, n draws, 7 octiles; param0 = c (0.8) */
     KABC_MODEL_LV_SSA = 3,         /* Lotka-Volterra Gillespie; param = {X0,Y0,T,G,max_events}; target = [X(t_g), Y(t_g)] */
-    KABC_MODEL_DETERMINISTIC = 4   /* test/runtests.jl:77-86 (param0=0: |th^2+1-t0|) and :177-182 (param0=1: |th-t0|) */
+    KABC_MODEL_DETERMINISTIC = 4,  /* test/runtests.jl:77-86 (param0=0: |th^2+1-t0|), :177-182 (param0=1: |th-t0|) and
+                                      :105-112 (param0=2, d=2: |(th0^2+th1)*(th0+randn*param1) - t0|) */
+    KABC_MODEL_SOCKS = 5           /* test/runtests.jl:34-44, d=2 (n_socks, prop_pairs); param0 = n_picked (<= 32);
+                                      cost = |pairs - t0| + |odds - t1| */
 };
 enum kabc_precision {
     KABC_F64 = 0,      /* simulator entirely in FP64, bit-reproducible against the oracle */

@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libkissabc_cuda.so")
 
 KABC_OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_RETRY_BUDGET, ERR_DEGENERATE, ERR_STATE = 1, 2, 3, 4, 5, 6
-PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_TRUNC_NORMAL = 0, 1, 2
-MODEL_NORMAL_MEANSTD, MODEL_MA2_AUTOCOV, MODEL_GK_OCTILE, MODEL_LV_SSA, MODEL_DETERMINISTIC = 0, 1, 2, 3, 4
+PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_TRUNC_NORMAL, PRIOR_BETA, PRIOR_NEG_BINOMIAL, PRIOR_DISCRETE_UNIFORM = 0, 1, 2, 3, 4, 5
+MODEL_NORMAL_MEANSTD, MODEL_MA2_AUTOCOV, MODEL_GK_OCTILE, MODEL_LV_SSA, MODEL_DETERMINISTIC, MODEL_SOCKS = 0, 1, 2, 3, 4, 5
 F64, F32_ACC64 = 0, 1
 NCCL_ID_BYTES = 128
 MAX_DIM = 16

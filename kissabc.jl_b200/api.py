@@ -65,6 +65,37 @@ class Truncated(UnivariateDistribution):
         return K.PriorT(K.PRIOR_TRUNC_NORMAL, 0, float(self.base.mu), float(self.base.sigma), float(self.lo), float(self.hi))
 
 
+@dataclass(frozen=True)
+class Beta(UnivariateDistribution):
+    """Beta(alpha, beta), ref test/runtests.jl:51, examples/example_n2.jl:28."""
+    alpha: float = 1.0
+    beta: float = 1.0
+
+    def _pod(self):
+        return K.PriorT(K.PRIOR_BETA, 0, float(self.alpha), float(self.beta), 0.0, 1.0)
+
+
+@dataclass(frozen=True)
+class NegativeBinomial(UnivariateDistribution):
+    """NegativeBinomial(r, p) (Distributions.jl parametrisation: failures before the r-th success), discrete:
+    particles are rounded (push_p, ref src/types.jl:32) before the prior density and the cost see them."""
+    r: float = 1.0
+    p: float = 0.5
+
+    def _pod(self):
+        return K.PriorT(K.PRIOR_NEG_BINOMIAL, 0, float(self.r), float(self.p), 0.0, math.inf)
+
+
+@dataclass(frozen=True)
+class DiscreteUniform(UnivariateDistribution):
+    """DiscreteUniform(a, b) on the integers a..b, discrete (push_p, ref src/types.jl:32)."""
+    a: int = 0
+    b: int = 1
+
+    def _pod(self):
+        return K.PriorT(K.PRIOR_DISCRETE_UNIFORM, 0, float(self.a), float(self.b), float(self.a), float(self.b))
+
+
 class Factored:
     """Product prior, ref src/priors.jl:10-13.  `length(Factored)` = number of components (:49)."""
 
@@ -166,6 +197,23 @@ class Deterministic(DeviceCost):
 
     def __init__(self, variant=0, target=1.5):
         super().__init__(0, (target,), (float(variant),), "f64")
+
+
+class NoisyProduct(DeviceCost):
+    """ref test/runtests.jl:105-112: sim((n, du)) = (n*n + du) * (n + randn()*noise); cost = |sim - target|."""
+    kind, ndim = K.MODEL_DETERMINISTIC, 2
+
+    def __init__(self, target=5.5, noise=0.01):
+        super().__init__(0, (target,), (2.0, float(noise)), "f64")
+
+
+class Socks(DeviceCost):
+    """"Tiny Data, ABC and the Socks of Karl Broman", ref test/runtests.jl:34-44 and :56: theta = (n_socks, prop_pairs);
+    n_picked socks are drawn without replacement; cost = |pairs - target[0]| + |odds - target[1]|."""
+    kind, ndim = K.MODEL_SOCKS, 2
+
+    def __init__(self, target=(0, 11), n_picked=11):
+        super().__init__(0, tuple(target), (float(n_picked),), "f64")
 
 
 # --------------------------------------------------------------------------------------- results

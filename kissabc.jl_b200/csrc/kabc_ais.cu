@@ -80,7 +80,7 @@ k_ais_init(AisBufs B, AisParams P, DPriors pri, DModel m, RoundKeys rk) {
             B.th[(long long)k * N + i] = x;
         }
         const double *th = B.th;
-        lp = prior_logpdf(pri, [&](int k) { return th[(long long)k * N + i]; });
+        lp = prior_logpdf_pushed(pri, [&](int k) { return th[(long long)k * N + i]; });
         ll = P.posterior == 1 ? -lp : lp;
         if (dfinite(lp)) {
             long long ev;
@@ -110,10 +110,11 @@ k_ais_init_gk(AisBufs B, AisParams P, DPriors pri, DModel m, RoundKeys rk) {
         for (;; ++t) { // every thread draws the same prior sample (same stream), so the loop is uniform
             Stream st(rk, ST_PRIOR, (uint32_t)i, (uint32_t)t);
             for (int k = 0; k < 4; ++k) ok &= prior1_sample(pri.p[k], st, x[k]);
-            lp = prior_logpdf(pri, [&](int k) { return x[k]; });
+            lp = prior_logpdf_pushed(pri, [&](int k) { return x[k]; });
             ll = P.posterior == 1 ? -lp : lp;
             if (dfinite(lp)) {
-                double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, (uint32_t)t, x[0], x[1], x[2], x[3], gk_smem);
+                double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, (uint32_t)t, pushk(m, 0, x[0]), pushk(m, 1, x[1]),
+                                            pushk(m, 2, x[2]), pushk(m, 3, x[3]), gk_smem);
                 ll = second_slot(P, c);
                 evals += 1;
             }
@@ -185,7 +186,7 @@ k_ais_propose(AisBufs B, AisParams P, DPriors pri, RoundKeys rk, long long lo, l
             }
         }
         const double *thp = B.thp;
-        const double lpp = prior_logpdf(pri, [&](int k) { return thp[(long long)k * N + i]; });
+        const double lpp = prior_logpdf_pushed(pri, [&](int k) { return thp[(long long)k * N + i]; });
         B.lpp[i] = lpp;
         B.corr[i] = corr;
         push = dfinite(lpp);
@@ -269,7 +270,8 @@ __global__ void __launch_bounds__(GK_THREADS) k_ais_simulate_gk(AisBufs B, AisPa
     for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const long long i = B.work[w];
         const double *thp = B.thp;
-        double c = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, epoch, thp[i], thp[N + i], thp[2 * N + i], thp[3 * N + i], gk_smem);
+        double c = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, epoch, pushk(m, 0, thp[i]), pushk(m, 1, thp[N + i]),
+                                    pushk(m, 2, thp[2 * N + i]), pushk(m, 3, thp[3 * N + i]), gk_smem);
         if (threadIdx.x == 0 && ais_accept(B, P, rk, i, epoch, c)) atomicAdd(&ctl->accepted, 1ull);
     }
 }
@@ -289,12 +291,15 @@ __global__ void k_ais_reset(AisBufs B) {
 
 // bundle_samples, ref src/KissABC.jl:78,90-93: saved sample m is walker w_m of the current ensemble
 __global__ void k_ais_record(AisBufs B, AisParams P, double *out, long long Ns, long long m0, long long m1,
-                             long long discard, long long thinning) {
+                             long long discard, long long thinning, uint32_t push_mask) {
     long long m = m0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= m1) return;
     const long long target = discard + m * thinning;
     const long long w = target > 0 ? (target - 1) % P.N : P.N - 1;
-    for (int k = 0; k < P.d; ++k) out[(long long)k * Ns + m] = B.th[(long long)k * P.N + w];
+    for (int k = 0; k < P.d; ++k) { // ref src/KissABC.jl:78: the recorded sample is push_p(model, sample[i])
+        double v = B.th[(long long)k * P.N + w];
+        out[(long long)k * Ns + m] = (push_mask >> k) & 1u ? rint(v) : v;
+    }
 }
 
 } // namespace kabc
@@ -366,6 +371,7 @@ static int ais_enqueue_half(kabc_ais *s, int colour) {
     case KABC_MODEL_MA2_AUTOCOV: ais_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s, n); break;
     case KABC_MODEL_LV_SSA: ais_launch_sim_t<KABC_MODEL_LV_SSA>(s, n); break;
     case KABC_MODEL_DETERMINISTIC: ais_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s, n); break;
+    case KABC_MODEL_SOCKS: ais_launch_sim_t<KABC_MODEL_SOCKS>(s, n); break;
     case KABC_MODEL_GK_OCTILE: {
         size_t smem;
         int grid = ais_gk_grid(s, n, smem);
@@ -404,6 +410,7 @@ int kabc_ais_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     if (cfg->nsamples < 0 || cfg->ntransitions < 1 || cfg->discard_initial < 0 || cfg->thinning < 1 || cfg->retry_sampling < 0)
         return set_error(KABC_ERR_INVALID_ARG, "bad AIS configuration");
     if (int rc = ingest_model(model, d, m)) return rc;
+    m.push_mask = push_mask_of(pri);
     KABC_CUDA_TRY(cudaSetDevice(ctx->device));
     kabc_ais *s = new kabc_ais();
     s->ctx = ctx; s->pri = pri; s->model = m; s->cfg = *cfg;
@@ -449,6 +456,7 @@ int kabc_ais_init(kabc_ais_t *s) {
     case KABC_MODEL_MA2_AUTOCOV: ais_launch_init_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
     case KABC_MODEL_LV_SSA: ais_launch_init_t<KABC_MODEL_LV_SSA>(s); break;
     case KABC_MODEL_DETERMINISTIC: ais_launch_init_t<KABC_MODEL_DETERMINISTIC>(s); break;
+    case KABC_MODEL_SOCKS: ais_launch_init_t<KABC_MODEL_SOCKS>(s); break;
     case KABC_MODEL_GK_OCTILE: {
         size_t smem;
         int grid = ais_gk_grid(s, s->P.N, smem);
@@ -594,7 +602,7 @@ int kabc_ais_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
         long long m1 = m;
         while (m1 < Ns && need_of(m1) == need) ++m1;
         if (!rc) {
-            k_ais_record<<<(unsigned)((m1 - m + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, dout.p, Ns, m, m1, cfg->discard_initial, cfg->thinning);
+            k_ais_record<<<(unsigned)((m1 - m + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, dout.p, Ns, m, m1, cfg->discard_initial, cfg->thinning, s->model.push_mask);
             AIS_LAUNCHED(s);
         }
         m = m1;

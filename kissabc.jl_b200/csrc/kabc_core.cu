@@ -29,7 +29,7 @@ int ingest_priors(const kabc_prior_t *prior, int d, DPriors &out) {
         DPrior &q = out.p[k];
         q.kind = p.kind;
         q.p0 = p.p0; q.p1 = p.p1; q.lo = p.lo; q.hi = p.hi;
-        q.c0 = 0.0; q.c1 = 0.0;
+        q.c0 = 0.0; q.c1 = 0.0; q.c2 = 0.0;
         switch (p.kind) {
         case KABC_PRIOR_UNIFORM:
             if (!(p.p1 > p.p0)) return set_error(KABC_ERR_INVALID_ARG, "Uniform(a,b) needs a < b (component %d)", k);
@@ -45,6 +45,23 @@ int ingest_priors(const kabc_prior_t *prior, int d, DPriors &out) {
             q.c0 = log(p.p1);
             q.c1 = log(std_normal_cdf((p.hi - p.p0) / p.p1) - std_normal_cdf((p.lo - p.p0) / p.p1));
             break;
+        case KABC_PRIOR_BETA:
+            if (!(p.p0 > 0 && p.p1 > 0) || !std::isfinite(p.p0) || !std::isfinite(p.p1))
+                return set_error(KABC_ERR_INVALID_ARG, "Beta(a,b) needs a, b > 0 (component %d)", k);
+            q.c0 = (lgamma(p.p0) + lgamma(p.p1)) - lgamma(p.p0 + p.p1);
+            break;
+        case KABC_PRIOR_NEG_BINOMIAL:
+            if (!(p.p0 > 0) || !std::isfinite(p.p0) || !(p.p1 > 0 && p.p1 <= 1))
+                return set_error(KABC_ERR_INVALID_ARG, "NegativeBinomial(r,p) needs r > 0 and 0 < p <= 1 (component %d)", k);
+            q.c0 = lgamma(p.p0);
+            q.c1 = p.p0 * log(p.p1);
+            q.c2 = log1p(-p.p1);
+            break;
+        case KABC_PRIOR_DISCRETE_UNIFORM:
+            if (p.p0 != floor(p.p0) || p.p1 != floor(p.p1) || !(p.p1 >= p.p0) || !(p.p1 - p.p0 < 2147483647.0))
+                return set_error(KABC_ERR_INVALID_ARG, "DiscreteUniform(a,b) needs integers a <= b (component %d)", k);
+            q.c0 = log((p.p1 - p.p0) + 1.0);
+            break;
         default:
             return set_error(KABC_ERR_INVALID_ARG, "unknown prior kind %d (component %d)", p.kind, k);
         }
@@ -55,6 +72,7 @@ int ingest_priors(const kabc_prior_t *prior, int d, DPriors &out) {
 int ingest_model(const kabc_model_t *model, int d, DModel &out) {
     if (!model) return set_error(KABC_ERR_INVALID_ARG, "model is NULL");
     out.kind = model->kind;
+    out.push_mask = 0;
     out.precision = model->precision;
     out.n_draws = model->n_draws;
     out.n_target = model->n_target;
@@ -82,6 +100,14 @@ int ingest_model(const kabc_model_t *model, int d, DModel &out) {
             return set_error(KABC_ERR_INVALID_ARG, "Lotka-Volterra grid size param[3] must be in 1..%d", KABC_MAX_TARGET / 2);
         break;
     case KABC_MODEL_DETERMINISTIC:
+        if (model->param[0] == 2.0 && d != 2)
+            return set_error(KABC_ERR_INVALID_ARG, "deterministic model with param0 = 2 needs d = 2 (n, du)");
+        break;
+    case KABC_MODEL_SOCKS:
+        if (d != 2) return set_error(KABC_ERR_INVALID_ARG, "socks model needs d = 2 (n_socks, prop_pairs)");
+        if (!(model->param[0] >= 1 && model->param[0] <= KABC_SOCKS_MAX_PICKED) || model->param[0] != floor(model->param[0]))
+            return set_error(KABC_ERR_INVALID_ARG, "socks model needs 1 <= n_picked (param0) <= %d", KABC_SOCKS_MAX_PICKED);
+        if (model->n_target != 2) return set_error(KABC_ERR_INVALID_ARG, "socks model needs n_target = 2 (pairs, odds)");
         break;
     default:
         return set_error(KABC_ERR_INVALID_ARG, "unknown model kind %d", model->kind);
@@ -156,6 +182,7 @@ int eval_cost_device(kabc_ctx *ctx, const DModel &m, const double *d_th, long lo
     case KABC_MODEL_MA2_AUTOCOV: launch_eval<KABC_MODEL_MA2_AUTOCOV>(ctx, m, d_th, n, first_id, epoch, d_out, d_ev); break;
     case KABC_MODEL_LV_SSA: launch_eval<KABC_MODEL_LV_SSA>(ctx, m, d_th, n, first_id, epoch, d_out, d_ev); break;
     case KABC_MODEL_DETERMINISTIC: launch_eval<KABC_MODEL_DETERMINISTIC>(ctx, m, d_th, n, first_id, epoch, d_out, d_ev); break;
+    case KABC_MODEL_SOCKS: launch_eval<KABC_MODEL_SOCKS>(ctx, m, d_th, n, first_id, epoch, d_out, d_ev); break;
     case KABC_MODEL_GK_OCTILE: {
         size_t smem = gk_smem_bytes(m.n_draws, m.precision);
         long long cap = (long long)ctx->sm_count * gk_blocks_per_sm(m.n_draws, m.precision);

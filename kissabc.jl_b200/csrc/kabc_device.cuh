@@ -196,20 +196,71 @@ __device__ __forceinline__ void normal_pair32(uint32_t w0, uint32_t w1, float &z
     z1 = __fmul_rn(r, mufu_sin(ang));
 }
 
+// log Gamma(x), x > 0 (part of the variate spec): recurrence up to x >= 10, then the Stirling series through x^-13
+static __constant__ double KC_LGAMMA[7] = {1.0 / 156.0, -691.0 / 360360.0, 1.0 / 1188.0, -1.0 / 1680.0, 1.0 / 1260.0,
+                                           -1.0 / 360.0, 1.0 / 12.0};
+static __device__ __noinline__ double xlgamma(double x) {
+    if (x != x) return x;
+    if (x < 0.0) return dnan();
+    if (x == 0.0 || x == dinf()) return dinf();
+    double prod = 1.0;
+    while (x < 10.0) { prod = xmul(prod, x); x = xadd(x, 1.0); }
+    double xi = xdiv(1.0, x);
+    double x2 = xmul(xi, xi);
+    double p = KC_LGAMMA[0];
+#pragma unroll
+    for (int q = 1; q < 7; ++q) p = xfma(p, x2, KC_LGAMMA[q]);
+    double r = xadd(xadd(xsub(xmul(xsub(x, 0.5), xlog(x)), x), 0.91893853320467274178), xmul(p, xi));
+    return xsub(r, xlog(prod));
+}
+
 // ---------------------------------------------------------------- priors
 #define KABC_LOG2PI 1.8378770664093453
 struct DPrior {
     int kind;
     double p0, p1, lo, hi;
-    double c0; // Uniform: log(b-a); Normal/Truncated: log(sigma)     (host libm, same expression as the oracle)
-    double c1; // Truncated: log(Phi((hi-mu)/sigma) - Phi((lo-mu)/sigma))
+    // host libm, same expressions as the oracle:
+    double c0; // Uniform: log(b-a); Normal/Truncated: log(sigma); Beta: logbeta(a,b); NegativeBinomial: lgamma(r);
+               // DiscreteUniform: log(b-a+1)
+    double c1; // Truncated: log(Phi((hi-mu)/sigma) - Phi((lo-mu)/sigma)); NegativeBinomial: r*log(p)
+    double c2; // NegativeBinomial: log1p(-p)
 };
 struct DPriors {
     int d;
     DPrior p[KABC_MAX_DIM];
 };
+__host__ __device__ __forceinline__ bool prior_is_discrete(const DPrior &p) {
+    return p.kind == KABC_PRIOR_NEG_BINOMIAL || p.kind == KABC_PRIOR_DISCRETE_UNIFORM;
+}
+// ref src/types.jl:28-32 push_p: round(Int, .) (ties to even) for discrete laws, identity otherwise
+__device__ __forceinline__ double push1(const DPrior &p, double x) { return prior_is_discrete(p) ? rint(x) : x; }
+__host__ __device__ __forceinline__ uint32_t push_mask_of(const DPriors &P) {
+    uint32_t m = 0;
+    for (int k = 0; k < P.d; ++k) m |= prior_is_discrete(P.p[k]) ? (1u << k) : 0u;
+    return m;
+}
+
+// the laws outside the headline workloads stay out of line so the hot kernels only pay a compare for them
+// (scalars, not a DPrior reference: taking the address of a kernel parameter would spill the whole DPriors to local memory)
+static __device__ __noinline__ double prior1_logpdf_ext(int kind, double p0, double p1, double c0, double c1, double c2,
+                                                        double x) {
+    if (kind == KABC_PRIOR_BETA) {
+        if (!(x >= 0.0 && x <= 1.0)) return -dinf();
+        double am = xsub(p0, 1.0), bm = xsub(p1, 1.0);
+        double t1 = am == 0.0 ? 0.0 : xmul(am, xlog(x));
+        double t2 = bm == 0.0 ? 0.0 : xmul(bm, xlog(xsub(1.0, x)));
+        return xsub(xadd(t1, t2), c0);
+    }
+    if (kind == KABC_PRIOR_NEG_BINOMIAL) {
+        if (!(x >= 0.0) || x != floor(x) || x == dinf()) return -dinf();
+        return xadd(xsub(xsub(xlgamma(xadd(x, p0)), xlgamma(xadd(x, 1.0))), c0), xadd(c1, xmul(x, c2)));
+    }
+    if (kind == KABC_PRIOR_DISCRETE_UNIFORM) return (x >= p0 && x <= p1 && x == floor(x)) ? -c0 : -dinf();
+    return dnan();
+}
 
 __device__ __forceinline__ double prior1_logpdf(const DPrior &p, double x) {
+    if (p.kind >= KABC_PRIOR_BETA) return prior1_logpdf_ext(p.kind, p.p0, p.p1, p.c0, p.c1, p.c2, x);
     if (p.kind == KABC_PRIOR_UNIFORM) return (x >= p.p0 && x <= p.p1) ? -p.c0 : -dinf();
     if (p.kind == KABC_PRIOR_TRUNC_NORMAL && !(x >= p.lo && x <= p.hi)) return -dinf();
     double z = xdiv(xsub(x, p.p0), p.p1);
@@ -223,8 +274,86 @@ __device__ __forceinline__ double prior_logpdf(const DPriors &P, F get) {
     for (int k = 1; k < P.d; ++k) s = xadd(s, prior1_logpdf(P.p[k], get(k)));
     return s;
 }
+// logpdf(prior, push_p(prior, x)), ref src/smc.jl:125,172 and src/KissABC.jl:51
+template <typename F>
+__device__ __forceinline__ double prior_logpdf_pushed(const DPriors &P, F get) {
+    return prior_logpdf(P, [&](int k) { return push1(P.p[k], get(k)); });
+}
+
+// Gamma(shape a, 1), Marsaglia & Tsang; Poisson: Knuth below 10, PTRS from 10 up (part of the variate spec)
+#define KABC_GAMMA_MAX_TRIES 4096
+static __device__ __noinline__ bool gamma_sample(Stream &st, double a, double &out) {
+    double boost = 1.0;
+    if (a < 1.0) {
+        boost = xexp(xdiv(xlog(next_uniform(st)), a));
+        a = xadd(a, 1.0);
+    }
+    double d = xsub(a, 1.0 / 3.0);
+    double c = xdiv(1.0, xsqrt(xmul(9.0, d)));
+    for (int t = 0; t < KABC_GAMMA_MAX_TRIES; ++t) {
+        double z = next_normal(st);
+        double u = next_uniform(st);
+        double v = xadd(1.0, xmul(c, z));
+        if (!(v > 0.0)) continue;
+        v = xmul(xmul(v, v), v);
+        if (xlog(u) < xadd(xsub(xadd(xmul(xmul(0.5, z), z), d), xmul(d, v)), xmul(d, xlog(v)))) {
+            out = xmul(xmul(d, v), boost);
+            return true;
+        }
+    }
+    out = dnan();
+    return false;
+}
+static __device__ __noinline__ bool poisson_sample(Stream &st, double lam, double &out) {
+    if (!(lam >= 0.0) || lam > 1e9) { out = dnan(); return false; }
+    if (lam == 0.0) { out = 0.0; return true; }
+    if (lam < 10.0) {
+        double L = xexp(-lam), p = 1.0;
+        for (int k = 0; k < KABC_GAMMA_MAX_TRIES; ++k) {
+            p = xmul(p, next_uniform(st));
+            if (!(p > L)) { out = (double)k; return true; }
+        }
+        out = dnan();
+        return false;
+    }
+    double slam = xsqrt(lam), loglam = xlog(lam);
+    double b = xadd(0.931, xmul(2.53, slam));
+    double a = xadd(-0.059, xmul(0.02483, b));
+    double invalpha = xadd(1.1239, xdiv(1.1328, xsub(b, 3.4)));
+    double vr = xsub(0.9277, xdiv(3.6224, xsub(b, 2.0)));
+    for (int t = 0; t < KABC_GAMMA_MAX_TRIES; ++t) {
+        double U = xsub(next_uniform(st), 0.5);
+        double V = next_uniform(st);
+        double us = xsub(0.5, fabs(U));
+        double k = floor(xadd(xadd(xmul(xadd(xdiv(xmul(2.0, a), us), b), U), lam), 0.43));
+        if (us >= 0.07 && V <= vr) { out = k; return true; }
+        if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        double lhs = xsub(xadd(xlog(V), xlog(invalpha)), xlog(xadd(xdiv(a, xmul(us, us)), b)));
+        if (lhs <= xsub(xsub(xmul(k, loglam), lam), xlgamma(xadd(k, 1.0)))) { out = k; return true; }
+    }
+    out = dnan();
+    return false;
+}
+static __device__ __noinline__ bool prior1_sample_ext(int kind, double p0, double p1, Stream &st, double &out) {
+    if (kind == KABC_PRIOR_BETA) {
+        double ga, gb;
+        bool ok = gamma_sample(st, p0, ga);
+        ok = gamma_sample(st, p1, gb) && ok;
+        out = xdiv(ga, xadd(ga, gb));
+        return ok;
+    }
+    if (kind == KABC_PRIOR_NEG_BINOMIAL) {
+        double g;
+        if (!gamma_sample(st, p0, g)) { out = dnan(); return false; }
+        return poisson_sample(st, xmul(g, xdiv(xsub(1.0, p1), p1)), out);
+    }
+    out = xadd(p0, (double)index_of(st.next(), (uint32_t)xadd(xsub(p1, p0), 1.0)));
+    return true;
+}
+
 #define KABC_TRUNC_MAX_TRIES (1 << 20)
 __device__ __forceinline__ bool prior1_sample(const DPrior &p, Stream &st, double &out) {
+    if (p.kind >= KABC_PRIOR_BETA) return prior1_sample_ext(p.kind, p.p0, p.p1, st, out);
     if (p.kind == KABC_PRIOR_UNIFORM) {
         out = xadd(p.p0, xmul(xsub(p.p1, p.p0), next_uniform(st)));
         return true;

@@ -13,6 +13,8 @@ namespace kabc {
 
 struct DModel {
     int kind, precision, n_draws, n_target;
+    uint32_t push_mask; // bit k: component k follows a discrete law and reaches the cost rounded (push_p, src/types.jl:32);
+                        // set by the smc / ais handles from their prior, 0 for the bare kabc_eval_cost entry point
     double target[KABC_MAX_TARGET];
     double param[KABC_MAX_PARAM];
 };
@@ -262,16 +264,64 @@ __device__ __forceinline__ double cost_lv(const DModel &m, const RoundKeys &rk, 
 }
 
 // ------------------------------------------------------------------ deterministic costs of the reference's tests
-__device__ __forceinline__ double cost_det(const DModel &m, double th0) {
+template <typename F>
+__device__ __forceinline__ double cost_det(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id, uint32_t epoch,
+                                           F th) {
+    const double th0 = th(0);
     if (m.param[0] == 0.0) return fabs(xsub(xadd(xmul(th0, th0), 1.0), m.target[0]));
+    if (m.param[0] == 2.0) { // test/runtests.jl:105-112: (n*n+du)*(n+randn()*0.01)
+        Stream st(rk, tag, id, epoch);
+        double noisy = xadd(th0, xmul(next_normal(st), m.param[1]));
+        return fabs(xsub(xmul(xadd(xmul(th0, th0), th(1)), noisy), m.target[0]));
+    }
     return fabs(xsub(th0, m.target[0]));
 }
 
+// ------------------------------------------------------------------ socks of Karl Broman, ref test/runtests.jl:34-44
+// Spec of the draw without replacement: forward Fisher-Yates over the sorted sock list, pick j swaps
+// position j with j + index(word_j, n - j); only the first m positions and the <= m displaced tail entries exist.
+#define KABC_SOCKS_MAX_PICKED 32
+static __device__ __noinline__ double cost_socks(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
+                                                 uint32_t epoch, double nf, double prop) {
+    const int n_picked = (int)m.param[0];
+    if (!(nf >= 0.0) || !(nf <= 1e9) || nf != floor(nf) || !(prop >= 0.0 && prop <= 1.0)) return dinf();
+    const long long n = (long long)nf;
+    const long long n_pairs = (long long)rint(xmul(prop, floor(xdiv(nf, 2.0))));
+    const int mp = n < n_picked ? (int)n : n_picked;
+    long long head[KABC_SOCKS_MAX_PICKED], tpos[KABC_SOCKS_MAX_PICKED], tval[KABC_SOCKS_MAX_PICKED];
+    int nt = 0;
+    Stream st(rk, tag, id, epoch);
+    for (int j = 0; j < mp; ++j) head[j] = j;
+    for (int j = 0; j < mp; ++j) {
+        long long r = j + (long long)index_of(st.next(), (uint32_t)(n - j));
+        if (r < mp) { long long t = head[j]; head[j] = head[r]; head[r] = t; }
+        else {
+            int q = 0;
+            while (q < nt && tpos[q] != r) ++q;
+            if (q == nt) { tpos[nt] = r; tval[nt] = r; ++nt; }
+            long long t = head[j]; head[j] = tval[q]; tval[q] = t;
+        }
+    }
+    int lu = 0;
+    for (int j = 0; j < mp; ++j) { // labels overwrite tpos (no longer needed)
+        long long sidx = head[j];
+        long long l = sidx < 2 * n_pairs ? sidx / 2 : sidx - n_pairs;
+        bool seen = false;
+        for (int q = 0; q < lu; ++q) seen |= (tpos[q] == l);
+        if (!seen) tpos[lu++] = l;
+    }
+    const double pairs = (double)(mp - lu), odds = (double)(lu - (mp - lu));
+    return xadd(fabs(xsub(pairs, m.target[0])), fabs(xsub(odds, m.target[1])));
+}
+
 // thread-per-particle dispatch.  KIND and PREC are compile-time so each kernel holds one simulator.
+__device__ __forceinline__ double pushk(const DModel &m, int k, double x) { return (m.push_mask >> k) & 1u ? rint(x) : x; }
+
 template <int KIND, int PREC, typename F>
 __device__ __forceinline__ double cost_thread(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
-                                              uint32_t epoch, F th, long long &events) {
+                                              uint32_t epoch, F raw, long long &events) {
     events = 0;
+    auto th = [&](int k) { return pushk(m, k, raw(k)); }; // cost(push_p(prior, theta)), ref src/smc.jl:123,176
     if (KIND == KABC_MODEL_NORMAL_MEANSTD)
         return PREC == KABC_F64 ? cost_normal_f64(m, rk, tag, id, epoch, th(0), th(1))
                                 : cost_normal_f32(m, rk, tag, id, epoch, th(0), th(1));
@@ -280,7 +330,8 @@ __device__ __forceinline__ double cost_thread(const DModel &m, const RoundKeys &
                                 : cost_ma2_f32(m, rk, tag, id, epoch, th(0), th(1));
     if (KIND == KABC_MODEL_LV_SSA)
         return cost_lv<PREC != KABC_F64>(m, rk, tag, id, epoch, th(0), th(1), th(2), events);
-    if (KIND == KABC_MODEL_DETERMINISTIC) return cost_det(m, th(0));
+    if (KIND == KABC_MODEL_DETERMINISTIC) return cost_det(m, rk, tag, id, epoch, th);
+    if (KIND == KABC_MODEL_SOCKS) return cost_socks(m, rk, tag, id, epoch, th(0), th(1));
     return dnan();
 }
 

@@ -138,7 +138,7 @@ k_smc_init(SmcBufs B, SmcParams P, DPriors pri, DModel m, RoundKeys rk, long lon
         double *thv = B.th[0];
         double X = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, [&](int k) { return thv[(long long)k * N + i]; }, ev);
         B.X[0][i] = X;
-        B.lpi[0][i] = prior_logpdf(pri, [&](int k) { return thv[(long long)k * N + i]; });
+        B.lpi[0][i] = prior_logpdf_pushed(pri, [&](int k) { return thv[(long long)k * N + i]; });
         B.alive[i] = 1;
         key = dkey(X);
         ev_u = (unsigned long long)ev;
@@ -164,7 +164,7 @@ __global__ void k_smc_init_prior(SmcBufs B, SmcParams P, DPriors pri, RoundKeys 
     }
     if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
     double *thv = B.th[0];
-    B.lpi[0][i] = prior_logpdf(pri, [&](int k) { return thv[(long long)k * N + i]; });
+    B.lpi[0][i] = prior_logpdf_pushed(pri, [&](int k) { return thv[(long long)k * N + i]; });
     B.alive[i] = 1;
 }
 
@@ -175,7 +175,8 @@ k_smc_init_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, long long lo, long
     const long long N = P.N;
     for (long long i = lo + blockIdx.x; i < hi; i += gridDim.x) {
         const double *th = B.th[0];
-        double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, th[i], th[N + i], th[2 * N + i], th[3 * N + i], gk_smem);
+        double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, pushk(m, 0, th[i]), pushk(m, 1, th[N + i]),
+                                    pushk(m, 2, th[2 * N + i]), pushk(m, 3, th[3 * N + i]), gk_smem);
         if (threadIdx.x == 0) {
             B.X[0][i] = c;
             atomicMin(&B.ctrl->sw_minkey, dkey(c));
@@ -671,7 +672,7 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
             }
             const uint32_t wu = st.next();
             const double *thp = B.thp;
-            lpip = prior_logpdf(pri, [&](int k) { return thp[(long long)k * N + i]; });
+            lpip = prior_logpdf_pushed(pri, [&](int k) { return thp[(long long)k * N + i]; });
             if (lpip < 0.0 && !dfinite(lpip)) dec = 1;
             else {
                 // ref :174-175  lM = min(lpip - lpi + logcorr, 0); proceed iff log(rand) < lM.
@@ -893,7 +894,7 @@ __global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P,
                 const unsigned int w = base + __popc(need & ((1u << lane) - 1u));
                 if (w < nwork) {
                     i = B.work[w];
-                    sim.init(m, ST_COST, (uint32_t)i, epoch, B.thp[i], B.thp[N + i], B.thp[2 * N + i]);
+                    sim.init(m, ST_COST, (uint32_t)i, epoch, pushk(m, 0, B.thp[i]), pushk(m, 1, B.thp[N + i]), pushk(m, 2, B.thp[2 * N + i]));
                     have = true;
                 } else {
                     exhausted = true;
@@ -939,7 +940,8 @@ __global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcPa
     for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const long long i = B.work[w];
         const double *thp = B.thp;
-        double Xp = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, thp[i], thp[N + i], thp[2 * N + i], thp[3 * N + i], gk_smem);
+        double Xp = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, pushk(m, 0, thp[i]), pushk(m, 1, thp[N + i]),
+                                     pushk(m, 2, thp[2 * N + i]), pushk(m, 3, thp[3 * N + i]), gk_smem);
         if (threadIdx.x == 0) {
             unsigned int acc = 0;
             smc_accept<4>(B, P, c, i, Xp, acc);
@@ -1140,6 +1142,7 @@ static int smc_enqueue_init(kabc_smc *s) {
     case KABC_MODEL_MA2_AUTOCOV: smc_launch_init_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
     case KABC_MODEL_LV_SSA: smc_launch_init_t<KABC_MODEL_LV_SSA>(s); break;
     case KABC_MODEL_DETERMINISTIC: smc_launch_init_t<KABC_MODEL_DETERMINISTIC>(s); break;
+    case KABC_MODEL_SOCKS: smc_launch_init_t<KABC_MODEL_SOCKS>(s); break;
     case KABC_MODEL_GK_OCTILE: {
         const long long n = s->hi - s->lo;
         k_smc_init_prior<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
@@ -1200,6 +1203,7 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
         break;
     }
     case KABC_MODEL_DETERMINISTIC: smc_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s, mode); break;
+    case KABC_MODEL_SOCKS: smc_launch_sim_t<KABC_MODEL_SOCKS>(s, mode); break;
     case KABC_MODEL_GK_OCTILE: {
         size_t smem;
         int grid = smc_gk_grid(s, smem);
@@ -1292,6 +1296,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     if (int rc = ingest_priors(prior, d, pri)) return rc;
     if (int rc = smc_check_cfg(cfg, d)) return rc;
     if (int rc = ingest_model(model, d, m)) return rc;
+    m.push_mask = push_mask_of(pri);
     const long long N = cfg->nparticles;
     if (ctx->world > 1 && N % ctx->world) return set_error(KABC_ERR_INVALID_ARG, "nparticles must be a multiple of the number of ranks");
     KABC_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1580,6 +1585,12 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
     }
     const double t3 = now();
     if (!rc) rc = kabc_smc_get_state(s, out_theta, out_cost, nullptr, out_alive);
+    if (!rc && out_theta) { // ref src/smc.jl:200: the returned particles are push_p(prior, .)
+        const long long N = s->P.N;
+        for (int k = 0; k < d; ++k)
+            if (prior_is_discrete(s->pri.p[k]))
+                for (long long i = 0; i < N; ++i) out_theta[(long long)k * N + i] = nearbyint(out_theta[(long long)k * N + i]);
+    }
     if (!rc) {
         if (out_eps) *out_eps = s->h_ctrl->eps;
         if (out_iterations) *out_iterations = s->h_ctrl->iteration;

@@ -199,6 +199,87 @@ static double next_normal(stream_t *s) { /* consumes 2 words, keeps the cosine b
 }
 static double next_exp(stream_t *s) { return -kor_log(next_uniform(s)); }
 
+/* log Gamma(x), x > 0: argument shifted to >= 10 by the recurrence, then the Stirling series (Abramowitz & Stegun 6.1.41)
+ * through x^-13.  Part of the variate spec: fixed operation order, same bits on CPU and GPU. */
+double kor_lgamma(double x) {
+    if (x != x) return x;
+    if (x < 0.0) return NAN;
+    if (x == 0.0 || x == INFINITY) return INFINITY;
+    double prod = 1.0;
+    while (x < 10.0) { prod = prod * x; x = x + 1.0; }
+    double xi = 1.0 / x;
+    double x2 = xi * xi;
+    double p = 1.0 / 156.0;
+    p = fma(p, x2, -691.0 / 360360.0);
+    p = fma(p, x2, 1.0 / 1188.0);
+    p = fma(p, x2, -1.0 / 1680.0);
+    p = fma(p, x2, 1.0 / 1260.0);
+    p = fma(p, x2, -1.0 / 360.0);
+    p = fma(p, x2, 1.0 / 12.0);
+    double r = (((x - 0.5) * kor_log(x) - x) + 0.91893853320467274178) + p * xi;
+    return r - kor_log(prod);
+}
+
+/* Gamma(shape a, scale 1), Marsaglia & Tsang (2000); a < 1 through Gamma(a+1) * U^(1/a).  Every try consumes one
+ * normal (2 words) and one uniform (1 word). */
+#define GAMMA_MAX_TRIES 4096
+static int gamma_sample(stream_t *s, double a, double *out) {
+    double boost = 1.0;
+    if (a < 1.0) {
+        boost = kor_exp(kor_log(next_uniform(s)) / a);
+        a = a + 1.0;
+    }
+    double d = a - 1.0 / 3.0;
+    double c = 1.0 / sqrt(9.0 * d);
+    for (int t = 0; t < GAMMA_MAX_TRIES; ++t) {
+        double z = next_normal(s);
+        double u = next_uniform(s);
+        double v = 1.0 + c * z;
+        if (!(v > 0.0)) continue;
+        v = (v * v) * v;
+        if (kor_log(u) < (((0.5 * z) * z + d) - d * v) + d * kor_log(v)) {
+            *out = (d * v) * boost;
+            return 0;
+        }
+    }
+    *out = NAN;
+    return 1;
+}
+/* Poisson(lam): product-of-uniforms (Knuth) below 10, PTRS transformed rejection (Hoermann 1993) from 10 up. */
+#define POISSON_MAX_TRIES 4096
+static int poisson_sample(stream_t *s, double lam, double *out) {
+    if (!(lam >= 0.0) || lam > 1e9) { *out = NAN; return 1; }
+    if (lam == 0.0) { *out = 0.0; return 0; }
+    if (lam < 10.0) {
+        double L = kor_exp(-lam), p = 1.0;
+        for (int k = 0; k < POISSON_MAX_TRIES; ++k) {
+            p = p * next_uniform(s);
+            if (!(p > L)) { *out = (double)k; return 0; }
+        }
+        *out = NAN;
+        return 1;
+    }
+    double slam = sqrt(lam), loglam = kor_log(lam);
+    double b = 0.931 + 2.53 * slam;
+    double a = -0.059 + 0.02483 * b;
+    double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+    double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (int t = 0; t < POISSON_MAX_TRIES; ++t) {
+        double U = next_uniform(s) - 0.5;
+        double V = next_uniform(s);
+        double us = 0.5 - fabs(U);
+        double k = floor(((2.0 * a) / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) { *out = k; return 0; }
+        if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        if (kor_log(V) + kor_log(invalpha) - kor_log(a / (us * us) + b) <= (k * loglam - lam) - kor_lgamma(k + 1.0)) {
+            *out = k;
+            return 0;
+        }
+    }
+    *out = NAN;
+    return 1;
+}
+
 /* ------------------------------------------------------------------ */
 /* priors -- ref: src/priors.jl:30-43 + Distributions.jl closed forms   */
 /* ------------------------------------------------------------------ */
@@ -219,8 +300,30 @@ static double prior1_logpdf(const kor_prior_t *p, double x) {
         double logtp = log(std_normal_cdf((p->hi - p->p0) / p->p1) - std_normal_cdf((p->lo - p->p0) / p->p1));
         return (-(z * z + LOG2PI) / 2.0 - log(p->p1)) - logtp;
     }
+    case KOR_PRIOR_BETA: { /* Distributions: xlogy(a-1,x) + xlog1py(b-1,-x) - logbeta(a,b) on [0,1] */
+        if (!(x >= 0.0 && x <= 1.0)) return -INFINITY;
+        double am = p->p0 - 1.0, bm = p->p1 - 1.0;
+        double t1 = am == 0.0 ? 0.0 : am * kor_log(x);
+        double t2 = bm == 0.0 ? 0.0 : bm * kor_log(1.0 - x);
+        return (t1 + t2) - ((lgamma(p->p0) + lgamma(p->p1)) - lgamma(p->p0 + p->p1));
+    }
+    case KOR_PRIOR_NEG_BINOMIAL: { /* pmf(k) = Gamma(k+r)/(k! Gamma(r)) p^r (1-p)^k, k = 0,1,2,... */
+        if (!(x >= 0.0) || x != floor(x) || x == INFINITY) return -INFINITY;
+        double r = p->p0;
+        return ((kor_lgamma(x + r) - kor_lgamma(x + 1.0)) - lgamma(r)) + (r * log(p->p1) + x * log1p(-p->p1));
+    }
+    case KOR_PRIOR_DISCRETE_UNIFORM:
+        return (x >= p->p0 && x <= p->p1 && x == floor(x)) ? -log((p->p1 - p->p0) + 1.0) : -INFINITY;
     }
     return NAN;
+}
+/* ref: src/types.jl:28-32 -- push_p: components of a discrete law are rounded (round(Int, .), ties to even) before the prior
+ * density and the cost see them; the stored particle keeps its real value */
+static int prior_is_discrete(const kor_prior_t *p) {
+    return p->kind == KOR_PRIOR_NEG_BINOMIAL || p->kind == KOR_PRIOR_DISCRETE_UNIFORM;
+}
+void kor_push_p(const kor_prior_t *prior, int d, const double *x, double *out) {
+    for (int k = 0; k < d; ++k) out[k] = prior_is_discrete(&prior[k]) ? nearbyint(x[k]) : x[k];
 }
 /* ref: src/priors.jl:30-36 -- left-to-right sum starting from component 1 */
 double kor_prior_logpdf(const kor_prior_t *prior, int d, const double *x) {
@@ -240,6 +343,21 @@ static int prior1_sample(const kor_prior_t *p, stream_t *s, double *out) {
         }
         *out = NAN;
         return 1;
+    case KOR_PRIOR_BETA: { /* X = Ga/(Ga+Gb) */
+        double ga, gb;
+        int rc = gamma_sample(s, p->p0, &ga);
+        rc |= gamma_sample(s, p->p1, &gb);
+        *out = ga / (ga + gb);
+        return rc;
+    }
+    case KOR_PRIOR_NEG_BINOMIAL: { /* Gamma(r, (1-p)/p) mixture of Poissons */
+        double g;
+        if (gamma_sample(s, p->p0, &g)) { *out = NAN; return 1; }
+        return poisson_sample(s, g * ((1.0 - p->p1) / p->p1), out);
+    }
+    case KOR_PRIOR_DISCRETE_UNIFORM:
+        *out = p->p0 + (double)kor_index(next_u32(s), (uint32_t)((p->p1 - p->p0) + 1.0));
+        return 0;
     }
     return 1;
 }
@@ -435,9 +553,50 @@ int kor_lv_trajectory(const kor_model_t *m, uint64_t seed, const double *th, uin
 /* deterministic costs used by the reference's own tests:
  * param[0]=0: |th0^2 + 1 - 1.5|  (test/runtests.jl:77-86, sim(mu)=mu*mu+1)
  * param[0]=1: |th0 - 1.5|        (test/runtests.jl:177-182) */
-static double cost_det(const kor_model_t *m, const double *th) {
+static double cost_det(const kor_model_t *m, stream_t *s, const double *th) {
     if (m->param[0] == 0.0) return fabs((th[0] * th[0] + 1.0) - m->target[0]);
+    if (m->param[0] == 2.0) /* test/runtests.jl:105-112: sim((n,du)) = (n*n+du)*(n+randn()*0.01); |sim - 5.5| */
+        return fabs((th[0] * th[0] + th[1]) * (th[0] + next_normal(s) * m->param[1]) - m->target[0]);
     return fabs(th[0] - m->target[0]);
+}
+
+/* "Tiny Data, ABC and the Socks of Karl Broman", ref test/runtests.jl:34-44: th = (n_socks, prop_pairs);
+ * n_pairs = round(prop * floor(n/2)), n_odd = n - 2 n_pairs; pick min(n, n_picked) socks without replacement from the sorted
+ * list [1,1,2,2,...,n_pairs,n_pairs, n_pairs+1, ..., n_pairs+n_odd]; pairs = picked - unique, odds = unique - pairs;
+ * cost = |pairs - t0| + |odds - t1|.  Spec of the draw: forward Fisher-Yates, pick j swaps position j with
+ * j + index(word_j, n - j); only the first m positions and the <= m displaced tail entries are materialised. */
+#define SOCKS_MAX_PICKED 32
+static double cost_socks(const kor_model_t *m, stream_t *s, const double *th) {
+    double nf = th[0], prop = th[1];
+    int n_picked = (int)m->param[0];
+    if (!(nf >= 0.0) || !(nf <= 1e9) || nf != floor(nf) || !(prop >= 0.0 && prop <= 1.0)) return INFINITY;
+    int64_t n = (int64_t)nf;
+    int64_t n_pairs = (int64_t)nearbyint(prop * floor(nf / 2.0));
+    int mp = n < n_picked ? (int)n : n_picked;
+    int64_t head[SOCKS_MAX_PICKED], tpos[SOCKS_MAX_PICKED], tval[SOCKS_MAX_PICKED];
+    int nt = 0;
+    for (int j = 0; j < mp; ++j) head[j] = j;
+    for (int j = 0; j < mp; ++j) {
+        int64_t r = j + (int64_t)kor_index(next_u32(s), (uint32_t)(n - j));
+        if (r < mp) { int64_t t = head[j]; head[j] = head[r]; head[r] = t; }
+        else {
+            int q = 0;
+            while (q < nt && tpos[q] != r) ++q;
+            if (q == nt) { tpos[nt] = r; tval[nt] = r; ++nt; }
+            int64_t t = head[j]; head[j] = tval[q]; tval[q] = t;
+        }
+    }
+    int lu = 0;
+    int64_t lab[SOCKS_MAX_PICKED];
+    for (int j = 0; j < mp; ++j) {
+        int64_t sidx = head[j];
+        int64_t l = sidx < 2 * n_pairs ? sidx / 2 : sidx - n_pairs;
+        int seen = 0;
+        for (int q = 0; q < lu; ++q) seen |= (lab[q] == l);
+        if (!seen) lab[lu++] = l;
+    }
+    double pairs = (double)(mp - lu), odds = (double)(lu - (mp - lu));
+    return fabs(pairs - m->target[0]) + fabs(odds - m->target[1]);
 }
 
 static double cost_dispatch(const kor_model_t *m, uint64_t seed, uint32_t tag, int d, const double *th,
@@ -451,7 +610,8 @@ static double cost_dispatch(const kor_model_t *m, uint64_t seed, uint32_t tag, i
     case KOR_MODEL_MA2_AUTOCOV: return cost_ma2(m, &s, th);
     case KOR_MODEL_GK_OCTILE: return cost_gk(m, &s, th);
     case KOR_MODEL_LV_SSA: return cost_lv(m, &s, th);
-    case KOR_MODEL_DETERMINISTIC: return cost_det(m, th);
+    case KOR_MODEL_DETERMINISTIC: return cost_det(m, &s, th);
+    case KOR_MODEL_SOCKS: return cost_socks(m, &s, th);
     }
     return NAN;
 }
@@ -580,6 +740,7 @@ int kor_smc_init(kor_smc_t *s) {
         double th[16];
         bad |= kor_prior_sample(s->seed, s->prior, d, (uint32_t)i, 0, th);
         for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = th[k];
+        kor_push_p(s->prior, d, th, th); /* ref :122-125 cost(push_p(prior, .)), logpdf(prior, push_p(prior, .)) */
         s->X[i] = cost_dispatch(&s->model, s->seed, ST_COST_INIT, d, th, (uint32_t)i, 0);
         events += g_last_events;
         s->lpi[i] = kor_prior_logpdf(s->prior, d, th);
@@ -634,6 +795,7 @@ static void smc_sweep(kor_smc_t *s, uint32_t e, int64_t lo, int64_t hi, int64_t 
         if (!s->alive[i]) continue;
         double thp[16];
         for (int k = 0; k < d; ++k) thp[k] = s->thp[(int64_t)k * N + i];
+        kor_push_p(s->prior, d, thp, thp); /* ref :172,176 */
         double lpip = kor_prior_logpdf(s->prior, d, thp);
         s->tlpip[i] = lpip;
         if (lpip < 0 && !isfinite(lpip)) { s->tdec[i] = 1; continue; }
@@ -849,8 +1011,10 @@ void kor_ais_destroy(kor_ais_t *s) {
 /* ref: src/types.jl:51-58 -- (logprior, loglikelihood) of the kernelized posterior (cfg.posterior == 0);
  * ref: src/types.jl:84-91 -- (logprior, cost) of the hard-threshold ApproxPosterior (cfg.posterior == 1): the second
  * slot then holds the cost itself (-logprior when the prior is not finite). */
-static void ais_loglike(kor_ais_t *s, const double *x, uint32_t tag, uint32_t id, uint32_t epoch, double *lp,
+static void ais_loglike(kor_ais_t *s, const double *xraw, uint32_t tag, uint32_t id, uint32_t epoch, double *lp,
                         double *ll, int *evals) {
+    double x[16];
+    kor_push_p(s->prior, s->d, xraw, x); /* ref src/KissABC.jl:51,56: loglike(model, push_p(model, particle)) */
     double p = kor_prior_logpdf(s->prior, s->d, x);
     double l = s->cfg.posterior == 1 ? -p : p;
     if (isfinite(p)) {
@@ -1033,7 +1197,10 @@ int kor_ais_run_sequential(kor_ais_t *s, double *out) {
             ++step;
         }
         if (target > 0) w = (target - 1) % N;
-        for (int k = 0; k < d; ++k) out[(int64_t)k * Ns + m] = s->th[(int64_t)k * N + w];
+        for (int k = 0; k < d; ++k) { /* ref src/KissABC.jl:78 records push_p(model, sample[i]) */
+            double v = s->th[(int64_t)k * N + w];
+            out[(int64_t)k * Ns + m] = prior_is_discrete(&s->prior[k]) ? nearbyint(v) : v;
+        }
     }
     return 0;
 }
@@ -1054,7 +1221,10 @@ int kor_ais_run_parallel(kor_ais_t *s, double *out) {
                 if (kor_ais_sweep(s)) return 1;
             ++rounds;
         }
-        for (int k = 0; k < d; ++k) out[(int64_t)k * Ns + m] = s->th[(int64_t)k * N + w];
+        for (int k = 0; k < d; ++k) { /* ref src/KissABC.jl:78 records push_p(model, sample[i]) */
+            double v = s->th[(int64_t)k * N + w];
+            out[(int64_t)k * Ns + m] = prior_is_discrete(&s->prior[k]) ? nearbyint(v) : v;
+        }
     }
     return 0;
 }

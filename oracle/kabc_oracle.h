@@ -30,7 +30,8 @@ extern "C" {
 #endif
 
 /* ---- descriptors (same field order as include/kissabc_cuda.h PODs) ---- */
-enum { KOR_PRIOR_UNIFORM = 0, KOR_PRIOR_NORMAL = 1, KOR_PRIOR_TRUNC_NORMAL = 2 };
+enum { KOR_PRIOR_UNIFORM = 0, KOR_PRIOR_NORMAL = 1, KOR_PRIOR_TRUNC_NORMAL = 2,
+       KOR_PRIOR_BETA = 3, KOR_PRIOR_NEG_BINOMIAL = 4, KOR_PRIOR_DISCRETE_UNIFORM = 5 };
 typedef struct {
     int32_t kind;
     int32_t _pad;
@@ -39,7 +40,7 @@ typedef struct {
 } kor_prior_t;
 
 enum { KOR_MODEL_NORMAL_MEANSTD = 0, KOR_MODEL_MA2_AUTOCOV = 1, KOR_MODEL_GK_OCTILE = 2,
-       KOR_MODEL_LV_SSA = 3, KOR_MODEL_DETERMINISTIC = 4 };
+       KOR_MODEL_LV_SSA = 3, KOR_MODEL_DETERMINISTIC = 4, KOR_MODEL_SOCKS = 5 };
 #define KOR_MAX_TARGET 32
 #define KOR_MAX_PARAM 8
 typedef struct {
@@ -91,6 +92,7 @@ typedef struct {
 /* ---- variate spec primitives ---- */
 void kor_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double kor_log(double x);
+double kor_lgamma(double x); /* x > 0 */
 double kor_exp(double x);
 void kor_sincos2pi(double u, double *s, double *c);
 double kor_u01(uint32_t w);
@@ -102,6 +104,8 @@ uint32_t kor_stream_word(uint64_t seed, uint32_t stream, uint32_t id, uint32_t e
 /* ---- priors: src/priors.jl:30-43 ---- */
 double kor_prior_logpdf(const kor_prior_t *prior, int d, const double *x);
 int kor_prior_sample(uint64_t seed, const kor_prior_t *prior, int d, uint32_t id, uint32_t epoch, double *x);
+/* ref src/types.jl:28-32: discrete components rounded (ties to even), continuous ones untouched; out may alias x */
+void kor_push_p(const kor_prior_t *prior, int d, const double *x, double *out);
 
 /* ---- cost: simulator + distance ---- */
 double kor_cost(const kor_model_t *model, uint64_t seed, int d, const double *theta, uint32_t id, uint32_t epoch);

@@ -48,8 +48,8 @@ class SmcLog(C.Structure):
                 ("sweeps", C.c_int64)]
 
 
-UNIFORM, NORMAL, TRUNC_NORMAL = 0, 1, 2
-NORMAL_MEANSTD, MA2_AUTOCOV, GK_OCTILE, LV_SSA, DETERMINISTIC = 0, 1, 2, 3, 4
+UNIFORM, NORMAL, TRUNC_NORMAL, BETA, NEG_BINOMIAL, DISCRETE_UNIFORM = 0, 1, 2, 3, 4, 5
+NORMAL_MEANSTD, MA2_AUTOCOV, GK_OCTILE, LV_SSA, DETERMINISTIC, SOCKS = 0, 1, 2, 3, 4, 5
 ST_PRIOR, ST_PROPOSE, ST_COST, ST_ACCEPT, ST_COST_INIT = 1, 2, 3, 4, 5
 
 
@@ -90,7 +90,7 @@ def lib():
     vp = C.c_void_p
     L.kor_last_error.restype = C.c_char_p
     L.kor_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
-    for f in (L.kor_log, L.kor_exp):
+    for f in (L.kor_log, L.kor_exp, L.kor_lgamma):
         f.argtypes = [C.c_double]
         f.restype = C.c_double
     L.kor_sincos2pi.argtypes = [C.c_double, dp, dp]
@@ -104,6 +104,8 @@ def lib():
     L.kor_prior_logpdf.argtypes = [C.POINTER(Prior), C.c_int, dp]
     L.kor_prior_logpdf.restype = C.c_double
     L.kor_prior_sample.argtypes = [C.c_uint64, C.POINTER(Prior), C.c_int, C.c_uint32, C.c_uint32, dp]
+    L.kor_push_p.argtypes = [C.POINTER(Prior), C.c_int, dp, dp]
+    L.kor_push_p.restype = None
     L.kor_cost.argtypes = [C.POINTER(Model), C.c_uint64, C.c_int, dp, C.c_uint32, C.c_uint32]
     L.kor_cost.restype = C.c_double
     L.kor_last_events.restype = C.c_int64
@@ -158,7 +160,8 @@ def _bp(a):
 
 
 def make_priors(specs):
-    """specs: list of ("uniform",a,b) | ("normal",mu,sigma) | ("truncnormal",mu,sigma,lo,hi)."""
+    """specs: list of ("uniform",a,b) | ("normal",mu,sigma) | ("truncnormal",mu,sigma,lo,hi) | ("beta",a,b) |
+    ("negbin",r,p) | ("duniform",a,b)."""
     arr = (Prior * len(specs))()
     for k, s in enumerate(specs):
         kind = s[0]
@@ -168,6 +171,12 @@ def make_priors(specs):
             arr[k] = Prior(NORMAL, 0, float(s[1]), float(s[2]), -np.inf, np.inf)
         elif kind == "truncnormal":
             arr[k] = Prior(TRUNC_NORMAL, 0, float(s[1]), float(s[2]), float(s[3]), float(s[4]))
+        elif kind == "beta":
+            arr[k] = Prior(BETA, 0, float(s[1]), float(s[2]), 0.0, 1.0)
+        elif kind == "negbin":
+            arr[k] = Prior(NEG_BINOMIAL, 0, float(s[1]), float(s[2]), 0.0, np.inf)
+        elif kind == "duniform":
+            arr[k] = Prior(DISCRETE_UNIFORM, 0, float(s[1]), float(s[2]), float(s[1]), float(s[2]))
         else:
             raise ValueError(kind)
     return arr

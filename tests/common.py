@@ -22,6 +22,11 @@ _c = _consts()
 LV_TARGET_X, LV_TARGET_Y, GK_TARGET, MA2_TARGET = _c["LV_TARGET_X"], _c["LV_TARGET_Y"], _c["GK_TARGET"], _c["MA2_TARGET"]
 
 
+# ref test/runtests.jl:46-50: prior_mu = 30, prior_sd = 15, prior_size = -mu^2/(mu - sd^2); NegativeBinomial(size, size/(mu+size))
+SOCKS_R = -30.0 ** 2 / (30.0 - 15.0 ** 2)
+SOCKS_P = SOCKS_R / (30.0 + SOCKS_R)
+
+
 def models(O, k):
     """name -> (oracle prior specs, product prior, oracle model factory(prec), product cost factory(prec))."""
     return {
@@ -53,6 +58,22 @@ def models(O, k):
             omodel=lambda n=0, cap=20000: O.make_model(O.LV_SSA, 0, target=LV_TARGET_X + LV_TARGET_Y,
                                                        param=(50, 100, 30, 16, cap)),
             kcost=lambda prec, n=0, cap=20000: k.LotkaVolterra(LV_TARGET_X + LV_TARGET_Y, 50, 100, 30, cap, precision=prec),
+        ),
+        # ref test/runtests.jl:34-56 (socks of Karl Broman: NegativeBinomial x Beta prior, discrete first component)
+        "socks": dict(
+            d=2,
+            ospec=[("negbin", SOCKS_R, SOCKS_P), ("beta", 15, 2)],
+            kprior=lambda: k.Factored(k.NegativeBinomial(SOCKS_R, SOCKS_P), k.Beta(15, 2)),
+            omodel=lambda n=0: O.make_model(O.SOCKS, 0, target=(0, 11), param=(11,)),
+            kcost=lambda prec, n=0: k.Socks((0, 11), 11),
+        ),
+        # ref test/runtests.jl:105-112 (Normal x DiscreteUniform prior, noisy product simulator)
+        "noisyprod": dict(
+            d=2,
+            ospec=[("normal", 1, 0.5), ("duniform", 1, 10)],
+            kprior=lambda: k.Factored(k.Normal(1, 0.5), k.DiscreteUniform(1, 10)),
+            omodel=lambda n=0: O.make_model(O.DETERMINISTIC, 0, target=(5.5,), param=(2.0, 0.01)),
+            kcost=lambda prec, n=0: k.NoisyProduct(5.5, 0.01),
         ),
     }
 

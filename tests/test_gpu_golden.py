@@ -23,7 +23,8 @@ def golden():
 
 def test_costs_match_golden(kabc, ctx, golden):
     W = kabc.workloads
-    mk = {"normal": W.normal, "ma2": W.ma2, "gk": W.gk, "lv": W.lv}
+    mk = {"normal": W.normal, "ma2": W.ma2, "gk": W.gk, "lv": W.lv, "socks": lambda prec, n: (None, kabc.Socks((0, 11), 11)),
+          "noisyprod": lambda prec, n: (None, kabc.NoisyProduct(5.5, 0.01))}
     for key, v in golden["costs"].items():
         name, nd = key.rsplit("_", 1)
         _, cost = mk[name]("f64", int(nd))
@@ -56,6 +57,39 @@ def test_ais_run_matches_golden(kabc, ctx, golden):
     assert [float(x).hex() for x in out.ravel()] == golden["ais_normal_12"]["samples"]
     assert cnt["cost_evals"] == golden["ais_normal_12"]["counters"]["cost_evals"]
     assert cnt["accepted"] == golden["ais_normal_12"]["counters"]["accepted"]
+
+
+def test_added_laws_and_socks_match_golden(kabc, ctx, golden):
+    """Beta / NegativeBinomial / DiscreteUniform draws and densities, and the reference's socks test at reduced size."""
+    g = golden["priors_ext"]
+    mk = {"beta": kabc.Beta, "negbin": kabc.NegativeBinomial, "duniform": kabc.DiscreteUniform}
+    laws = [mk[s_[0]](*s_[1:]) for s_ in g["spec"]]
+    n = g["shape"][1]
+    th = ctx.prior_sample(kabc.Factored(*laws), n, first_id=0, epoch=7)
+    assert [float(x).hex() for x in th.ravel()] == g["draws"]
+    lps = []
+    for k, law in enumerate(laws):
+        xs = np.array(list(th[k]) + [0.0, 1.0, 2.5, -1.0, 7.0])
+        lps += list(ctx.prior_logpdf(law, xs[None, :]))
+    assert [float(x).hex() for x in lps] == g["logpdf"]
+    R = -30.0 ** 2 / (30.0 - 15.0 ** 2)
+    pri = kabc.Factored(kabc.NegativeBinomial(R, R / (30.0 + R)), kabc.Beta(15, 2))
+    s = kabc.SmcSession(ctx, pri, kabc.Socks((0, 11), 11), kabc.smc_config(nparticles=500, alpha=0.99, r_epstol=0, epstol=0.01))
+    s.init()
+    while not s.iterate():
+        pass
+    gs = golden["smc_socks_500"]
+    log = s.log()
+    assert [float(r["eps"]).hex() for r in log] == gs["eps"]
+    assert [r["n_alive"] for r in log] == gs["n_alive"] and [r["accepted"] for r in log] == gs["accepted"]
+    th, X, _, _ = s.state()
+    assert float(th.sum()).hex() == gs["theta_sum"] and float(X.sum()).hex() == gs["X_sum"]
+    assert s.scalars()["cost_evals"] == gs["cost_evals"]
+    res, cnt = kabc.sample(kabc.ApproxPosterior(pri, kabc.Socks((0, 11), 11), 0.1), kabc.AIS(50), 200, ntransitions=10, ctx=ctx,
+                           return_counters=True)
+    out = np.vstack([p.particles for p in res])
+    assert [float(x).hex() for x in out.ravel()] == golden["ais_socks_50"]["samples"]
+    assert cnt["cost_evals"] == golden["ais_socks_50"]["counters"]["cost_evals"]
 
 
 def test_select_handles_ties_and_infinities(kabc, ctx):

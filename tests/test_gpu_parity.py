@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import SEED, models, prior_draws
+from common import SEED, SOCKS_P, SOCKS_R, models, prior_draws
 
 pytestmark = pytest.mark.gpu
 
@@ -78,9 +78,45 @@ def test_prior_sample_bit_exact(oracle, kabc, ctx):
     assert (dev[1] >= 0).all()
 
 
+def test_added_laws_bit_exact(oracle, kabc, ctx):
+    """Beta / NegativeBinomial / DiscreteUniform (ref test/runtests.jl:50-51,106): samplers (Marsaglia-Tsang gamma, PTRS /
+    Knuth Poisson) and log-densities (spec'd log-gamma) are part of the variate spec -> same bits as the oracle."""
+    O = oracle
+    spec = [("beta", 15, 2), ("beta", 0.5, 0.7), ("negbin", SOCKS_R, SOCKS_P), ("negbin", 0.6, 0.9), ("duniform", 1, 10),
+            ("duniform", -3, 3)]
+    kpri = kabc.Factored(kabc.Beta(15, 2), kabc.Beta(0.5, 0.7), kabc.NegativeBinomial(SOCKS_R, SOCKS_P),
+                         kabc.NegativeBinomial(0.6, 0.9), kabc.DiscreteUniform(1, 10), kabc.DiscreteUniform(-3, 3))
+    n, d = 4096, len(spec)
+    dev = ctx.prior_sample(kpri, n, first_id=3, epoch=2)
+    pri = O.make_priors(spec)
+    ref = np.empty((d, n))
+    buf = (C.c_double * d)()
+    for i in range(n):
+        assert O.lib().kor_prior_sample(SEED, pri, d, 3 + i, 2, buf) == 0
+        ref[:, i] = list(buf)
+    assert_bits_equal(dev, ref, "added laws: samples")
+    assert (dev[2] == np.rint(dev[2])).all() and dev[2].max() > 60 and (dev[4] >= 1).all() and (dev[4] <= 10).all()
+    th = dev.copy()
+    rng = np.random.default_rng(1)
+    th[:, ::7] += rng.normal(0, 0.6, (d, len(th[0, ::7])))      # off-support and non-integer arguments
+    th[0, :4] = [0.0, 1.0, -0.1, 1.1]
+    ldev = ctx.prior_logpdf(kpri, th)
+    lref = np.array([O.lib().kor_prior_logpdf(pri, d, np.ascontiguousarray(th[:, i]).ctypes.data_as(C.POINTER(C.c_double)))
+                     for i in range(n)])
+    assert_bits_equal(ldev, lref, "added laws: logpdf")
+    assert np.isneginf(ldev).sum() > 100 and np.isfinite(ldev).sum() > n // 2
+    with pytest.raises(kabc.KissABCError):
+        ctx.prior_sample(kabc.Beta(0, 2), 4)
+    with pytest.raises(kabc.KissABCError):
+        ctx.prior_sample(kabc.NegativeBinomial(2, 1.5), 4)
+    with pytest.raises(kabc.KissABCError):
+        ctx.prior_sample(kabc.DiscreteUniform(1.5, 4), 4)
+
+
 # ------------------------------------------------------------------ simulators
 @pytest.mark.parametrize("name,n,ndraws", [("normal", 3000, 1000), ("normal", 257, 37), ("ma2", 4000, 100),
-                                            ("ma2", 300, 7), ("lv", 600, 0), ("gk", 96, 10000), ("gk", 64, 1001)])
+                                            ("ma2", 300, 7), ("lv", 600, 0), ("gk", 96, 10000), ("gk", 64, 1001),
+                                            ("socks", 3000, 0), ("noisyprod", 1000, 0)])
 def test_cost_f64_bit_exact(oracle, kabc, ctx, name, n, ndraws):
     O = oracle
     M = models(O, kabc)[name]
@@ -165,6 +201,8 @@ def _compare_smc_state(osmc, dsmc, what):
     ("normal", 999, dict(alpha=0.5, mcmc_retrys=3, mcmc_tol=0.3)),   # retry sweeps, odd N
     ("ma2", 4096, dict(alpha=0.9)),                                  # +Inf costs culled by the quantile cut
     ("lv", 512, dict(alpha=0.8)),
+    ("socks", 800, dict(alpha=0.99, r_epstol=0, epstol=0.01)),       # discrete prior (push_p), integer costs: ties everywhere
+    ("noisyprod", 600, dict(alpha=0.9)),                             # Normal x DiscreteUniform prior
 ])
 def test_smc_f64_whole_run_bit_exact(oracle, kabc, ctx, name, N, cfg):
     """Every iteration of a whole smc run: state, epsilon, flags, counters identical to the oracle's, bit for bit."""
@@ -303,7 +341,8 @@ def test_ais_sweeps_f64_bit_exact(oracle, kabc, ctx, name, N, scale, ndraws):
     assert da.counters()["accepted"] > 0
 
 
-@pytest.mark.parametrize("name,N,maxcost,ndraws", [("normal", 40, 0.3, 100), ("ma2", 300, 0.5, 100)])
+@pytest.mark.parametrize("name,N,maxcost,ndraws", [("normal", 40, 0.3, 100), ("ma2", 300, 0.5, 100), ("socks", 60, 0.1, None),
+                                                    ("noisyprod", 50, 0.01, None)])
 def test_ais_hard_threshold_posterior_bit_exact(oracle, kabc, ctx, name, N, maxcost, ndraws):
     """ApproxPosterior (ref src/types.jl:76-104): (logprior, cost) state, accept = (-randexp <= lW) && max(maxcost,old)-new >= 0."""
     cfg = dict(nwalkers=N, nsamples=1, scale=maxcost, posterior=1)
@@ -349,6 +388,31 @@ def test_ais_readme_posterior_f32(kabc, ctx):
     print(mu, sg)
     assert abs(mu.mean() - 2.0) < 0.002 and abs(sg.mean() - 0.04) < 0.0005
     assert 0.0005 < sg.std() < 0.002  # README.md:66: sigma = 0.0395 +- 0.00093
+
+
+def test_socks_reference_integration_test(kabc, ctx):
+    """ref test/runtests.jl:33-74 at the reference's own sizes: Factored(NegativeBinomial, Beta) prior, the socks simulator,
+    tinydata = (0, 11): results ≈ 46.2 and ≈ 0.866 from AIS on the hard-threshold posterior and from smc."""
+    pri = kabc.Factored(kabc.NegativeBinomial(SOCKS_R, SOCKS_P), kabc.Beta(15, 2))
+    plan = kabc.ApproxPosterior(pri, kabc.Socks((0, 11), 11), 0.1)
+    res = kabc.sample(plan, kabc.AIS(500), 5000, ntransitions=100, ctx=ctx)
+    assert res[0].approx(46.2) and abs(res[0].mean() - 46.2) < 1.5 and (res[0].particles == np.rint(res[0].particles)).all()
+    assert res[1].approx(0.866) and abs(res[1].mean() - 0.866) < 0.01
+    out = kabc.smc(pri, kabc.Socks((0, 11), 11), nparticles=5000, alpha=0.99, r_epstol=0, epstol=0.01, ctx=ctx)
+    P = out.P
+    assert P[0].approx(46.2) and abs(P[0].mean() - 46.2) < 1.5 and (P[0].particles == np.rint(P[0].particles)).all()
+    assert P[1].approx(0.866) and abs(P[1].mean() - 0.866) < 0.01
+    assert out.eps <= 0.01 and (out.C <= out.eps).all()
+
+
+def test_normal_times_discrete_uniform_inference(kabc, ctx):
+    """ref test/runtests.jl:105-112 at the reference's sizes: sim(Tuple(res)) ≈ 5.5."""
+    pri = kabc.Factored(kabc.Normal(1, 0.5), kabc.DiscreteUniform(1, 10))
+    plan = kabc.ApproxPosterior(pri, kabc.NoisyProduct(5.5, 0.01), 0.01)
+    n, du = kabc.sample(plan, kabc.AIS(100), 1000, discard_initial=10000, ctx=ctx)
+    assert (du.particles == np.rint(du.particles)).all() and du.particles.min() >= 1 and du.particles.max() <= 10
+    sim = kabc.Particles((n.particles ** 2 + du.particles) * n.particles)
+    assert sim.approx(5.5) and abs(sim.mean() - 5.5) < 0.05
 
 
 def test_ais_errors(kabc, ctx):

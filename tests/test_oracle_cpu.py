@@ -133,6 +133,145 @@ def test_prior_sampling_moments(oracle):
     assert abs(th[2].mean() + 1) < 0.06 and abs(th[2].std() - 2.5) < 0.05
 
 
+def test_lgamma_and_added_laws_against_scipy(oracle, golden):
+    """Beta / NegativeBinomial / DiscreteUniform (ref test/runtests.jl:50-51,106) + the spec'd log-gamma they use."""
+    from scipy import special, stats
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    for x in np.concatenate([rng.uniform(1e-6, 30, 5000), rng.uniform(30, 1e5, 1000), [1.0, 2.0, 0.5, 10.0, 9.999999]]):
+        r = special.gammaln(x)
+        assert abs(L.kor_lgamma(float(x)) - r) <= 1e-14 * max(1.0, abs(r))
+    for x, y in golden["lgamma"]:
+        assert L.kor_lgamma(fh(x)) == fh(y)
+    from common import SOCKS_P, SOCKS_R
+    cases = [(("beta", 15, 2), stats.beta(15, 2).logpdf), (("beta", 0.5, 0.7), stats.beta(0.5, 0.7).logpdf),
+             (("beta", 1, 3), stats.beta(1, 3).logpdf), (("negbin", SOCKS_R, SOCKS_P), stats.nbinom(SOCKS_R, SOCKS_P).logpmf),
+             (("negbin", 0.6, 0.9), stats.nbinom(0.6, 0.9).logpmf), (("duniform", 1, 10), stats.randint(1, 11).logpmf)]
+    for spec, ref in cases:
+        pri = oracle.make_priors([spec])
+        xs = rng.uniform(0.001, 0.999, 300) if spec[0] == "beta" else np.arange(0, 300, dtype=float)
+        for x in xs:
+            a, b = lp(oracle, pri, [x]), ref(x)
+            assert (a == b == -math.inf) or abs(a - b) < 1e-11 * max(1.0, abs(b)), (spec, x, a, b)
+    # outside the support / non-integer arguments of the discrete laws
+    assert lp(oracle, oracle.make_priors([("beta", 15, 2)]), [1.5]) == -math.inf
+    assert lp(oracle, oracle.make_priors([("negbin", 3, 0.5)]), [-1.0]) == -math.inf
+    assert lp(oracle, oracle.make_priors([("negbin", 3, 0.5)]), [2.5]) == -math.inf
+    assert lp(oracle, oracle.make_priors([("duniform", 1, 10)]), [3.5]) == -math.inf
+    assert lp(oracle, oracle.make_priors([("duniform", 1, 10)]), [11.0]) == -math.inf
+    assert abs(lp(oracle, oracle.make_priors([("beta", 1, 3)]), [0.0]) - math.log(3.0)) < 1e-15   # xlogy(0, 0) = 0
+
+
+def test_added_laws_sampling_distributions(oracle):
+    from scipy import stats
+    from common import SOCKS_P, SOCKS_R
+    n = 20000
+    th = prior_draws(oracle, [("negbin", SOCKS_R, SOCKS_P), ("beta", 15, 2), ("duniform", 1, 10), ("beta", 0.5, 0.7),
+                              ("negbin", 0.6, 0.9)], n)
+    assert stats.kstest(th[1], stats.beta(15, 2).cdf).pvalue > 1e-3 and stats.kstest(th[3], stats.beta(0.5, 0.7).cdf).pvalue > 1e-3
+    for row, law in [(th[0], stats.nbinom(SOCKS_R, SOCKS_P)), (th[4], stats.nbinom(0.6, 0.9)), (th[2], stats.randint(1, 11))]:
+        assert (row == np.rint(row)).all() and row.min() >= 0
+        k, c = np.unique(row, return_counts=True)
+        e = law.pmf(k) * n
+        sel = e > 20
+        chi2 = ((c[sel] - e[sel]) ** 2 / e[sel]).sum()
+        assert chi2 < sel.sum() + 5 * math.sqrt(2 * sel.sum()) + 5, (chi2, sel.sum())
+    assert abs(th[0].mean() - 30) < 0.5 and abs(th[0].std() - 15) < 0.5       # prior_mu, prior_sd of the reference test
+
+
+def test_push_p(oracle):
+    """ref test/runtests.jl:24-31 and src/types.jl:28-32: continuous components pass, discrete ones round (ties to even)."""
+    L = oracle.lib()
+    pri = oracle.make_priors([("normal", 0, 1), ("duniform", 0, 1), ("negbin", 3, 0.5), ("beta", 2, 2)])
+    x = np.array([2.0, 1.0, 2.5, 0.3])
+    out = np.empty(4)
+    L.kor_push_p(pri, 4, x.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert list(out) == [2.0, 1.0, 2.0, 0.3]
+    x = np.array([-0.49, 3.5, -0.5, 0.3])
+    L.kor_push_p(pri, 4, x.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert list(out) == [-0.49, 4.0, -0.0, 0.3]
+
+
+def test_added_priors_match_golden(oracle, golden):
+    g = golden["priors_ext"]
+    spec = [tuple(s_) for s_ in g["spec"]]
+    th = prior_draws(oracle, spec, g["shape"][1])
+    assert [float(x).hex() for x in th.ravel()] == g["draws"]
+    pri = oracle.make_priors(spec)
+    lps = []
+    for k in range(len(spec)):
+        one = (oracle.Prior * 1)(pri[k])
+        for x in list(th[k]) + [0.0, 1.0, 2.5, -1.0, 7.0]:
+            lps.append(oracle.lib().kor_prior_logpdf(one, 1, (C.c_double * 1)(float(x))))
+    assert [float(x).hex() for x in lps] == g["logpdf"]
+
+
+def test_socks_cost_against_numpy(oracle):
+    """ref test/runtests.jl:34-44 restated with numpy on the spec'd Fisher-Yates draw."""
+    L = oracle.lib()
+    m = oracle.make_model(oracle.SOCKS, 0, (0, 11), (11,))
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        n = int(rng.integers(0, 80)) if trial else 0
+        prop = float(rng.uniform(0, 1))
+        pid, ep = int(rng.integers(0, 1000)), int(rng.integers(0, 50))
+        n_pairs = int(np.rint(prop * math.floor(n / 2)))
+        n_odd = n - 2 * n_pairs
+        socks = sorted(list(range(1, n_pairs + 1)) * 2 + list(range(n_pairs + 1, n_pairs + n_odd + 1)))
+        perm = list(range(n))
+        mp = min(n, 11)
+        for j in range(mp):
+            r = j + L.kor_index(L.kor_stream_word(SEED, 3, pid, ep, j), n - j)
+            perm[j], perm[r] = perm[r], perm[j]
+        picked = [socks[q] for q in perm[:mp]]
+        lu = len(set(picked))
+        pairs, odds = mp - lu, lu - (mp - lu)
+        th = np.array([float(n), prop])
+        c = L.kor_cost(m, SEED, 2, th.ctypes.data_as(C.POINTER(C.c_double)), pid, ep)
+        assert c == abs(pairs - 0) + abs(odds - 11)
+    th = np.array([-1.0, 0.5])
+    assert L.kor_cost(m, SEED, 2, th.ctypes.data_as(C.POINTER(C.c_double)), 0, 0) == math.inf
+
+
+def test_socks_reference_integration_test(oracle, golden):
+    """ref test/runtests.jl:46-74: the posterior of (n_socks, prop_pairs) given (0 pairs, 11 odd): 46.2 and 0.866 from both
+    sample(ApproxPosterior(..., 0.1), AIS(500), 5000, ntransitions = 100) and smc(..., nparticles = 5000, alpha = 0.99,
+    r_epstol = 0, epstol = 0.01)."""
+    M = models(oracle, None)["socks"]
+    s = oracle.Smc(SEED, oracle.make_priors(M["ospec"]), M["omodel"](),
+                   oracle.smc_config(nparticles=5000, alpha=0.99, r_epstol=0, epstol=0.01), nthreads=8)
+    s.run()
+    th, X, _, alive = s.state()
+    n, p = np.rint(th[0][alive > 0]), th[1][alive > 0]
+    assert (X[alive > 0] <= s.scalars()["eps"]).all()
+    assert abs(n.mean() - 46.2) / n.std(ddof=1) < 2 and abs(n.mean() - 46.2) < 1.5          # P[1] ≈ 46.2
+    assert abs(p.mean() - 0.866) / p.std(ddof=1) < 2 and abs(p.mean() - 0.866) < 0.01       # P[2] ≈ 0.866
+    a = oracle.Ais(SEED, oracle.make_priors(M["ospec"]), M["omodel"](),
+                   oracle.ais_config(500, 5000, ntransitions=100, scale=0.1, posterior=1), nthreads=8)
+    out = a.run_parallel()
+    assert (out[0] == np.rint(out[0])).all()                                                 # recorded samples are pushed
+    assert abs(out[0].mean() - 46.2) < 1.5 and abs(out[1].mean() - 0.866) < 0.01
+    # reduced-size golden runs
+    s = oracle.Smc(SEED, oracle.make_priors(M["ospec"]), M["omodel"](),
+                   oracle.smc_config(nparticles=500, alpha=0.99, r_epstol=0, epstol=0.01))
+    s.run()
+    g = golden["smc_socks_500"]
+    assert [float(r["eps"]).hex() for r in s.log()] == g["eps"] and [r["n_alive"] for r in s.log()] == g["n_alive"]
+    assert float(s.state()[0].sum()).hex() == g["theta_sum"] and s.scalars()["cost_evals"] == g["cost_evals"]
+
+
+def test_normal_times_discrete_uniform_inference(oracle):
+    """ref test/runtests.jl:105-112: Factored(Normal(1,0.5), DiscreteUniform(1,10)), sim((n,du)) = (n*n+du)*(n+randn()*0.01),
+    ApproxPosterior(|sim - 5.5|, 0.01), AIS(100), 1000 samples, discard_initial = 10000 -> sim(res) ≈ 5.5."""
+    M = models(oracle, None)["noisyprod"]
+    a = oracle.Ais(SEED, oracle.make_priors(M["ospec"]), M["omodel"](),
+                   oracle.ais_config(100, 1000, discard_initial=10000, scale=0.01, posterior=1), nthreads=8)
+    n, du = a.run_sequential()
+    assert (du == np.rint(du)).all() and du.min() >= 1 and du.max() <= 10 and len(np.unique(du)) > 3
+    sim = (n * n + du) * n
+    assert abs(sim.mean() - 5.5) / sim.std(ddof=1) < 2 and abs(sim.mean() - 5.5) < 0.05
+
+
 # ------------------------------------------------------------------ quantile (Statistics.jl type 7, ref src/smc.jl:134)
 def test_quantile_type7_against_numpy(oracle):
     L = oracle.lib()
