@@ -810,7 +810,7 @@ static void smc_sweep(kor_smc_t *s, uint32_t e, int64_t lo, int64_t hi, int64_t 
         evals += 1;
         s->txp[i] = Xp;
         if (flag ? (Xp > eps) : (Xp >= eps)) { s->tdec[i] = 3; continue; }
-        for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = thp[k];
+        for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = s->thp[(int64_t)k * N + i]; /* ref :182 stores the raw proposal */
         s->X[i] = Xp;
         s->lpi[i] = lpip;
         s->tdec[i] = 4;
