@@ -47,10 +47,18 @@ pod(c::GandK) = KabcModel(2, c.f32, c.n, 7, pad(c.target, 32), pad((c.c,), 8))
 struct LotkaVolterra <: DeviceCost; target::Vector{Float64}; x0::Float64; y0::Float64; T::Float64; max_events::Int; f32::Bool; end
 pod(c::LotkaVolterra) = KabcModel(3, c.f32, 0, length(c.target), pad(c.target, 32),
                                   pad((c.x0, c.y0, c.T, length(c.target) ÷ 2, c.max_events), 8))
+# the simulators of the reference's own integration tests (test/runtests.jl:34-44 and :105-112)
+struct Socks <: DeviceCost; target::NTuple{2,Float64}; n_picked::Int; end
+pod(c::Socks) = KabcModel(5, 0, 0, 2, pad(c.target, 32), pad((c.n_picked,), 8))
+struct NoisyProduct <: DeviceCost; target::Float64; noise::Float64; end
+pod(c::NoisyProduct) = KabcModel(4, 0, 0, 1, pad((c.target,), 32), pad((2.0, c.noise), 8))
 
 pod(d::Uniform) = KabcPrior(0, 0, d.a, d.b, d.a, d.b)
 pod(d::Normal) = KabcPrior(1, 0, d.μ, d.σ, -Inf, Inf)
 pod(d::Truncated{<:Normal}) = KabcPrior(2, 0, d.untruncated.μ, d.untruncated.σ, d.lower, d.upper)
+pod(d::Beta) = KabcPrior(3, 0, d.α, d.β, 0.0, 1.0)
+pod(d::NegativeBinomial) = KabcPrior(4, 0, d.r, d.p, 0.0, Inf)      # discrete: the library applies push_p (round) itself
+pod(d::DiscreteUniform) = KabcPrior(5, 0, d.a, d.b, d.a, d.b)
 pods(p::Factored) = KabcPrior[pod(q) for q in p.p]
 pods(p::UnivariateDistribution) = KabcPrior[pod(p)]
 
@@ -108,5 +116,5 @@ function sample(model::KissABC.ApproxPosterior{<:Any,<:DeviceCost}, spl::AIS, Ns
     bundle(out)
 end
 
-export DeviceCost, NormalMeanStd, MA2, GandK, LotkaVolterra, Context
+export DeviceCost, NormalMeanStd, MA2, GandK, LotkaVolterra, Socks, NoisyProduct, Context
 end # module
