@@ -45,6 +45,7 @@ struct SmcCtrl {
     unsigned long long sw_accepted, sw_events, sw_minkey; // per-sweep partials of this rank
     long long iteration;
     unsigned int work_count, cand_count, epoch, lv_head;
+    unsigned int push_count; // rows final after k_smc_propose whose peer pushes ride under the simulate kernel (multi GPU)
     unsigned int tk_hist, tk_final, tk_cut, tk_gather, tk_sim;
     int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log, sel_done, bounds_known;
     int honor_stop; // kabc_smc_run enqueues one iteration ahead: once `stop` is set the queued kernels do nothing
@@ -629,7 +630,7 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
     const int resample = c->resample;
     const unsigned int n_src = (unsigned int)c->ess;
     const uint32_t epoch = c->epoch;
-    bool push = false;
+    bool push = false, defer = false;
     int dec = 0;
     long long a = -1, b = -1;
     double z = dnan(), lprob = dnan(), lpip = dnan();
@@ -688,9 +689,9 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
             }
             if (B.trace_on && lprob != lprob) lprob = xlog(u01(wu));
         }
-        if (!push && B.n_peers > 0) {
-            push_row<DM>(B, P, D, i, row, Xi, lpi_i);
-        }
+        // multi GPU: a row that is final here still has to reach the peers.  Pushing it from this (latency-bound) kernel
+        // cost 300 us at 8 GPUs; it is queued instead and the simulate kernel issues the NVLink stores under its arithmetic
+        defer = !push && B.n_peers > 0;
         if (B.trace_on) {
             B.tr.a[i] = a; B.tr.b[i] = b; B.tr.z[i] = z; B.tr.lprob[i] = lprob; B.tr.lpip[i] = lpip;
             B.tr.dec[i] = (unsigned char)dec; B.tr.xp[i] = dnan();
@@ -712,6 +713,20 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
     }
     __syncthreads();
     if (push) B.work[s_base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
+    if (B.n_peers > 0) { // the deferred pushes fill the same array from its far end: work + deferred <= shard size <= N
+        __syncthreads();
+        const unsigned int ball2 = __ballot_sync(0xffffffffu, defer);
+        if (lane == 0) s_cnt[warp] = __popc(ball2);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
+            s_base = tot ? atomicAdd(&c->push_count, tot) : 0u;
+        }
+        __syncthreads();
+        if (defer) B.work[(N - 1) - (long long)(s_base + s_cnt[warp] + __popc(ball2 & ((1u << lane) - 1u)))] = (unsigned int)i;
+    }
 }
 
 // ------------------------------------------------------------------ sweep / iteration bookkeeping
@@ -731,7 +746,7 @@ __device__ void post_sweep(SmcBufs &B, const SmcParams &P, bool from_partials) {
     c->cost_evals += work;
     c->events += ev;
     if (mk < c->xmin_key) c->xmin_key = mk;
-    c->sw_accepted = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->work_count = 0; c->lv_head = 0;
+    c->sw_accepted = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->work_count = 0; c->lv_head = 0; c->push_count = 0;
     c->sweeps += 1;
     c->epoch += 1;
     c->cur ^= 1;      // copy D is now complete on every rank
@@ -816,6 +831,18 @@ __device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCt
     if (B.trace_on) { B.tr.xp[i] = Xp; B.tr.dec[i] = reject ? 3 : 4; }
 }
 
+// entry j of the deferred list (rows k_smc_propose finalised in copy D): NVLink stores into every peer replica
+template <int DM>
+__device__ __forceinline__ void push_deferred(const SmcBufs &B, const SmcParams &P, const SmcCtrl *c, unsigned int j) {
+    const long long N = P.N;
+    const int D = c->cur ^ 1;
+    const long long i = B.work[(N - 1) - (long long)j];
+    double row[DM];
+#pragma unroll
+    for (int k = 0; k < DM; ++k) row[k] = k < P.d ? B.th[D][(long long)k * N + i] : 0.0;
+    push_row<DM>(B, P, D, i, row, B.X[D][i], B.lpi[D][i]);
+}
+
 template <int KIND, int PREC>
 __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
     SmcCtrl *c = B.ctrl;
@@ -826,6 +853,7 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
     }
     const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int nwork = c->work_count;
+    constexpr int DM = KIND == KABC_MODEL_LV_SSA ? 3 : (KIND == KABC_MODEL_DETERMINISTIC ? KABC_MAX_DIM : 2);
     unsigned int nacc_w = 0;
     unsigned long long e_w = 0, key_w = ~0ull;
     if ((w & ~31u) < nwork) {
@@ -837,7 +865,6 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
             const long long N = P.N;
             const double *thp = B.thp;
             double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, [&](int k) { return thp[(long long)k * N + i]; }, ev);
-            constexpr int DM = KIND == KABC_MODEL_LV_SSA ? 3 : (KIND == KABC_MODEL_DETERMINISTIC ? KABC_MAX_DIM : 2);
             smc_accept<DM>(B, P, c, i, Xp, acc);
             if (acc) key = dkey(Xp);
         }
@@ -845,6 +872,9 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
         e_w = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
         if (nacc_w) key_w = warp_min_u64(key);
     }
+    // deferred peer pushes go AFTER the thread's own simulation: CTAs retire at staggered times, so the NVLink stores are
+    // spread over the whole kernel and stall no warp that still has arithmetic to do
+    if (B.n_peers > 0 && w < c->push_count) push_deferred<DM>(B, P, c, w);
     // block-level fold of the sweep counters: one set of global atomics per CTA
     __shared__ unsigned int s_acc;
     __shared__ unsigned long long s_ev, s_key;
@@ -879,6 +909,9 @@ __global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P,
     const long long N = P.N;
     const uint32_t epoch = c->epoch;
     const unsigned int lane = threadIdx.x & 31;
+    if (B.n_peers > 0)
+        for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < c->push_count; j += gridDim.x * blockDim.x)
+            push_deferred<3>(B, P, c, j);
     LvSim<PREC != KABC_F64> sim;
     long long i = -1;
     bool have = false, exhausted = false;
@@ -937,6 +970,9 @@ __global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcPa
     }
     const unsigned int nwork = c->work_count;
     const long long N = P.N;
+    if (B.n_peers > 0)
+        for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < c->push_count; j += gridDim.x * blockDim.x)
+            push_deferred<4>(B, P, c, j);
     for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const long long i = B.work[w];
         const double *thp = B.thp;
@@ -1005,6 +1041,11 @@ struct kabc_smc {
     bool inited = false;
     long long launches = 0;
     int nblocks_scan = 0;
+    // one whole iteration (cut + sweep, all control flow on the device) captured as a CUDA graph: a single launch instead
+    // of 7-9, so the short selection kernels run back to back even when the host is not ahead of the device
+    cudaGraphExec_t iter_graph = nullptr;
+    int graph_kernels = 0;
+    bool graph_ok = true;
     // optional warm per-kernel timing of one iteration (kabc_smc_profile_iteration)
     std::vector<cudaEvent_t> *prof = nullptr;
     void mark() {
@@ -1286,6 +1327,46 @@ static int smc_enqueue_iteration(kabc_smc *s) {
     return KABC_OK;
 }
 
+static void smc_drop_graph(kabc_smc *s) {
+    if (s->iter_graph) cudaGraphExecDestroy(s->iter_graph);
+    s->iter_graph = nullptr;
+}
+
+// enqueue one iteration: through the captured graph when the launch sequence is fixed (no retry sweeps, which need the
+// host between sweeps; no NCCL row all-gather, whose buffers alternate), else kernel by kernel
+static int smc_launch_iteration(kabc_smc *s) {
+    kabc_ctx *ctx = s->ctx;
+    static const bool env_off = [] { const char *e = getenv("KABC_NO_GRAPH"); return e && e[0] == '1'; }();
+    const bool eligible = s->graph_ok && !env_off && !s->prof && s->P.mcmc_retrys == 0 &&
+                          s->model.kind != KABC_MODEL_GK_OCTILE && (ctx->world == 1 || s->p2p);
+    if (!eligible) return smc_enqueue_iteration(s);
+    if (!s->iter_graph) {
+        const long long l0 = s->launches, c0 = ctx->launches;
+        const int cur0 = s->cur;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = KABC_OK;
+        if (e == cudaSuccess) {
+            rc = smc_enqueue_iteration(s);
+            e = cudaStreamEndCapture(ctx->stream, &g);
+        }
+        s->graph_kernels = (int)(s->launches - l0);
+        s->launches = l0; ctx->launches = c0; s->cur = cur0; // nothing ran yet
+        if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&s->iter_graph, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess || rc) { // capture not possible here: fall back for good
+            cudaGetLastError();
+            s->iter_graph = nullptr;
+            s->graph_ok = false;
+            return smc_enqueue_iteration(s);
+        }
+    }
+    KABC_CUDA_TRY(cudaGraphLaunch(s->iter_graph, ctx->stream));
+    SMC_LAUNCHED(s, s->graph_kernels);
+    s->cur ^= 1;
+    return KABC_OK;
+}
+
 extern "C" {
 
 int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model,
@@ -1355,6 +1436,7 @@ int kabc_smc_destroy(kabc_smc_t *s) {
     if (!s) return KABC_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    smc_drop_graph(s);
     for (void *m : s->peer_maps) cudaIpcCloseMemHandle(m);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     delete s;
@@ -1375,7 +1457,7 @@ int kabc_smc_iterate(kabc_smc_t *s, int *stop) {
     if (!s || !stop) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
     if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_smc_init must be called first");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
-    if (int rc = smc_enqueue_iteration(s)) return rc;
+    if (int rc = smc_launch_iteration(s)) return rc;
     if (int rc = smc_read_ctrl(s)) return rc;
     if (int rc = smc_ctrl_error(s)) return rc;
     *stop = s->h_ctrl->stop;
@@ -1390,7 +1472,7 @@ int kabc_smc_iterate_n(kabc_smc_t *s, int n, int ignore_stop, int *done, float *
     KABC_CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     int it = 0;
     for (; it < n; ++it) {
-        if (int rc = smc_enqueue_iteration(s)) return rc;
+        if (int rc = smc_launch_iteration(s)) return rc;
         if (!ignore_stop) {
             if (int rc = smc_read_ctrl(s)) return rc;
             if (int rc = smc_ctrl_error(s)) return rc;
@@ -1506,6 +1588,7 @@ int kabc_smc_trace_enable(kabc_smc_t *s, int on) {
         s->B.tr.lpip = s->tlpip.p; s->B.tr.xp = s->txp.p; s->B.tr.dec = s->tdec.p; s->B.tr.thp = s->thp.p;
     }
     s->B.trace_on = on ? 1 : 0;
+    smc_drop_graph(s); // the captured launches hold SmcBufs by value
     return KABC_OK;
 }
 
@@ -1559,7 +1642,7 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
             SMC_LAUNCHED(s, 1);
         }
         auto enqueue = [&](int slot) -> int {
-            if (int r2 = smc_enqueue_iteration(s)) return r2;
+            if (int r2 = smc_launch_iteration(s)) return r2;
             if (cudaMemcpyAsync(&slots[slot], s->B.ctrl, sizeof(SmcCtrl), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaEventRecord(ev[slot], st) != cudaSuccess)
                 return set_error(KABC_ERR_CUDA, "pipeline enqueue failed");
