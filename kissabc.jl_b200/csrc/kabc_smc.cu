@@ -31,6 +31,7 @@ constexpr int SCAN_THREADS = 1024; // particles per block of the cut / scatter k
 
 struct RankPartial { // what a rank contributes to the sweep bookkeeping
     unsigned long long accepted, work, events, minkey;
+    unsigned long long pushed; // records this rank left in every peer's inbox during the sweep (packed pushes)
 };
 
 struct SmcCtrl {
@@ -45,7 +46,7 @@ struct SmcCtrl {
     unsigned long long sw_accepted, sw_events, sw_minkey; // per-sweep partials of this rank
     long long iteration;
     unsigned int work_count, cand_count, epoch, lv_head;
-    unsigned int push_count; // rows final after k_smc_propose whose peer pushes ride under the simulate kernel (multi GPU)
+    unsigned int push_count; // rows k_smc_propose finalised and packed into the peers' inboxes this sweep (multi GPU)
     unsigned int tk_hist, tk_final, tk_cut, tk_gather, tk_sim;
     int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log, sel_done, bounds_known;
     int honor_stop; // kabc_smc_run enqueues one iteration ahead: once `stop` is set the queued kernels do nothing
@@ -76,6 +77,12 @@ struct SmcBufs {
     double *peer[KABC_MAX_PEERS];
     int n_peers;
     int shard_rows; // 1: only X is replicated; theta/lpi rows are read from their owner's slab in k_smc_propose
+    // packed pushes: rows that are final after k_smc_propose are few and scattered, and as single 8-byte NVLink stores
+    // they cost one packet each.  They are written instead as dense records into an inbox inside every peer's slab
+    // (planes [index | th_0..th_{d-1} | X | lpi], one region per (sweep parity, source rank)), which k_apply_inbox
+    // scatters locally after the sweep barrier.
+    int packed;
+    long long inbox_off; // offset (doubles) of the inbox region inside a slab
     unsigned char *alive;
     double *thp, *lpip;
     unsigned int *work, *idxalive, *blockcnt, *hist;
@@ -217,6 +224,7 @@ __global__ void k_smc_write_partial(SmcBufs B, SmcParams P) {
     SmcCtrl *c = B.ctrl;
     RankPartial p;
     p.accepted = c->sw_accepted; p.work = c->work_count; p.events = c->sw_events; p.minkey = c->sw_minkey;
+    p.pushed = 0;
     B.partial[P.rank] = p;
 }
 
@@ -689,9 +697,11 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
             }
             if (B.trace_on && lprob != lprob) lprob = xlog(u01(wu));
         }
-        // multi GPU: a row that is final here still has to reach the peers.  Pushing it from this (latency-bound) kernel
-        // cost 300 us at 8 GPUs; it is queued instead and the simulate kernel issues the NVLink stores under its arithmetic
-        defer = !push && B.n_peers > 0;
+        // multi GPU: a row that is final here still has to reach the peers
+        if (!push && B.n_peers > 0) {
+            if (B.packed) defer = true;
+            else push_row<DM>(B, P, D, i, row, Xi, lpi_i);
+        }
         if (B.trace_on) {
             B.tr.a[i] = a; B.tr.b[i] = b; B.tr.z[i] = z; B.tr.lprob[i] = lprob; B.tr.lpip[i] = lpip;
             B.tr.dec[i] = (unsigned char)dec; B.tr.xp[i] = dnan();
@@ -713,7 +723,7 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
     }
     __syncthreads();
     if (push) B.work[s_base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
-    if (B.n_peers > 0) { // the deferred pushes fill the same array from its far end: work + deferred <= shard size <= N
+    if (B.packed) { // record j of this rank's stream into every peer's inbox: consecutive lanes -> consecutive slots
         __syncthreads();
         const unsigned int ball2 = __ballot_sync(0xffffffffu, defer);
         if (lane == 0) s_cnt[warp] = __popc(ball2);
@@ -725,8 +735,39 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, l
             s_base = tot ? atomicAdd(&c->push_count, tot) : 0u;
         }
         __syncthreads();
-        if (defer) B.work[(N - 1) - (long long)(s_base + s_cnt[warp] + __popc(ball2 & ((1u << lane) - 1u)))] = (unsigned int)i;
+        if (defer) {
+            const long long j = (long long)(s_base + s_cnt[warp] + __popc(ball2 & ((1u << lane) - 1u)));
+            const long long per = N / P.world;
+            const long long box = B.inbox_off + ((long long)(c->epoch & 1u) * P.world + P.rank) * per * (P.d + 3);
+            const double Xi = B.X[D][i], lpi_i = B.lpi[D][i]; // the row was written above (L1/L2 hit)
+            for (int r = 0; r < B.n_peers; ++r) {
+                if (r == P.rank) continue;
+                double *q = B.peer[r] + box;
+                q[j] = __longlong_as_double(i);
+                for (int k = 0; k < P.d; ++k) q[(long long)(1 + k) * per + j] = B.th[D][(long long)k * N + i];
+                q[(long long)(1 + P.d) * per + j] = Xi;
+                q[(long long)(2 + P.d) * per + j] = lpi_i;
+            }
+        }
     }
+}
+
+// receiver side of the packed pushes: after the sweep barrier every rank scatters the records its peers left in its
+// inbox into copy D (local stores).  blockIdx.y = source rank.
+__global__ void __launch_bounds__(256) k_apply_inbox(SmcBufs B, SmcParams P) {
+    const SmcCtrl *c = B.ctrl;
+    if ((c->honor_stop && c->stop) || c->err || c->retry_done) return;
+    const int r = blockIdx.y;
+    if (r == P.rank) return;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (long long)B.partial[r].pushed) return;
+    const long long N = P.N, per = N / P.world;
+    const int D = c->cur ^ 1;
+    const double *q = B.peer[P.rank] + B.inbox_off + ((long long)(c->epoch & 1u) * P.world + r) * per * (P.d + 3);
+    const long long i = __double_as_longlong(q[j]);
+    for (int k = 0; k < P.d; ++k) B.th[D][(long long)k * N + i] = q[(long long)(1 + k) * per + j];
+    B.X[D][i] = q[(long long)(1 + P.d) * per + j];
+    B.lpi[D][i] = q[(long long)(2 + P.d) * per + j];
 }
 
 // ------------------------------------------------------------------ sweep / iteration bookkeeping
@@ -780,6 +821,7 @@ __device__ __forceinline__ void sweep_epilogue(SmcBufs &B, const SmcParams &P, i
     if (mode & 4) {
         RankPartial p;
         p.accepted = c->sw_accepted; p.work = c->work_count; p.events = c->sw_events; p.minkey = c->sw_minkey;
+        p.pushed = c->push_count;
         B.partial[P.rank] = p;
     }
     if (mode & 1) post_sweep(B, P, false);
@@ -831,18 +873,6 @@ __device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCt
     if (B.trace_on) { B.tr.xp[i] = Xp; B.tr.dec[i] = reject ? 3 : 4; }
 }
 
-// entry j of the deferred list (rows k_smc_propose finalised in copy D): NVLink stores into every peer replica
-template <int DM>
-__device__ __forceinline__ void push_deferred(const SmcBufs &B, const SmcParams &P, const SmcCtrl *c, unsigned int j) {
-    const long long N = P.N;
-    const int D = c->cur ^ 1;
-    const long long i = B.work[(N - 1) - (long long)j];
-    double row[DM];
-#pragma unroll
-    for (int k = 0; k < DM; ++k) row[k] = k < P.d ? B.th[D][(long long)k * N + i] : 0.0;
-    push_row<DM>(B, P, D, i, row, B.X[D][i], B.lpi[D][i]);
-}
-
 template <int KIND, int PREC>
 __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
     SmcCtrl *c = B.ctrl;
@@ -872,9 +902,6 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
         e_w = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
         if (nacc_w) key_w = warp_min_u64(key);
     }
-    // deferred peer pushes go AFTER the thread's own simulation: CTAs retire at staggered times, so the NVLink stores are
-    // spread over the whole kernel and stall no warp that still has arithmetic to do
-    if (B.n_peers > 0 && w < c->push_count) push_deferred<DM>(B, P, c, w);
     // block-level fold of the sweep counters: one set of global atomics per CTA
     __shared__ unsigned int s_acc;
     __shared__ unsigned long long s_ev, s_key;
@@ -909,9 +936,6 @@ __global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P,
     const long long N = P.N;
     const uint32_t epoch = c->epoch;
     const unsigned int lane = threadIdx.x & 31;
-    if (B.n_peers > 0)
-        for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < c->push_count; j += gridDim.x * blockDim.x)
-            push_deferred<3>(B, P, c, j);
     LvSim<PREC != KABC_F64> sim;
     long long i = -1;
     bool have = false, exhausted = false;
@@ -970,9 +994,6 @@ __global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcPa
     }
     const unsigned int nwork = c->work_count;
     const long long N = P.N;
-    if (B.n_peers > 0)
-        for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < c->push_count; j += gridDim.x * blockDim.x)
-            push_deferred<4>(B, P, c, j);
     for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const long long i = B.work[w];
         const double *thp = B.thp;
@@ -1166,6 +1187,12 @@ static int smc_attach_peers(kabc_smc *s) {
         // (propose 311 us vs 165 us at 2^22 particles), so full-row replication is the default
         const char *e2 = getenv("KABC_SHARD_ROWS");
         s->B.shard_rows = (e2 && e2[0] == '1') ? 1 : 0;
+        // measured on B200s (2^20 particles per GPU): at 2 GPUs the direct row stores are as fast (0.925 vs 0.926 ms per
+        // iteration), at 4 GPUs the packed records win (propose 128 us vs 165 us, 0.98 vs 1.01 ms per iteration)
+        const char *e3 = getenv("KABC_PACKED_PUSH");
+        const bool want_packed = e3 ? (e3[0] == '1') : (world >= 4);
+        s->B.packed = (!s->B.shard_rows && want_packed) ? 1 : 0;
+        s->B.inbox_off = 2 * (long long)(s->P.d + 2) * s->P.N;
     } else {
         for (int r = 0; r < world; ++r)
             if (r != ctx->rank && maps[r]) cudaIpcCloseMemHandle(maps[r]);
@@ -1263,6 +1290,11 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     if (dist) {
         // barrier + counters; without peer memory also the rows this rank wrote into copy D
         if (int rc = smc_allgather_state(s, s->cur ^ 1, !s->p2p)) return rc;
+        if (s->B.packed) {
+            const dim3 grid((unsigned)((n + 255) / 256), (unsigned)ctx->world);
+            k_apply_inbox<<<grid, 256, 0, ctx->stream>>>(s->B, s->P);
+            SMC_LAUNCHED(s, 1);
+        }
         k_post_sweep_dist<<<1, 1, 0, ctx->stream>>>(s->B, s->P, close_iter ? 1 : 0);
         SMC_LAUNCHED(s, 1);
         s->mark();
@@ -1394,7 +1426,8 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     const size_t copy_elems = nd + 2 * (size_t)N; // [th | X | lpi]
-    if (ctx->world > 1) A(s->slab.alloc(2 * copy_elems)); // peer-mapped slabs are not recycled
+    // multi GPU: + the inbox of the packed pushes, 2 sweep parities x world sources x (N/world) records of d+3 doubles
+    if (ctx->world > 1) A(s->slab.alloc(2 * copy_elems + 2 * (size_t)N * (d + 3))); // peer-mapped slabs are not recycled
     else A(s->slab.alloc(ctx, 2 * copy_elems));
     A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, N));
     A(s->alive.alloc(ctx, N)); A(s->work.alloc(ctx, N)); A(s->idxalive.alloc(ctx, N)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
@@ -1415,6 +1448,8 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     memset(s->B.peer, 0, sizeof s->B.peer);
     s->B.n_peers = 0;
     s->B.shard_rows = 0;
+    s->B.packed = 0;
+    s->B.inbox_off = 0;
     s->B.alive = s->alive.p; s->B.thp = s->thp.p;
     s->B.lpip = s->lpip.p; s->B.work = s->work.p; s->B.idxalive = s->idxalive.p; s->B.blockcnt = s->blockcnt.p;
     s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p; s->B.partial = s->partial.p;
