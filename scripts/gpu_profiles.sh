@@ -1,4 +1,5 @@
-# round-end evidence run: bench lines for every workload, ncu launch list and full captures of the top kernels
+# gpurun -- 'bash scripts/gpu_profiles.sh'   : round-end evidence: bench lines for every workload, ncu launch list, one
+# `--set full` capture of the two top kernels, warm and cold (L2 flushed) per-kernel times.  Copy what matters to profiles/.
 set -x
 python bench.py > gpurun_out/BENCH_normal_smc.json 2> gpurun_out/BENCH_normal_smc.err; cat gpurun_out/BENCH_normal_smc.json
 for w in ma2_smc lv_smc gk_ais; do
@@ -9,21 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --l
     python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_smc_simulate|k_smc_propose" -s 20 -c 4 -o gpurun_out/prof_final \
     python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_final.log 2>&1
-python - <<'PY'
-import sys, json
-sys.path.insert(0,'.')
-import kissabc_jl_b200 as k
-ctx = k.Context()
-out = {}
-for wl in ("normal_smc","ma2_smc","lv_smc"):
-    prior, cost = k.workloads.WORKLOADS[wl]("f32")
-    s = k.SmcSession(ctx, prior, cost, k.smc_config(nparticles=1<<20))
-    s.init(); s.iterate_n(30, ignore_stop=True)
-    acc = {}
-    for _ in range(10):
-        for kk,v in s.profile_iteration().items(): acc[kk] = acc.get(kk,0)+v/10
-    out[wl] = {kk: round(v,1) for kk,v in acc.items()}
-    print(wl, out[wl])
-json.dump(out, open('gpurun_out/warm_kernel_times.json','w'), indent=1)
-PY
+python scripts/kernel_times.py normal_smc ma2_smc lv_smc
+python scripts/kernel_times.py normal_smc --cold
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv
