@@ -212,6 +212,41 @@ int kabc_ais_trace_enable(kabc_ais_t *ais, int on);
 int kabc_ais_get_trace(kabc_ais_t *ais, uint8_t *move, int64_t *a, int64_t *b, int64_t *c, double *corr,
                        double *theta_p, double *lp_p, double *ll_p, double *e, uint8_t *decision);
 
+/* ---- ABCDE(prior, cost, eps_target; nparticles, generations, alpha, earlystop, proposal_width): src/smc.jl:352-428.
+ *      Population Monte Carlo with differential-evolution moves; every generation proposes for all particles from the
+ *      previous generation's state (Jacobi update, ref :379-381).  out_theta: d x nparticles SoA, push_p'ed (ref :421);
+ *      out_cost: nparticles; out_reached: maximum(cost) <= eps_target (ref :418); out_nsim: sum(nsims) (ref :407) ---- */
+typedef struct {
+    int64_t nparticles;    /* 50 */
+    int64_t generations;   /* 20 */
+    double eps_target;
+    double alpha;          /* 0 <= alpha < 1 (ref :353) */
+    double proposal_width; /* 1.0 */
+    int32_t earlystop;     /* false */
+    int32_t _pad;
+} kabc_abcde_config_t;
+int kabc_abcde_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model, const kabc_abcde_config_t *cfg,
+                   double *out_theta, double *out_cost, int32_t *out_reached, int64_t *out_nsim, int64_t *out_generations);
+
+/* ---- pfilter(prior, cost, N; q, eff_tol, epstol, max_iters, proposal_width): src/smc.jl:275-345.
+ *      Every iteration cuts at the q-quantile of the costs and redraws each particle above it from three particles
+ *      below it until prior pre-test and cost pass.  The particle count is kabc_pfilter_nparticles(N, d, q)
+ *      (ref :276-279); the caller sizes out_theta (d x that, SoA, push_p'ed) and out_cost with it.
+ *      max_iters = 0 means Inf.  Deviation: an iteration with no particle above the quantile ends the run (the
+ *      reference computes eff = 0/0 there and loops forever) ---- */
+typedef struct {
+    int64_t nparticles;
+    double q;              /* 0.7 */
+    double eff_tol;        /* 0.1 */
+    double epstol;         /* -Inf */
+    double proposal_width; /* 0.75 */
+    int64_t max_iters;     /* 0 = Inf */
+} kabc_pfilter_config_t;
+int64_t kabc_pfilter_nparticles(int64_t n, int d, double q);
+int kabc_pfilter_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model, const kabc_pfilter_config_t *cfg,
+                     double *out_theta, double *out_cost, double *out_eps, int64_t *out_iterations, int64_t *out_nreps,
+                     int64_t *out_cost_evals);
+
 /* ---- instruction-pipe microbenchmarks used to state the issue roofline (DESIGN.md "Roofline") ----
  * kind: 0 FFMA, 1 IMAD, 2 IMAD.WIDE(mul.wide.u32), 3 LOP3, 4 MUFU.LG2, 5 MUFU.SIN, 6 MUFU.SQRT, 7 DFMA,
  *       8 I2F, 9 Philox4x32-10 words, 10 F32 Box-Muller normals, 11 F64 spec normals.

@@ -5,14 +5,14 @@ _capi.py (ctypes binding), api.py (host mirror of the reference's Julia interfac
 Import as `import kissabc_jl_b200` (shim at the repo root).
 """
 from ._capi import KissABCError, LIB_PATH, SYMBOLS, lib  # noqa: F401
-from .api import (AIS, ApproxKernelizedPosterior, ApproxPosterior, AisSession, Beta, Context, Deterministic, DeviceCost,  # noqa: F401
+from .api import (ABCDE, AIS, AbcdeResult, PfilterResult, pfilter, ApproxKernelizedPosterior, ApproxPosterior, AisSession, Beta, Context, Deterministic, DeviceCost,  # noqa: F401
                   DiscreteUniform, Factored, NegativeBinomial, NoisyProduct, Socks,
                   GandK, LotkaVolterra, MA2, Normal, NormalMeanStd, Particles, SmcResult, SmcSession, Truncated,
                   Uniform, ais_config, default_context, sample, smc, smc_config)
 from . import _capi, dist, workloads  # noqa: F401
 
 __all__ = [
-    "sample", "AIS", "ApproxKernelizedPosterior", "ApproxPosterior", "Factored", "smc", "Uniform", "Normal", "Truncated", "Beta", "NegativeBinomial",
+    "sample", "AIS", "ABCDE", "pfilter", "ApproxKernelizedPosterior", "ApproxPosterior", "Factored", "smc", "Uniform", "Normal", "Truncated", "Beta", "NegativeBinomial",
     "DiscreteUniform", "Particles",
     "DeviceCost", "NormalMeanStd", "MA2", "GandK", "LotkaVolterra", "Deterministic", "NoisyProduct", "Socks", "Context", "SmcSession",
     "AisSession", "KissABCError", "smc_config", "ais_config",

@@ -44,6 +44,16 @@ class AisConfigT(C.Structure):
                 ("scale", C.c_double), ("posterior", C.c_int32), ("_pad", C.c_int32)]
 
 
+class AbcdeConfigT(C.Structure):
+    _fields_ = [("nparticles", C.c_int64), ("generations", C.c_int64), ("eps_target", C.c_double), ("alpha", C.c_double),
+                ("proposal_width", C.c_double), ("earlystop", C.c_int32), ("_pad", C.c_int32)]
+
+
+class PfilterConfigT(C.Structure):
+    _fields_ = [("nparticles", C.c_int64), ("q", C.c_double), ("eff_tol", C.c_double), ("epstol", C.c_double),
+                ("proposal_width", C.c_double), ("max_iters", C.c_int64)]
+
+
 class SmcLogT(C.Structure):
     _fields_ = [("iteration", C.c_int64), ("eps", C.c_double), ("n_alive", C.c_int64), ("flag", C.c_int32),
                 ("resampled", C.c_int32), ("accepted", C.c_int64), ("cost_evals", C.c_int64),
@@ -67,7 +77,8 @@ SYMBOLS = [
     "kabc_smc_get_scalars", "kabc_smc_get_log", "kabc_smc_kernel_launches", "kabc_smc_profile_iteration", "kabc_smc_trace_enable",
     "kabc_smc_get_trace", "kabc_ais_run", "kabc_ais_create", "kabc_ais_destroy", "kabc_ais_init",
     "kabc_ais_sweep", "kabc_ais_get_state", "kabc_ais_set_state", "kabc_ais_get_counters",
-    "kabc_ais_kernel_launches", "kabc_ais_trace_enable", "kabc_ais_get_trace", "kabc_microbench",
+    "kabc_ais_kernel_launches", "kabc_ais_trace_enable", "kabc_ais_get_trace", "kabc_abcde_run",
+    "kabc_pfilter_nparticles", "kabc_pfilter_run", "kabc_microbench",
 ]
 
 _lib = None
@@ -125,6 +136,12 @@ def lib():
     L.kabc_ais_kernel_launches.restype = C.c_int64
     L.kabc_ais_trace_enable.argtypes = [vp, C.c_int]
     L.kabc_ais_get_trace.argtypes = [vp, u8p, i64p, i64p, i64p, dp, dp, dp, dp, dp, u8p]
+    L.kabc_abcde_run.argtypes = [vp, C.POINTER(PriorT), C.c_int, C.POINTER(ModelT), C.POINTER(AbcdeConfigT), dp, dp,
+                                 C.POINTER(C.c_int32), i64p, i64p]
+    L.kabc_pfilter_nparticles.argtypes = [C.c_int64, C.c_int, C.c_double]
+    L.kabc_pfilter_nparticles.restype = C.c_int64
+    L.kabc_pfilter_run.argtypes = [vp, C.POINTER(PriorT), C.c_int, C.POINTER(ModelT), C.POINTER(PfilterConfigT), dp, dp, dp,
+                                   i64p, i64p, i64p]
     L.kabc_microbench.argtypes = [vp, C.c_int, dp, fp]
     _lib = L
     return L

@@ -470,6 +470,79 @@ def smc(prior, cost: DeviceCost, *, nparticles=100, alpha=0.95, mcmc_retrys=0, m
                      cost_evals=evals.value, log=log)
 
 
+# --------------------------------------------------------------------------------------- ABCDE, pfilter
+
+
+@dataclass
+class AbcdeResult:
+    P: Union[Particles, List[Particles]]
+    C: Particles
+    reached_eps: bool
+    nsim: int = 0
+    generations: int = 0
+
+    @property
+    def reached_ϵ(self):  # noqa: PLC2401  (the reference's field name)
+        return self.reached_eps
+
+
+def ABCDE(prior, cost: DeviceCost, eps_target, *, nparticles=50, generations=20, alpha=0.0, parallel=False, earlystop=False,
+          verbose=False, proposal_width=1.0, ctx: Optional[Context] = None) -> AbcdeResult:
+    """ABCDE(prior, cost, ϵ_target; nparticles=50, generations=20, α=0, earlystop=false, proposal_width=1.0)
+    -> (P, C, reached_ϵ), ref src/smc.jl:352-428.  `parallel` is accepted and ignored; `rng` is the context seed."""
+    del parallel
+    if not isinstance(cost, DeviceCost):
+        raise KissABCError(K.ERR_INVALID_ARG, "the device path needs a registered DeviceCost, not a closure")
+    ctx = ctx or default_context()
+    prior = _as_factored(prior)
+    d, N = len(prior), int(nparticles)
+    cfg = K.AbcdeConfigT(N, int(generations), float(eps_target), float(alpha), float(proposal_width), int(bool(earlystop)), 0)
+    th, X = np.empty((d, max(N, 1))), np.empty(max(N, 1))
+    reached, nsim, gens = C.c_int32(), C.c_int64(), C.c_int64()
+    m = cost._pod()
+    K.check(ctx.L.kabc_abcde_run(ctx.h, prior._pods(), d, C.byref(m), C.byref(cfg), K.dptr(th), K.dptr(X), C.byref(reached),
+                                 C.byref(nsim), C.byref(gens)))
+    if verbose:
+        print(f"End: converged = {bool(reached.value)} nsim = {nsim.value} range_ϵ = ({X.min()!r}, {X.max()!r})")
+    return AbcdeResult(P=_bundle(th), C=Particles(X), reached_eps=bool(reached.value), nsim=nsim.value, generations=gens.value)
+
+
+@dataclass
+class PfilterResult:
+    P: Union[Particles, List[Particles]]
+    C: Particles
+    eps: float = 0.0
+    iterations: int = 0
+    nreps: int = 0
+    cost_evals: int = 0
+
+
+def pfilter(prior, cost: DeviceCost, N, *, q=0.7, eff_tol=0.1, epstol=-math.inf, max_iters=math.inf, proposal_width=0.75,
+            verbose=False, parallel=False, ctx: Optional[Context] = None) -> PfilterResult:
+    """pfilter(prior, cost, N; q=0.7, eff_tol=0.1, epstol=-Inf, max_iters=Inf, proposal_width=0.75) -> (P, C),
+    ref src/smc.jl:275-345.  The particle count is raised to ceil((4d+1)/q) when N*q <= 4d, as in the reference."""
+    del parallel
+    if not isinstance(cost, DeviceCost):
+        raise KissABCError(K.ERR_INVALID_ARG, "the device path needs a registered DeviceCost, not a closure")
+    ctx = ctx or default_context()
+    prior = _as_factored(prior)
+    d = len(prior)
+    if not (0 < q <= 1):
+        raise KissABCError(K.ERR_INVALID_ARG, "pfilter needs 0 < q <= 1")
+    n = int(ctx.L.kabc_pfilter_nparticles(int(N), d, float(q)))
+    cfg = K.PfilterConfigT(int(N), float(q), float(eff_tol), float(epstol), float(proposal_width),
+                           0 if math.isinf(max_iters) else int(max_iters))
+    th, X = np.empty((d, n)), np.empty(n)
+    eps, it, reps, evals = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+    m = cost._pod()
+    K.check(ctx.L.kabc_pfilter_run(ctx.h, prior._pods(), d, C.byref(m), C.byref(cfg), K.dptr(th), K.dptr(X), C.byref(eps),
+                                   C.byref(it), C.byref(reps), C.byref(evals)))
+    if verbose:
+        print(f"(iters, ϵ, nreps) = ({it.value}, {eps.value!r}, {reps.value})")
+    return PfilterResult(P=_bundle(th), C=Particles(X), eps=eps.value, iterations=it.value, nreps=reps.value,
+                         cost_evals=evals.value)
+
+
 # --------------------------------------------------------------------------------------- AIS
 
 

@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkissabc_cuda.so")
-SOURCES = ["kabc_core.cu", "kabc_smc.cu", "kabc_ais.cu", "kabc_nccl.cu"]
+SOURCES = ["kabc_core.cu", "kabc_smc.cu", "kabc_ais.cu", "kabc_pmc.cu", "kabc_nccl.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -161,6 +161,71 @@ k_eval_cost_gk(DModel m, RoundKeys rk, const double *__restrict__ th, long long 
     }
 }
 
+// list-driven variant (ABCDE / pfilter): entry w of `list` names a particle i of an N-particle SoA state; its cost is
+// drawn from stream (tag, i, epoch) and written to out[i].  The entry count lives in device memory.
+template <int KIND, int PREC>
+__global__ void __launch_bounds__(256)
+k_eval_cost_list(DModel m, RoundKeys rk, const double *__restrict__ th, long long N, const unsigned int *__restrict__ list,
+                 const unsigned int *__restrict__ count, uint32_t tag, uint32_t epoch, double *__restrict__ out) {
+    const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= *count) return;
+    const long long i = list[w];
+    long long ev;
+    out[i] = cost_thread<KIND, PREC>(m, rk, tag, (uint32_t)i, epoch, [&](int k) { return th[(long long)k * N + i]; }, ev);
+}
+template <int PREC>
+__global__ void __launch_bounds__(GK_THREADS)
+k_eval_cost_list_gk(DModel m, RoundKeys rk, const double *__restrict__ th, long long N, const unsigned int *__restrict__ list,
+                    const unsigned int *__restrict__ count, uint32_t tag, uint32_t epoch, double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    const unsigned int n = *count;
+    for (unsigned int w = blockIdx.x; w < n; w += gridDim.x) {
+        const long long i = list[w];
+        double c = cost_gk_block<PREC>(m, rk, tag, (uint32_t)i, epoch, th[i], th[N + i], th[2 * N + i], th[3 * N + i], gk_smem);
+        if (threadIdx.x == 0) out[i] = c;
+    }
+}
+
+template <int KIND>
+static void launch_eval_list(kabc_ctx *ctx, const DModel &m, const double *d_th, long long N, const unsigned int *list,
+                             const unsigned int *count, long long max_count, uint32_t tag, uint32_t epoch, double *d_out) {
+    const unsigned blocks = (unsigned)((max_count + 255) / 256);
+    if (m.precision == KABC_F64)
+        k_eval_cost_list<KIND, KABC_F64><<<blocks, 256, 0, ctx->stream>>>(m, ctx->rk, d_th, N, list, count, tag, epoch, d_out);
+    else
+        k_eval_cost_list<KIND, KABC_F32_ACC64><<<blocks, 256, 0, ctx->stream>>>(m, ctx->rk, d_th, N, list, count, tag, epoch, d_out);
+    ctx->launches += 1;
+}
+
+int eval_cost_list_device(kabc_ctx *ctx, const DModel &m, const double *d_th, long long N, const unsigned int *list,
+                          const unsigned int *count, long long max_count, uint32_t tag, uint32_t epoch, double *d_out) {
+    if (max_count <= 0) return KABC_OK;
+    switch (m.kind) {
+    case KABC_MODEL_NORMAL_MEANSTD: launch_eval_list<KABC_MODEL_NORMAL_MEANSTD>(ctx, m, d_th, N, list, count, max_count, tag, epoch, d_out); break;
+    case KABC_MODEL_MA2_AUTOCOV: launch_eval_list<KABC_MODEL_MA2_AUTOCOV>(ctx, m, d_th, N, list, count, max_count, tag, epoch, d_out); break;
+    case KABC_MODEL_LV_SSA: launch_eval_list<KABC_MODEL_LV_SSA>(ctx, m, d_th, N, list, count, max_count, tag, epoch, d_out); break;
+    case KABC_MODEL_DETERMINISTIC: launch_eval_list<KABC_MODEL_DETERMINISTIC>(ctx, m, d_th, N, list, count, max_count, tag, epoch, d_out); break;
+    case KABC_MODEL_SOCKS: launch_eval_list<KABC_MODEL_SOCKS>(ctx, m, d_th, N, list, count, max_count, tag, epoch, d_out); break;
+    case KABC_MODEL_GK_OCTILE: {
+        size_t smem = gk_smem_bytes(m.n_draws, m.precision);
+        long long cap = (long long)ctx->sm_count * gk_blocks_per_sm(m.n_draws, m.precision);
+        unsigned blocks = (unsigned)(max_count < cap ? max_count : cap);
+        if (m.precision == KABC_F64) {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_eval_cost_list_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_eval_cost_list_gk<KABC_F64><<<blocks, GK_THREADS, smem, ctx->stream>>>(m, ctx->rk, d_th, N, list, count, tag, epoch, d_out);
+        } else {
+            KABC_CUDA_TRY(cudaFuncSetAttribute(k_eval_cost_list_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_eval_cost_list_gk<KABC_F32_ACC64><<<blocks, GK_THREADS, smem, ctx->stream>>>(m, ctx->rk, d_th, N, list, count, tag, epoch, d_out);
+        }
+        ctx->launches += 1;
+        break;
+    }
+    default: return set_error(KABC_ERR_INVALID_ARG, "unknown model kind %d", m.kind);
+    }
+    KABC_CUDA_TRY(cudaGetLastError());
+    return KABC_OK;
+}
+
 template <int KIND>
 static int launch_eval(kabc_ctx *ctx, const DModel &m, const double *d_th, long long n, uint32_t first_id,
                        uint32_t epoch, double *d_out, long long *d_ev) {

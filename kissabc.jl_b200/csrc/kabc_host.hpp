@@ -74,6 +74,9 @@ namespace kabc {
 // descriptor ingestion (validates and derives the constants the kernels need)
 int ingest_priors(const kabc_prior_t *prior, int d, DPriors &out);
 int ingest_model(const kabc_model_t *model, int d, DModel &out);
+// costs of the particles named by a device-side list (count in device memory, at most max_count), written to out[i]
+int eval_cost_list_device(kabc_ctx *ctx, const DModel &m, const double *d_th, long long N, const unsigned int *list,
+                          const unsigned int *count, long long max_count, uint32_t tag, uint32_t epoch, double *d_out);
 
 // host <-> device helpers bound to a context
 template <typename T>

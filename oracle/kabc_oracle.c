@@ -1258,3 +1258,233 @@ void kor_ais_get_trace(const kor_ais_t *s, uint8_t *move, int64_t *a, int64_t *b
     if (e) memcpy(e, s->te, 8 * N);
     if (decision) memcpy(decision, s->tdec, N);
 }
+
+/* ------------------------------------------------------------------ */
+/* ABCDE and pfilter -- ref: src/smc.jl:275-428                         */
+/* Shared spec: init draws particle i from stream (PRIOR, i, t) and      */
+/* costs it with (COST_INIT, i, t), t = 0,1,... until cost and logprior  */
+/* are finite (ref :284-297, :358-371).  The cost sees the RAW particle  */
+/* (`cost(p.x)`), the prior the push_p'ed one, as in the reference.      */
+/* ------------------------------------------------------------------ */
+#define PMC_INIT_TRIES 1000
+static int pmc_init(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model, int64_t N, int nthreads,
+                    double *th, double *lp, double *C, int64_t *evals_out) {
+    int bad = 0;
+    int64_t evals = 0;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1) reduction(| : bad) reduction(+ : evals)
+    for (int64_t i = 0; i < N; ++i) {
+        double x[16], xp[16];
+        int ok = 0;
+        for (int t = 0; t < PMC_INIT_TRIES && !ok; ++t) {
+            if (kor_prior_sample(seed, prior, d, (uint32_t)i, (uint32_t)t, x)) { bad = 1; break; }
+            kor_push_p(prior, d, x, xp);
+            double l = kor_prior_logpdf(prior, d, xp), c = NAN;
+            if (isfinite(l)) {
+                c = cost_dispatch(model, seed, ST_COST_INIT, d, x, (uint32_t)i, (uint32_t)t);
+                evals += 1;
+            }
+            if (isfinite(l) && isfinite(c)) {
+                for (int k = 0; k < d; ++k) th[(int64_t)k * N + i] = x[k];
+                lp[i] = l;
+                C[i] = c;
+                ok = 1;
+            }
+        }
+        if (!ok) bad = 1;
+    }
+    *evals_out = evals;
+    return bad;
+}
+
+typedef struct { uint64_t key; int64_t idx; } pmc_kv_t;
+static uint64_t dkey_of(double x) {
+    uint64_t b = d2u(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static int pmc_kv_cmp(const void *a, const void *b) {
+    const pmc_kv_t *p = (const pmc_kv_t *)a, *q = (const pmc_kv_t *)b;
+    if (p->key != q->key) return p->key < q->key ? -1 : 1;
+    return p->idx < q->idx ? -1 : (p->idx > q->idx ? 1 : 0);
+}
+
+int kor_abcde_run(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model, const kor_abcde_config_t *cfg,
+                  int nthreads, double *theta_out, double *cost_out, int32_t *reached, int64_t *nsim, int64_t *generations_done) {
+    const int64_t N = cfg->nparticles;
+    if (!(cfg->alpha >= 0.0 && cfg->alpha < 1.0)) return fail("\u03b1 must be in 0 <= \u03b1 < 1."); /* ref :353 */
+    if (N < 3) return fail("ABCDE needs at least 3 particles");
+    double *th = malloc(sizeof(double) * (size_t)N * d), *nth = malloc(sizeof(double) * (size_t)N * d);
+    double *lp = malloc(sizeof(double) * N), *nlp = malloc(sizeof(double) * N);
+    double *D = malloc(sizeof(double) * N), *nD = malloc(sizeof(double) * N);
+    pmc_kv_t *kv = malloc(sizeof(pmc_kv_t) * N);
+    int64_t sims = 0, gen = 0;
+    int rc = pmc_init(seed, prior, d, model, N, nthreads, th, lp, D, &sims);
+    if (rc) fail("Prior leads to non-finite costs too often");
+    sims = 0; /* ref :373 nsims counts the simulations of the generations only */
+    const double gam = (cfg->proposal_width * 2.38) / sqrt((double)(2 * d)); /* ref :374 */
+    while (!rc && gen < cfg->generations) {
+        gen += 1;
+        memcpy(nth, th, sizeof(double) * (size_t)N * d);
+        memcpy(nlp, lp, sizeof(double) * N);
+        memcpy(nD, D, sizeof(double) * N);
+        for (int64_t i = 0; i < N; ++i) { kv[i].key = dkey_of(D[i]); kv[i].idx = i; }
+        qsort(kv, (size_t)N, sizeof(pmc_kv_t), pmc_kv_cmp);
+        const double eps_l = D[kv[0].idx], eps_h = D[kv[N - 1].idx]; /* ref :382 extrema */
+        if (cfg->earlystop && eps_h <= cfg->eps_target) { gen -= 1; break; }
+        const double eps_pop = fmax(cfg->eps_target, eps_l + cfg->alpha * (eps_h - eps_l));
+        int64_t gsims = 0;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : gsims)
+        for (int64_t i = 0; i < N; ++i) {
+            if (cfg->earlystop && D[i] <= cfg->eps_target) continue;
+            stream_t st;
+            stream_init(&st, seed, ST_PROPOSE, (uint32_t)i, (uint32_t)gen);
+            int64_t s = i;
+            const double eps = D[i] <= cfg->eps_target ? cfg->eps_target : eps_pop;
+            if (D[i] > eps) {
+                /* ref :393 rand((1:n)[D .<= D[i]]): uniform over that set; spec: the set in (cost, index) order */
+                const uint64_t ki = dkey_of(D[i]);
+                int64_t lo = 0, hi = N; /* first position with key > ki */
+                while (lo < hi) { int64_t mid = (lo + hi) / 2; if (kv[mid].key <= ki) lo = mid + 1; else hi = mid; }
+                s = kv[kor_index(next_u32(&st), (uint32_t)lo)].idx;
+            }
+            int64_t a = s, b;
+            while (a == s) a = (int64_t)kor_index(next_u32(&st), (uint32_t)N);
+            b = a;
+            while (b == a || b == s) b = (int64_t)kor_index(next_u32(&st), (uint32_t)N);
+            double thp[16], thq[16];
+            for (int k = 0; k < d; ++k)
+                thp[k] = th[(int64_t)k * N + s] + (th[(int64_t)k * N + a] - th[(int64_t)k * N + b]) * gam;
+            kor_push_p(prior, d, thp, thq);
+            const double l = kor_prior_logpdf(prior, d, thq);
+            const double w = l - lp[i];
+            if (kor_log(next_uniform(&st)) > fmin(0.0, w)) continue;
+            gsims += 1;
+            const double dp = cost_dispatch(model, seed, ST_COST, d, thp, (uint32_t)i, (uint32_t)gen);
+            if (dp <= fmax(eps, D[i])) {
+                nD[i] = dp;
+                for (int k = 0; k < d; ++k) nth[(int64_t)k * N + i] = thp[k];
+                nlp[i] = l;
+            }
+        }
+        sims += gsims;
+        double *t;
+        t = th; th = nth; nth = t;
+        t = lp; lp = nlp; nlp = t;
+        t = D; D = nD; nD = t;
+    }
+    if (!rc) {
+        double mx = -INFINITY;
+        for (int64_t i = 0; i < N; ++i) {
+            double x[16], xp[16];
+            for (int k = 0; k < d; ++k) x[k] = th[(int64_t)k * N + i];
+            kor_push_p(prior, d, x, xp);
+            for (int k = 0; k < d; ++k) theta_out[(int64_t)k * N + i] = xp[k];
+            cost_out[i] = D[i];
+            if (D[i] > mx) mx = D[i];
+        }
+        if (reached) *reached = mx <= cfg->eps_target;
+        if (nsim) *nsim = sims;
+        if (generations_done) *generations_done = gen;
+    }
+    free(th); free(nth); free(lp); free(nlp); free(D); free(nD); free(kv);
+    return rc;
+}
+
+int64_t kor_pfilter_nparticles(int64_t n, int d, double q) {
+    const int64_t lowN = 4 * (int64_t)d;
+    if ((double)n * q <= (double)lowN) n = (int64_t)ceil((double)(lowN + 1) / q);
+    return n;
+}
+
+#define PF_MAX_ROUNDS 100000
+int kor_pfilter_run(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model, const kor_pfilter_config_t *cfg,
+                    int nthreads, double *theta_out, double *cost_out, double *eps_out, int64_t *iters_out, int64_t *nreps_out,
+                    int64_t *cost_evals) {
+    if (!(cfg->q > 0.0 && cfg->q <= 1.0)) return fail("pfilter needs 0 < q <= 1");
+    const int64_t N = kor_pfilter_nparticles(cfg->nparticles, d, cfg->q);
+    double *th = malloc(sizeof(double) * (size_t)N * d), *lp = malloc(sizeof(double) * N), *C = malloc(sizeof(double) * N);
+    int64_t *idxok = malloc(sizeof(int64_t) * N), *pend = malloc(sizeof(int64_t) * N), *pend2 = malloc(sizeof(int64_t) * N);
+    pmc_kv_t *kv = malloc(sizeof(pmc_kv_t) * N);
+    double *srt = malloc(sizeof(double) * N);
+    int64_t evals = 0, iters = 0, reps_total = 0;
+    uint32_t round = 0; /* epoch of the attempt streams: one per rejection round over the whole run */
+    double eps = INFINITY;
+    int rc = pmc_init(seed, prior, d, model, N, nthreads, th, lp, C, &evals);
+    if (rc) fail("Prior leads to non-finite costs too often");
+    while (!rc) {
+        iters += 1;
+        /* ref :300-302; spec: `rand(trng, idxok)` is taken over idxok in (cost, index) order, i.e. the head of one
+         * sort of the costs, whose tail is idxbad */
+        for (int64_t i = 0; i < N; ++i) { kv[i].key = dkey_of(C[i]); kv[i].idx = i; }
+        qsort(kv, (size_t)N, sizeof(pmc_kv_t), pmc_kv_cmp);
+        for (int64_t i = 0; i < N; ++i) srt[i] = C[kv[i].idx];
+        eps = quantile7_sorted(srt, N, cfg->q);
+        int64_t n_ok = 0, n_bad = 0;
+        for (int64_t i = 0; i < N; ++i) {
+            if (C[kv[i].idx] > eps) pend[n_bad++] = kv[i].idx;
+            else idxok[n_ok++] = kv[i].idx;
+        }
+        if (n_bad > 0 && n_ok < 3) { rc = fail("pfilter: fewer than 3 particles under the quantile"); break; }
+        int64_t nreps = 0, n_pend = n_bad;
+        for (int r = 0; n_pend > 0; ++r) {
+            if (r >= PF_MAX_ROUNDS) { rc = fail("pfilter: rejection loop does not terminate"); break; }
+            round += 1;
+            nreps += n_pend; /* ref :313 localreps: every attempt counts */
+            int64_t gev = 0;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : gev)
+            for (int64_t w = 0; w < n_pend; ++w) {
+                const int64_t i = pend[w];
+                stream_t st;
+                stream_init(&st, seed, ST_PROPOSE, (uint32_t)i, round);
+                int64_t b = (int64_t)kor_index(next_u32(&st), (uint32_t)n_ok), c = b, e;
+                while (c == b) c = (int64_t)kor_index(next_u32(&st), (uint32_t)n_ok);
+                e = b;
+                while (e == b || e == c) e = (int64_t)kor_index(next_u32(&st), (uint32_t)n_ok);
+                b = idxok[b]; c = idxok[c]; e = idxok[e];
+                const double sc = next_normal(&st) * cfg->proposal_width; /* ref :312 */
+                double p[16], pq[16];
+                for (int k = 0; k < d; ++k)
+                    p[k] = th[(int64_t)k * N + b] + (th[(int64_t)k * N + e] - th[(int64_t)k * N + c]) * sc;
+                kor_push_p(prior, d, p, pq);
+                const double ll = kor_prior_logpdf(prior, d, pq);
+                pend2[w] = i; /* still pending unless accepted below */
+                if (kor_log(next_uniform(&st)) > fmin(0.0, ll - lp[i])) continue;
+                const double Cp = cost_dispatch(model, seed, ST_COST, d, p, (uint32_t)i, round);
+                gev += 1;
+                if (Cp > eps || Cp != Cp) continue;
+                C[i] = Cp;
+                for (int k = 0; k < d; ++k) th[(int64_t)k * N + i] = p[k];
+                lp[i] = ll;
+                pend2[w] = -1;
+            }
+            evals += gev;
+            int64_t m = 0;
+            for (int64_t w = 0; w < n_pend; ++w)
+                if (pend2[w] >= 0) pend[m++] = pend2[w];
+            n_pend = m;
+        }
+        if (rc) break;
+        reps_total += nreps;
+        /* ref :331-335; an iteration without bad particles (eff = 0/0 in the reference, which then never leaves the
+         * loop) ends the run here */
+        if (n_bad == 0) break;
+        const double eff = (double)n_bad / (double)nreps;
+        if (eff < cfg->eff_tol) break;
+        if (eps < cfg->epstol) break;
+        if (cfg->max_iters > 0 && iters > cfg->max_iters) break;
+    }
+    if (!rc) {
+        for (int64_t i = 0; i < N; ++i) {
+            double x[16], xp[16];
+            for (int k = 0; k < d; ++k) x[k] = th[(int64_t)k * N + i];
+            kor_push_p(prior, d, x, xp);
+            for (int k = 0; k < d; ++k) theta_out[(int64_t)k * N + i] = xp[k];
+            cost_out[i] = C[i];
+        }
+        if (eps_out) *eps_out = eps;
+        if (iters_out) *iters_out = iters;
+        if (nreps_out) *nreps_out = reps_total;
+        if (cost_evals) *cost_evals = evals;
+    }
+    free(th); free(lp); free(C); free(idxok); free(pend); free(pend2); free(kv); free(srt);
+    return rc;
+}

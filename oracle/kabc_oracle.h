@@ -167,6 +167,35 @@ void kor_ais_get_counters(const kor_ais_t *s, int64_t *cost_evals, int64_t *acce
 void kor_ais_get_trace(const kor_ais_t *s, uint8_t *move, int64_t *a, int64_t *b, int64_t *c, double *corr,
                        double *theta_p_soa, double *lp_p, double *ll_p, double *e, uint8_t *decision);
 
+/* ---- ABCDE: src/smc.jl:352-428 (population Monte Carlo with differential-evolution moves, Jacobi update) ---- */
+typedef struct {
+    int64_t nparticles;    /* 50 */
+    int64_t generations;   /* 20 */
+    double eps_target;
+    double alpha;          /* 0 <= alpha < 1 */
+    double proposal_width; /* 1.0 */
+    int32_t earlystop;     /* false */
+    int32_t _pad;
+} kor_abcde_config_t;
+/* theta_out: d x N SoA of push_p'ed particles; cost_out: N; returns 0 or 1 (error text in kor_last_error) */
+int kor_abcde_run(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model, const kor_abcde_config_t *cfg,
+                  int nthreads, double *theta_out, double *cost_out, int32_t *reached, int64_t *nsim, int64_t *generations_done);
+
+/* ---- pfilter: src/smc.jl:275-345 (quantile filter, bad particles redrawn from the good ones until they pass) ---- */
+typedef struct {
+    int64_t nparticles;
+    double q;              /* 0.7 */
+    double eff_tol;        /* 0.1 */
+    double epstol;         /* -Inf */
+    double proposal_width; /* 0.75 */
+    int64_t max_iters;     /* 0 = Inf */
+} kor_pfilter_config_t;
+/* ref :276-279: N is raised to ceil((4d+1)/q) when N*q <= 4d */
+int64_t kor_pfilter_nparticles(int64_t n, int d, double q);
+int kor_pfilter_run(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model, const kor_pfilter_config_t *cfg,
+                    int nthreads, double *theta_out, double *cost_out, double *eps_out, int64_t *iters, int64_t *nreps,
+                    int64_t *cost_evals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,16 @@ class AisConfig(C.Structure):
                 ("scale", C.c_double), ("posterior", C.c_int32), ("_pad", C.c_int32)]
 
 
+class AbcdeConfig(C.Structure):
+    _fields_ = [("nparticles", C.c_int64), ("generations", C.c_int64), ("eps_target", C.c_double), ("alpha", C.c_double),
+                ("proposal_width", C.c_double), ("earlystop", C.c_int32), ("_pad", C.c_int32)]
+
+
+class PfilterConfig(C.Structure):
+    _fields_ = [("nparticles", C.c_int64), ("q", C.c_double), ("eff_tol", C.c_double), ("epstol", C.c_double),
+                ("proposal_width", C.c_double), ("max_iters", C.c_int64)]
+
+
 class SmcLog(C.Structure):
     _fields_ = [("iteration", C.c_int64), ("eps", C.c_double), ("n_alive", C.c_int64), ("flag", C.c_int32),
                 ("resampled", C.c_int32), ("accepted", C.c_int64), ("cost_evals", C.c_int64),
@@ -128,6 +138,12 @@ def lib():
     L.kor_smc_get_log.argtypes = [vp, C.POINTER(SmcLog), C.c_int64]
     L.kor_smc_get_log.restype = C.c_int64
     L.kor_smc_get_trace.argtypes = [vp, i64p, i64p, dp, dp, dp, dp, u8p, dp]
+    L.kor_abcde_run.argtypes = [C.c_uint64, C.POINTER(Prior), C.c_int, C.POINTER(Model), C.POINTER(AbcdeConfig), C.c_int, dp, dp,
+                                C.POINTER(C.c_int32), i64p, i64p]
+    L.kor_pfilter_nparticles.argtypes = [C.c_int64, C.c_int, C.c_double]
+    L.kor_pfilter_nparticles.restype = C.c_int64
+    L.kor_pfilter_run.argtypes = [C.c_uint64, C.POINTER(Prior), C.c_int, C.POINTER(Model), C.POINTER(PfilterConfig), C.c_int, dp, dp,
+                                  dp, i64p, i64p, i64p]
     L.kor_ais_create.argtypes = [C.c_uint64, C.POINTER(Prior), C.c_int, C.POINTER(Model), C.POINTER(AisConfig), C.c_int, C.POINTER(vp)]
     L.kor_ais_destroy.argtypes = [vp]
     L.kor_ais_init.argtypes = [vp]
@@ -207,6 +223,32 @@ def ais_config(nwalkers, nsamples, ntransitions=1, discard_initial=0, thinning=1
                posterior=0):
     return AisConfig(int(nwalkers), int(nsamples), int(ntransitions), int(discard_initial), int(thinning),
                      int(retry_sampling), float(scale), int(posterior), 0)
+
+
+def abcde(seed, priors, model, eps_target, nparticles=50, generations=20, alpha=0.0, earlystop=False, proposal_width=1.0,
+          nthreads=1):
+    """ref src/smc.jl:352 ABCDE(prior, cost, eps_target; nparticles=50, generations=20, alpha=0, earlystop=false, ...)."""
+    d, N = len(priors), int(nparticles)
+    cfg = AbcdeConfig(N, int(generations), float(eps_target), float(alpha), float(proposal_width), int(bool(earlystop)), 0)
+    th, cost = np.empty((d, N)), np.empty(N)
+    reached, nsim, gens = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+    if lib().kor_abcde_run(seed, priors, d, C.byref(model), C.byref(cfg), nthreads, _dp(th), _dp(cost), C.byref(reached),
+                           C.byref(nsim), C.byref(gens)):
+        raise OracleError(lib().kor_last_error().decode())
+    return dict(theta=th, C=cost, reached=bool(reached.value), nsim=nsim.value, generations=gens.value)
+
+
+def pfilter(seed, priors, model, nparticles, q=0.7, eff_tol=0.1, epstol=-np.inf, max_iters=0, proposal_width=0.75, nthreads=1):
+    """ref src/smc.jl:275 pfilter(prior, cost, N; q=0.7, eff_tol=0.1, epstol=-Inf, max_iters=Inf, proposal_width=0.75)."""
+    d = len(priors)
+    N = int(lib().kor_pfilter_nparticles(int(nparticles), d, float(q)))
+    cfg = PfilterConfig(int(nparticles), float(q), float(eff_tol), float(epstol), float(proposal_width), int(max_iters))
+    th, cost = np.empty((d, N)), np.empty(N)
+    eps, iters, nreps, evals = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    if lib().kor_pfilter_run(seed, priors, d, C.byref(model), C.byref(cfg), nthreads, _dp(th), _dp(cost), C.byref(eps),
+                             C.byref(iters), C.byref(nreps), C.byref(evals)):
+        raise OracleError(lib().kor_last_error().decode())
+    return dict(theta=th, C=cost, eps=eps.value, iterations=iters.value, nreps=nreps.value, cost_evals=evals.value)
 
 
 def philox(ctr, key):

@@ -3,7 +3,7 @@
 set -x
 python bench.py > gpurun_out/BENCH_normal_smc.json 2> gpurun_out/BENCH_normal_smc.err; cat gpurun_out/BENCH_normal_smc.json
 for w in ma2_smc lv_smc gk_ais; do
-  timeout 900 python bench.py --workload $w --steps 30 --warmup 3 > gpurun_out/BENCH_$w.json 2>/dev/null
+  timeout 900 python bench.py --workload $w --steps 30 --warmup 3 $EXTRA_BENCH_FLAGS > gpurun_out/BENCH_$w.json 2>/dev/null
 done
 python bench.py --precision f64 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/BENCH_normal_smc_f64.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file gpurun_out/launches_final.csv \

@@ -92,6 +92,21 @@ def test_added_laws_and_socks_match_golden(kabc, ctx, golden):
     assert cnt["cost_evals"] == golden["ais_socks_50"]["counters"]["cost_evals"]
 
 
+def test_abcde_pfilter_match_golden(kabc, ctx, golden):
+    prior, cost = kabc.workloads.normal("f64", 100)
+    r = kabc.ABCDE(prior, cost, 0.05, nparticles=300, generations=25, alpha=0.3, ctx=ctx)
+    g = golden["abcde_normal_300"]
+    assert [float(x).hex() for x in np.vstack([p.particles for p in r.P]).ravel()] == g["theta"]
+    assert [float(x).hex() for x in r.C.particles] == g["C"] and r.nsim == g["nsim"] and r.reached_eps == g["reached"]
+    R = -30.0 ** 2 / (30.0 - 15.0 ** 2)
+    pri = kabc.Factored(kabc.NegativeBinomial(R, R / (30.0 + R)), kabc.Beta(15, 2))
+    f = kabc.pfilter(pri, kabc.Socks((0, 11), 11), 400, max_iters=4, ctx=ctx)
+    g = golden["pfilter_socks_400"]
+    assert [float(x).hex() for x in np.vstack([p.particles for p in f.P]).ravel()] == g["theta"]
+    assert [float(x).hex() for x in f.C.particles] == g["C"] and float(f.eps).hex() == g["eps"]
+    assert (f.nreps, f.iterations, f.cost_evals) == (g["nreps"], g["iterations"], g["cost_evals"])
+
+
 def test_select_handles_ties_and_infinities(kabc, ctx):
     """bucket select edge cases: all-equal costs (slow path), many +Inf, tiny populations."""
     # deterministic cost |theta - 1.5| with a 2-point-like prior -> massive ties after resampling

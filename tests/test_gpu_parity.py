@@ -415,6 +415,67 @@ def test_normal_times_discrete_uniform_inference(kabc, ctx):
     assert sim.approx(5.5) and abs(sim.mean() - 5.5) < 0.05
 
 
+# ------------------------------------------------------------------ ABCDE / pfilter (ref src/smc.jl:275-428)
+@pytest.mark.parametrize("name,N,kw", [
+    ("normal", 300, dict(eps_target=0.05, generations=25, alpha=0.3)),            # one-CTA sort
+    ("normal", 5000, dict(eps_target=0.05, generations=12)),                      # multi-pass sort
+    ("ma2", 1000, dict(eps_target=0.2, generations=15, alpha=0.5, earlystop=True)),
+    ("noisyprod", 500, dict(eps_target=0.05, generations=40, earlystop=True, proposal_width=0.8)),   # discrete component
+    ("noisyprod", 300, dict(eps_target=0.5, generations=80, earlystop=True)),     # earlystop ends the run at generation 35
+    ("gk", 64, dict(eps_target=1.0, generations=4)),                              # block-per-particle simulator
+])
+def test_abcde_f64_bit_exact(oracle, kabc, ctx, name, N, kw):
+    """Whole ABCDE runs: particles, costs, nsim, generation count and the convergence flag equal the oracle's."""
+    M = models(oracle, kabc)[name]
+    nd = {"normal": 100, "gk": 1000}.get(name)
+    mk = {} if nd is None else {"n": nd}
+    ref = oracle.abcde(SEED, oracle.make_priors(M["ospec"]), M["omodel"](**mk), nparticles=N, nthreads=8, **kw)
+    kw2 = dict(kw)
+    eps_target = kw2.pop("eps_target")
+    dev = kabc.ABCDE(M["kprior"](), M["kcost"]("f64", **mk), eps_target, nparticles=N, ctx=ctx, **kw2)
+    P = dev.P if isinstance(dev.P, list) else [dev.P]
+    assert_bits_equal(np.vstack([p.particles for p in P]), ref["theta"], f"ABCDE {name}: particles")
+    assert_bits_equal(dev.C.particles, ref["C"], f"ABCDE {name}: costs")
+    assert dev.nsim == ref["nsim"] and dev.generations == ref["generations"] and dev.reached_eps == ref["reached"]
+    assert ref["nsim"] > 0
+
+
+@pytest.mark.parametrize("name,N,kw", [
+    ("normal", 1000, dict()),
+    ("normal", 6000, dict(q=0.5, max_iters=6)),
+    ("socks", 600, dict(max_iters=4)),
+    ("noisyprod", 400, dict(epstol=0.05, proposal_width=0.5)),
+    ("ma2", 3, dict(max_iters=3)),                                                # particle count raised to 13 (ref :276-279)
+])
+def test_pfilter_f64_bit_exact(oracle, kabc, ctx, name, N, kw):
+    M = models(oracle, kabc)[name]
+    mk = {"n": 100} if name == "normal" else {}
+    ref = oracle.pfilter(SEED, oracle.make_priors(M["ospec"]), M["omodel"](**mk), N, nthreads=8, **kw)
+    dev = kabc.pfilter(M["kprior"](), M["kcost"]("f64", **mk), N, ctx=ctx, **kw)
+    P = dev.P if isinstance(dev.P, list) else [dev.P]
+    assert_bits_equal(np.vstack([p.particles for p in P]), ref["theta"], f"pfilter {name}: particles")
+    assert_bits_equal(dev.C.particles, ref["C"], f"pfilter {name}: costs")
+    assert bits(np.array([dev.eps]))[0] == bits(np.array([ref["eps"]]))[0]
+    assert (dev.iterations, dev.nreps, dev.cost_evals) == (ref["iterations"], ref["nreps"], ref["cost_evals"])
+    assert (dev.C.particles <= dev.eps).all()
+
+
+def test_abcde_pfilter_reference_style(kabc, ctx):
+    """The cost of test/runtests.jl:77-86 and the README model through the two other samplers; argument errors."""
+    pri = kabc.Normal(1, 0.2)
+    r = kabc.ABCDE(pri, kabc.Deterministic(0, 1.5), 0.01, nparticles=200, generations=60, ctx=ctx)
+    assert r.reached_eps and r.P.approx(0.707) and (r.C.particles <= 0.01).all()
+    f = kabc.pfilter(pri, kabc.Deterministic(0, 1.5), 500, epstol=0.01, ctx=ctx)
+    assert f.eps < 0.01 and f.P.approx(0.707)
+    prior, cost = kabc.workloads.normal("f32", 1000)
+    f = kabc.pfilter(prior, cost, 20000, ctx=ctx)
+    assert abs(f.P[0].mean() - 2.0) < 0.005 and abs(f.P[1].mean() - 0.04) < 0.003
+    with pytest.raises(kabc.KissABCError, match="must be in 0 <="):
+        kabc.ABCDE(pri, kabc.Deterministic(0, 1.5), 0.01, alpha=1.0, ctx=ctx)
+    with pytest.raises(kabc.KissABCError):
+        kabc.pfilter(pri, kabc.Deterministic(0, 1.5), 100, q=0.0, ctx=ctx)
+
+
 def test_ais_errors(kabc, ctx):
     prior = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100))
     post = kabc.ApproxKernelizedPosterior(prior, kabc.NormalMeanStd(), 0.005)

@@ -528,6 +528,65 @@ def test_ais_hard_threshold_issue10(oracle):
     assert abs(out.mean() - 1.5) / out.std(ddof=1) < 2 and (np.abs(out - 1.5) <= 0.01).all()
 
 
+# ------------------------------------------------------------------ ABCDE / pfilter (ref src/smc.jl:275-428)
+def test_abcde_normal_to_dirac_and_invariants(oracle):
+    """ref src/smc.jl:352-428 on the cost of test/runtests.jl:77-86 (|mu^2+1-1.5|, prior Normal(1,0.2))."""
+    pri = oracle.make_priors([("normal", 1, 0.2)])
+    m = oracle.make_model(oracle.DETERMINISTIC, 0, (1.5,), (0.0,))
+    r = oracle.abcde(SEED, pri, m, 0.01, nparticles=200, generations=60)
+    assert r["reached"] and (r["C"] <= 0.01).all() and r["generations"] == 60
+    assert abs(r["theta"].mean() - 0.7071) < 0.005 and 0 < r["nsim"] <= 200 * 60
+    e = oracle.abcde(SEED, pri, m, 0.01, nparticles=200, generations=600, earlystop=True)
+    assert e["reached"] and e["generations"] < 100 and e["nsim"] < r["nsim"]
+    n0 = oracle.abcde(SEED, pri, m, 0.01, nparticles=200, generations=0)          # generations = 0: the prior sample
+    assert n0["nsim"] == 0 and not n0["reached"] and abs(n0["theta"].mean() - 1.0) < 0.05
+    a = oracle.abcde(SEED, pri, m, 0.01, nparticles=200, generations=60, alpha=0.5)
+    assert a["reached"] and (a["theta"] != r["theta"]).any()
+    with pytest.raises(oracle.OracleError, match="must be in 0 <="):              # ref :353 @assert
+        oracle.abcde(SEED, pri, m, 0.01, alpha=1.0)
+
+
+def test_abcde_and_pfilter_readme_posterior(oracle):
+    """README.md:35-66 model through the two other samplers: posterior around mu = 2, sigma = 0.04."""
+    M = models(oracle, None)["normal"]
+    r = oracle.abcde(SEED, oracle.make_priors(M["ospec"]), M["omodel"](1000), 0.02, nparticles=300, generations=150, alpha=0.5,
+                     nthreads=8)
+    assert r["reached"] and abs(r["theta"][0].mean() - 2.0) < 0.01 and abs(r["theta"][1].mean() - 0.04) < 0.004
+    f = oracle.pfilter(SEED, oracle.make_priors(M["ospec"]), M["omodel"](1000), 500, nthreads=8)
+    assert abs(f["theta"][0].mean() - 2.0) < 0.01 and abs(f["theta"][1].mean() - 0.04) < 0.004
+    assert (f["C"] <= f["eps"]).all() and f["iterations"] >= 5 and f["nreps"] >= f["iterations"]
+
+
+def test_pfilter_semantics(oracle):
+    """ref src/smc.jl:275-345: particle-count floor, stop rules, discrete prior through push_p."""
+    L = oracle.lib()
+    assert L.kor_pfilter_nparticles(5, 2, 0.7) == 13 and L.kor_pfilter_nparticles(100, 2, 0.7) == 100   # ref :276-279
+    assert L.kor_pfilter_nparticles(8, 2, 1.0) == 9
+    pri = oracle.make_priors([("normal", 1, 0.2)])
+    m = oracle.make_model(oracle.DETERMINISTIC, 0, (1.5,), (0.0,))
+    r = oracle.pfilter(SEED, pri, m, 500, epstol=0.01)
+    assert r["eps"] < 0.01 and (r["C"] <= r["eps"]).all() and abs(r["theta"].mean() - 0.7071) < 0.005   # ref :333
+    one = oracle.pfilter(SEED, pri, m, 500, max_iters=1)                                                 # ref :334 iters > max_iters
+    assert one["iterations"] == 2
+    tiny = oracle.pfilter(SEED, pri, m, 2)
+    assert tiny["theta"].shape == (1, 8)
+    S = models(oracle, None)["socks"]
+    f = oracle.pfilter(SEED, oracle.make_priors(S["ospec"]), S["omodel"](), 1000, max_iters=3, nthreads=8)
+    assert (f["theta"][0] == np.rint(f["theta"][0])).all() and (f["C"] <= f["eps"]).all()
+
+
+def test_abcde_pfilter_match_golden(oracle, golden):
+    M = models(oracle, None)
+    g = golden["abcde_normal_300"]
+    r = oracle.abcde(SEED, oracle.make_priors(M["normal"]["ospec"]), M["normal"]["omodel"](100), 0.05, nparticles=300,
+                     generations=25, alpha=0.3)
+    assert [float(x).hex() for x in r["theta"].ravel()] == g["theta"] and r["nsim"] == g["nsim"]
+    g = golden["pfilter_socks_400"]
+    f = oracle.pfilter(SEED, oracle.make_priors(M["socks"]["ospec"]), M["socks"]["omodel"](), 400, max_iters=4)
+    assert [float(x).hex() for x in f["theta"].ravel()] == g["theta"] and f["nreps"] == g["nreps"]
+    assert float(f["eps"]).hex() == g["eps"]
+
+
 def test_ais_errors(oracle):
     M = models(oracle, None)["normal"]
     with pytest.raises(oracle.OracleError, match="is insufficient"):
