@@ -116,5 +116,41 @@ function sample(model::KissABC.ApproxPosterior{<:Any,<:DeviceCost}, spl::AIS, Ns
     bundle(out)
 end
 
+# ---- ABCDE / pfilter, ref src/smc.jl:275-428
+struct KabcAbcdeConfig
+    nparticles::Int64; generations::Int64; eps_target::Float64; alpha::Float64; proposal_width::Float64
+    earlystop::Int32; _pad::Int32
+end
+struct KabcPfilterConfig
+    nparticles::Int64; q::Float64; eff_tol::Float64; epstol::Float64; proposal_width::Float64; max_iters::Int64
+end
+
+function KissABC.ABCDE(prior::Distribution, cost::DeviceCost, ϵ_target; nparticles=50, generations=20, α=0, parallel=false,
+                       earlystop=false, verbose=true, proposal_width=1.0, context::Context=ctx())
+    pr = pods(prior); d = length(pr); N = nparticles
+    cfg = KabcAbcdeConfig(N, generations, ϵ_target, α, proposal_width, earlystop, 0)
+    θ = Matrix{Float64}(undef, N, d); Δ = Vector{Float64}(undef, N)
+    reached = Ref{Int32}(0); nsim = Ref{Int64}(0); gens = Ref{Int64}(0)
+    check(ccall((:kabc_abcde_run, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{KabcPrior}, Cint, Ref{KabcModel}, Ref{KabcAbcdeConfig}, Ptr{Float64}, Ptr{Float64},
+                 Ref{Int32}, Ref{Int64}, Ref{Int64}),
+                context.h, pr, d, pod(cost), cfg, θ, Δ, reached, nsim, gens))
+    (P=bundle(θ), C=Particles(Δ), reached_ϵ=reached[] != 0)
+end
+
+function KissABC.pfilter(prior::Distribution, cost::DeviceCost, N; q=0.7, eff_tol=0.1, epstol=-Inf, max_iters=Inf,
+                         proposal_width=0.75, verbose=false, parallel=false, context::Context=ctx())
+    pr = pods(prior); d = length(pr)
+    n = ccall((:kabc_pfilter_nparticles, LIB), Int64, (Int64, Cint, Float64), N, d, q)
+    cfg = KabcPfilterConfig(N, q, eff_tol, epstol, proposal_width, isinf(max_iters) ? 0 : Int64(max_iters))
+    θ = Matrix{Float64}(undef, n, d); C = Vector{Float64}(undef, n)
+    ϵ = Ref(0.0); it = Ref{Int64}(0); reps = Ref{Int64}(0); ev = Ref{Int64}(0)
+    check(ccall((:kabc_pfilter_run, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{KabcPrior}, Cint, Ref{KabcModel}, Ref{KabcPfilterConfig}, Ptr{Float64}, Ptr{Float64},
+                 Ref{Float64}, Ref{Int64}, Ref{Int64}, Ref{Int64}),
+                context.h, pr, d, pod(cost), cfg, θ, C, ϵ, it, reps, ev))
+    (P=bundle(θ), C=Particles(C))
+end
+
 export DeviceCost, NormalMeanStd, MA2, GandK, LotkaVolterra, Socks, NoisyProduct, Context
 end # module
