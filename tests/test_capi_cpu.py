@@ -39,8 +39,10 @@ def test_pod_layouts_match_header(kabc):
     K = kabc._capi
     assert C.sizeof(K.PriorT) == 40 and C.sizeof(K.ModelT) == 16 + 32 * 8 + 8 * 8
     assert C.sizeof(K.SmcConfigT) == 72 and C.sizeof(K.AisConfigT) == 64 and C.sizeof(K.SmcLogT) == 56
+    assert C.sizeof(K.AbcdeConfigT) == 48 and C.sizeof(K.PfilterConfigT) == 48
     from oracle import oracle as O
-    for a, b in [(K.PriorT, O.Prior), (K.ModelT, O.Model), (K.SmcConfigT, O.SmcConfig), (K.AisConfigT, O.AisConfig), (K.SmcLogT, O.SmcLog)]:
+    for a, b in [(K.PriorT, O.Prior), (K.ModelT, O.Model), (K.SmcConfigT, O.SmcConfig), (K.AisConfigT, O.AisConfig), (K.SmcLogT, O.SmcLog),
+                 (K.AbcdeConfigT, O.AbcdeConfig), (K.PfilterConfigT, O.PfilterConfig)]:
         assert [(n, t) for n, t in a._fields_] == [(n, t) for n, t in b._fields_]
 
 
@@ -53,6 +55,11 @@ def test_host_mirror_defaults_and_validation(kabc):
     assert len(pri) == 2
     pods = pri._pods()
     assert (pods[0].kind, pods[0].p0, pods[0].p1) == (0, 1.0, 3.0) and (pods[1].kind, pods[1].lo, pods[1].hi) == (2, 0.0, 100.0)
+    # the laws and simulators added for the reference's integration tests (test/runtests.jl:46-56, :105-112)
+    dp = kabc.Factored(kabc.NegativeBinomial(4.5, 0.13), kabc.Beta(15, 2), kabc.DiscreteUniform(1, 10))._pods()
+    assert [(q.kind, q.p0, q.p1) for q in dp] == [(4, 4.5, 0.13), (3, 15.0, 2.0), (5, 1.0, 10.0)]
+    sm, nm = kabc.Socks((0, 11), 11)._pod(), kabc.NoisyProduct(5.5, 0.01)._pod()
+    assert (sm.kind, sm.n_target, sm.param[0]) == (5, 2, 11.0) and (nm.kind, nm.param[0], nm.param[1]) == (4, 2.0, 0.01)
     with pytest.raises(kabc.KissABCError):
         kabc.Factored()
     with pytest.raises(kabc.KissABCError):
