@@ -196,6 +196,23 @@ __device__ __forceinline__ void normal_pair32(uint32_t w0, uint32_t w1, float &z
     z1 = __fmul_rn(r, mufu_sin(ang));
 }
 
+// The normal model only needs sum(z) and sum(z^2) of its draws, and for a Box-Muller pair both follow from the pair's
+// polar form without forming z0, z1:  z0 + z1 = r (cos t + sin t) = sqrt(2) r sin(t + pi/4),  z0^2 + z1^2 = r^2 = -2 ln u1.
+// With s = sqrt(-lg2 u1): z0 + z1 = 2 sqrt(ln 2) * s sin(t + pi/4) and z0^2 + z1^2 = -2 ln 2 * lg2 u1, so a pair costs
+// three MUFU (lg2, sqrt, sin) + one FFMA + one FADD instead of four MUFU + 2 FMUL + 2 FADD + 2 FFMA + 1 FMUL; the constant
+// factors are applied once per particle in FP64.  Same Philox words, same u1 / u2 as normal_pair32.
+__device__ __forceinline__ void normal_pair_sums32(uint32_t w0, uint32_t w1, float &acc_s_sin, float &acc_lg2) {
+    const float u1 = __fmaf_rn(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    // angle 2 pi u2 + pi/4 from the top 23 bits of w1 placed in the mantissa of a float in [1,2) (two ALU operations;
+    // an I2F would go to the XU pipe, which the three MUFU of the pair already load as much as Philox loads IMAD.WIDE):
+    // f = 1 + floor(w1 / 2^9) 2^-23, ang = 2 pi (f - 1 + 2^-24) + pi/4, |u2 - (w1 + 0.5) 2^-32| < 2^-24
+    const float f = __uint_as_float((w1 >> 9) | 0x3f800000u);
+    const float ang = __fmaf_rn(f, 6.2831853071795865f, -5.4977867692f);
+    const float l = mufu_lg2(u1);
+    acc_s_sin = __fmaf_rn(mufu_sqrt(-l), mufu_sin(ang), acc_s_sin);
+    acc_lg2 = __fadd_rn(acc_lg2, l);
+}
+
 // log Gamma(x), x > 0 (part of the variate spec): recurrence up to x >= 10, then the Stirling series through x^-13
 static __constant__ double KC_LGAMMA[7] = {1.0 / 156.0, -691.0 / 360360.0, 1.0 / 1188.0, -1.0 / 1680.0, 1.0 / 1260.0,
                                            -1.0 / 360.0, 1.0 / 12.0};

@@ -59,12 +59,13 @@ __device__ __forceinline__ double cost_normal_f64(const DModel &m, const RoundKe
 
 // FP32 draws.  mean(x) = mu + sigma*mean(z) and std(x) = sigma*std(z) exactly (x = mu + sigma*z), so the kernel
 // accumulates the one-pass sums of z and z^2 in FP32 (well conditioned: z is centred, unit scale) and applies mu and
-// sigma once, in FP64, at the end.
+// sigma once, in FP64, at the end.  Full Philox blocks go through the pair-sum identities of normal_pair_sums32.
 __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
                                                   uint32_t epoch, double mu, double sigma) {
     const int n = m.n_draws;
     const int nbf = n >> 2; // full blocks
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float ps[2] = {0.f, 0.f}, pl[2] = {0.f, 0.f}; // full blocks: pair sums of s sin(t + pi/4) and of lg2(u1)
 #ifndef KABC_NORMAL_UNROLL
 #define KABC_NORMAL_UNROLL 4
 #endif
@@ -74,14 +75,8 @@ __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKe
     for (int b = 0; b < nbf; ++b) {
         uint32_t w0, w1, w2, w3;
         philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);
-        float z[4];
-        normal_pair32(w0, w1, z[0], z[1]);
-        normal_pair32(w2, w3, z[2], z[3]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            s1[q] = __fadd_rn(s1[q], z[q]);
-            s2[q] = __fmaf_rn(z[q], z[q], s2[q]);
-        }
+        normal_pair_sums32(w0, w1, ps[0], pl[0]);
+        normal_pair_sums32(w2, w3, ps[1], pl[1]);
     }
     if (n & 3) {
         uint32_t w0, w1, w2, w3;
@@ -96,8 +91,11 @@ __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKe
                 s2[q] = __fmaf_rn(z[q], z[q], s2[q]);
             }
     }
-    const double S1 = ((double)s1[0] + (double)s1[1]) + ((double)s1[2] + (double)s1[3]);
-    const double S2 = ((double)s2[0] + (double)s2[1]) + ((double)s2[2] + (double)s2[3]);
+    // sum z = 2 sqrt(ln 2) * sum(s sin),  sum z^2 = -2 ln 2 * sum(lg2 u1)   (+ the draws of the partial last block)
+    const double S1 = 1.6651092223153954 * ((double)ps[0] + (double)ps[1]) +
+                      (((double)s1[0] + (double)s1[1]) + ((double)s1[2] + (double)s1[3]));
+    const double S2 = -1.3862943611198906 * ((double)pl[0] + (double)pl[1]) +
+                      (((double)s2[0] + (double)s2[1]) + ((double)s2[2] + (double)s2[3]));
     const double dn = (double)n;
     const double mean = mu + sigma * (S1 / dn);
     double var = (S2 - S1 * S1 / dn) / (double)(n - 1);
