@@ -15,12 +15,13 @@ def main():
     import kissabc_jl_b200 as k
     from common import SEED
     out_dir, name, prec, N, iters = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
+    retrys = int(sys.argv[6]) if len(sys.argv) > 6 else 1
     rank, world, local = k.dist.env_rank_world()
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = k.dist.make_context(SEED)
     prior, cost = k.workloads.WORKLOADS[name](prec) if name != "normal_small" else k.workloads.normal(prec, 100)
-    s = k.SmcSession(ctx, prior, cost, k.smc_config(nparticles=N, alpha=0.9, min_r_ess=0.7, mcmc_retrys=1, mcmc_tol=0.3, max_iterations=iters))
+    s = k.SmcSession(ctx, prior, cost, k.smc_config(nparticles=N, alpha=0.9, min_r_ess=0.7, mcmc_retrys=retrys, mcmc_tol=0.3, max_iterations=iters))
     s.init()
     stops = []
     for _ in range(iters):
