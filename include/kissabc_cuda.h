@@ -36,7 +36,9 @@ enum kabc_status {
     KABC_ERR_NCCL = 3,
     KABC_ERR_RETRY_BUDGET = 4, /* "Prior leads to inf costs too often", src/KissABC.jl:58-59 */
     KABC_ERR_DEGENERATE = 5,   /* no alive particles left to resample (Julia would throw at src/smc.jl:147) */
-    KABC_ERR_STATE = 6         /* handle used out of order */
+    KABC_ERR_STATE = 6,        /* handle used out of order; also the reference's "starting sample invalid" / "ld_correction is
+                                  invalid" errors of accept (src/types.jl:69-70) */
+    KABC_ERR_PEER = 7          /* a rank of the job did not reach a cross-rank barrier in time (peer memory, multi GPU) */
 };
 
 /* ---- prior: Factored(Uniform(a,b), Normal(mu,sigma), Truncated(Normal(mu,sigma),lo,hi), Beta(a,b),
@@ -146,7 +148,20 @@ int kabc_nccl_unique_id(char id[KABC_NCCL_ID_BYTES]); /* rank 0 creates, the hos
 int kabc_ctx_create(int device, uint64_t seed, kabc_ctx_t **ctx);
 int kabc_ctx_create_dist(int device, uint64_t seed, int rank, int world, const char id[KABC_NCCL_ID_BYTES],
                          kabc_ctx_t **ctx);
-int kabc_ctx_destroy(kabc_ctx_t *ctx);
+/* Multi-rank jobs (one process per GPU) synchronise and exchange rows through a PEER ARENA: one device allocation per rank,
+ * mapped into every other rank with cudaIpc (NVLink peer memory) and kept for the life of the context.  A context made by
+ * kabc_ctx_create_dist sizes, exchanges and maps its arena by itself (the 64-byte handles travel through its NCCL
+ * communicator; NCCL is not used on the data path).  kabc_ctx_create_ranks makes a rank of a job WITHOUT NCCL -- e.g. several
+ * ranks sharing one GPU, which NCCL refuses -- and leaves the exchange to the host: every rank calls
+ * kabc_ctx_arena_export(bytes), the host all-gathers the handles (MPI, torch.distributed, Distributed.jl, ...) and every rank
+ * calls kabc_ctx_arena_attach with the world x 64 bytes in rank order.  bytes: kabc_smc_arena_bytes / kabc_ais_arena_bytes. */
+#define KABC_IPC_HANDLE_BYTES 64
+int kabc_ctx_create_ranks(int device, uint64_t seed, int rank, int world, kabc_ctx_t **ctx);
+int kabc_ctx_arena_export(kabc_ctx_t *ctx, uint64_t bytes, char handle[KABC_IPC_HANDLE_BYTES]);
+int kabc_ctx_arena_attach(kabc_ctx_t *ctx, const char *handles /* world x KABC_IPC_HANDLE_BYTES */);
+uint64_t kabc_smc_arena_bytes(int64_t nparticles, int d, int world);
+uint64_t kabc_ais_arena_bytes(int64_t nwalkers, int d, int world);
+int kabc_ctx_destroy(kabc_ctx_t *ctx); /* KABC_ERR_STATE while smc / ais handles of the context are alive */
 int kabc_ctx_info(const kabc_ctx_t *ctx, int *device, int *rank, int *world, int *sm_count);
 
 /* ---- priors on device: logpdf(Factored, x) src/priors.jl:30-36; rand(rng, Factored) src/priors.jl:42-43 ---- */
@@ -184,8 +199,11 @@ int kabc_smc_get_scalars(kabc_smc_t *smc, double *eps, int32_t *flag, int64_t *i
                          int64_t *accepted, int64_t *cost_evals, int64_t *next_epoch, int64_t *events);
 int64_t kabc_smc_get_log(kabc_smc_t *smc, kabc_smc_log_t *log, int64_t cap);
 int64_t kabc_smc_kernel_launches(kabc_smc_t *smc);
+/* benchmark helper: n bodies enqueued back to back (stop rules ignored), each preceded by a flush of the L2 cache
+ * (a device memset of flush_bytes, outside the timed region); out_ms[i] = device time of body i between two events */
+int kabc_smc_bench_steps(kabc_smc_t *smc, int n, uint64_t flush_bytes, float *out_ms);
 /* one iteration with CUDA events between its kernels: warm per-kernel times in microseconds, in launch order
- * (hist0, hist1, final, cut, scatter, gather+propose, simulate [, barrier+post]) */
+ * (select x3, cut, table, sweep -- or table, propose, simulate for the work-list simulators) */
 int kabc_smc_profile_iteration(kabc_smc_t *smc, float *out_us, int cap, int *out_n);
 /* replay hooks: record, for the next sweeps, the variates and decisions each particle used so that the CPU
  * oracle can replay them through the reference logic (north_star "Philox uniforms replayed").

@@ -13,11 +13,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkissabc_cuda.so")
 
 KABC_OK = 0
-ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_RETRY_BUDGET, ERR_DEGENERATE, ERR_STATE = 1, 2, 3, 4, 5, 6
+ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_RETRY_BUDGET, ERR_DEGENERATE, ERR_STATE, ERR_PEER = 1, 2, 3, 4, 5, 6, 7
 PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_TRUNC_NORMAL, PRIOR_BETA, PRIOR_NEG_BINOMIAL, PRIOR_DISCRETE_UNIFORM = 0, 1, 2, 3, 4, 5
 MODEL_NORMAL_MEANSTD, MODEL_MA2_AUTOCOV, MODEL_GK_OCTILE, MODEL_LV_SSA, MODEL_DETERMINISTIC, MODEL_SOCKS = 0, 1, 2, 3, 4, 5
 F64, F32_ACC64 = 0, 1
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 MAX_DIM = 16
 
 
@@ -71,10 +72,11 @@ class KissABCError(RuntimeError):
 # every symbol include/kissabc_cuda.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "kabc_version", "kabc_last_error", "kabc_device_count", "kabc_nccl_unique_id", "kabc_ctx_create",
-    "kabc_ctx_create_dist", "kabc_ctx_destroy", "kabc_ctx_info", "kabc_prior_logpdf", "kabc_prior_sample",
+    "kabc_ctx_create_dist", "kabc_ctx_create_ranks", "kabc_ctx_arena_export", "kabc_ctx_arena_attach", "kabc_smc_arena_bytes",
+    "kabc_ais_arena_bytes", "kabc_ctx_destroy", "kabc_ctx_info", "kabc_prior_logpdf", "kabc_prior_sample",
     "kabc_eval_cost", "kabc_eval_cost_device", "kabc_smc_run", "kabc_smc_create", "kabc_smc_destroy",
     "kabc_smc_init", "kabc_smc_iterate", "kabc_smc_iterate_n", "kabc_smc_get_state", "kabc_smc_set_state",
-    "kabc_smc_get_scalars", "kabc_smc_get_log", "kabc_smc_kernel_launches", "kabc_smc_profile_iteration", "kabc_smc_trace_enable",
+    "kabc_smc_get_scalars", "kabc_smc_get_log", "kabc_smc_kernel_launches", "kabc_smc_bench_steps", "kabc_smc_profile_iteration", "kabc_smc_trace_enable",
     "kabc_smc_get_trace", "kabc_ais_run", "kabc_ais_create", "kabc_ais_destroy", "kabc_ais_init",
     "kabc_ais_sweep", "kabc_ais_get_state", "kabc_ais_set_state", "kabc_ais_get_counters",
     "kabc_ais_kernel_launches", "kabc_ais_trace_enable", "kabc_ais_get_trace", "kabc_abcde_run",
@@ -101,6 +103,13 @@ def lib():
     L.kabc_nccl_unique_id.argtypes = [C.c_char_p]
     L.kabc_ctx_create.argtypes = [C.c_int, C.c_uint64, vpp]
     L.kabc_ctx_create_dist.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_char_p, vpp]
+    L.kabc_ctx_create_ranks.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, vpp]
+    L.kabc_ctx_arena_export.argtypes = [vp, C.c_uint64, C.c_char_p]
+    L.kabc_ctx_arena_attach.argtypes = [vp, C.c_char_p]
+    L.kabc_smc_arena_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
+    L.kabc_smc_arena_bytes.restype = C.c_uint64
+    L.kabc_ais_arena_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
+    L.kabc_ais_arena_bytes.restype = C.c_uint64
     L.kabc_ctx_destroy.argtypes = [vp]
     L.kabc_ctx_info.argtypes = [vp, ip, ip, ip, ip]
     L.kabc_prior_logpdf.argtypes = [vp, C.POINTER(PriorT), C.c_int, dp, C.c_int64, dp]
@@ -122,6 +131,7 @@ def lib():
     L.kabc_smc_kernel_launches.argtypes = [vp]
     L.kabc_smc_kernel_launches.restype = C.c_int64
     L.kabc_smc_profile_iteration.argtypes = [vp, fp, C.c_int, ip]
+    L.kabc_smc_bench_steps.argtypes = [vp, C.c_int, C.c_uint64, fp]
     L.kabc_smc_trace_enable.argtypes = [vp, C.c_int]
     L.kabc_smc_get_trace.argtypes = [vp, i64p, i64p, dp, dp, dp, dp, u8p, dp]
     L.kabc_ais_run.argtypes = [vp, C.POINTER(PriorT), C.c_int, C.POINTER(ModelT), C.POINTER(AisConfigT), dp, i64p, i64p]

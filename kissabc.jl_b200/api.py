@@ -260,14 +260,29 @@ class SmcResult:
 
 
 class Context:
-    """Device + stream + Philox seed (+ NCCL communicator): replaces the `rng` keyword of the reference."""
+    """Device + stream + Philox seed: replaces the `rng` keyword of the reference.
+
+    Multi-rank jobs (one process per GPU): pass rank / world and either `nccl_id` (the context then moves the cudaIpc handles
+    of its peer arena through NCCL by itself) or `exchange`, a callable `all_gather(bytes) -> list[bytes]` over the ranks
+    (MPI, torch.distributed, ...) together with `arena_bytes` -- this mode also lets several ranks share one GPU, which
+    NCCL refuses.  NCCL is never used on the data path: ranks meet in flag barriers through NVLink peer memory."""
 
     def __init__(self, device: int = 0, seed: int = 0x4B49535341424300, rank: int = 0, world: int = 1,
-                 nccl_id: Optional[bytes] = None):
+                 nccl_id: Optional[bytes] = None, exchange=None, arena_bytes: int = 0):
         self.L = K.lib()
         self.h = C.c_void_p()
-        if world > 1:
+        if world > 1 and nccl_id is not None:
             K.check(self.L.kabc_ctx_create_dist(device, seed, rank, world, nccl_id, C.byref(self.h)))
+        elif world > 1:
+            if exchange is None or arena_bytes <= 0:
+                raise KissABCError(K.ERR_INVALID_ARG, "a multi-rank context needs nccl_id, or exchange + arena_bytes")
+            K.check(self.L.kabc_ctx_create_ranks(device, seed, rank, world, C.byref(self.h)))
+            buf = C.create_string_buffer(K.IPC_HANDLE_BYTES)
+            K.check(self.L.kabc_ctx_arena_export(self.h, int(arena_bytes), buf))
+            handles = exchange(buf.raw)
+            if len(handles) != world or any(len(x) != K.IPC_HANDLE_BYTES for x in handles):
+                raise KissABCError(K.ERR_INVALID_ARG, "exchange() must return one 64-byte handle per rank, in rank order")
+            K.check(self.L.kabc_ctx_arena_attach(self.h, b"".join(handles)))
         else:
             K.check(self.L.kabc_ctx_create(device, seed, C.byref(self.h)))
         self.device, self.seed, self.rank, self.world = device, seed, rank, world
@@ -283,10 +298,15 @@ class Context:
         K.check(self.L.kabc_ctx_info(self.h, None, None, None, C.byref(v)))
         return v.value
 
-    def close(self):
+    def close(self, strict: bool = False):
+        """Destroys the context.  While smc / ais handles of the context are alive the library refuses (KABC_ERR_STATE) and the
+        context stays valid, so that the handles can still be closed afterwards (strict=True raises instead)."""
         if self.h:
-            self.L.kabc_ctx_destroy(self.h)
-            self.h = C.c_void_p()
+            rc = self.L.kabc_ctx_destroy(self.h)
+            if rc == K.KABC_OK:
+                self.h = C.c_void_p()
+            elif strict or rc != K.ERR_STATE:
+                K.check(rc)
 
     def __del__(self):
         try:
@@ -413,13 +433,20 @@ class SmcSession:
     def kernel_launches(self) -> int:
         return int(self.L.kabc_smc_kernel_launches(self.h))
 
+    def bench_steps(self, n: int, flush_bytes: int = 256 << 20) -> np.ndarray:
+        """n iterations enqueued back to back, each after an L2 flush outside its timed region: device ms per iteration"""
+        buf = (C.c_float * max(n, 1))()
+        K.check(self.L.kabc_smc_bench_steps(self.h, n, int(flush_bytes), buf))
+        return np.array(buf[:n], dtype=np.float64)
+
     def profile_iteration(self) -> dict:
         """one iteration with CUDA events between its kernels: warm per-kernel microseconds"""
         buf = (C.c_float * 16)()
         n = C.c_int()
         K.check(self.L.kabc_smc_profile_iteration(self.h, buf, 16, C.byref(n)))
-        names = ["sel_hist0", "sel_hist1", "sel_final", "alive_cut", "resample_scatter", "gather_propose",
-                 "simulate", "barrier_post"]
+        names = ["sel_1", "sel_2", "sel_3", "cut", "compact_table", "sweep"]
+        if n.value == 7:  # work-list path (Lotka-Volterra, g-and-k)
+            names = names[:5] + ["propose", "simulate"]
         return {names[i]: float(buf[i]) for i in range(n.value)}
 
     def trace_enable(self, on=True):

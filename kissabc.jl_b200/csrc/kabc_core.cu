@@ -457,9 +457,10 @@ int kabc_device_count(int *count) {
 
 int kabc_nccl_unique_id(char id[KABC_NCCL_ID_BYTES]) { return nccl_unique_id(id); }
 
-int kabc_ctx_create_dist(int device, uint64_t seed, int rank, int world, const char id[KABC_NCCL_ID_BYTES], kabc_ctx_t **out) {
+static int ctx_create_common(int device, uint64_t seed, int rank, int world, kabc_ctx **out) {
     if (!out) return set_error(KABC_ERR_INVALID_ARG, "ctx out pointer is NULL");
     if (world < 1 || rank < 0 || rank >= world) return set_error(KABC_ERR_INVALID_ARG, "bad rank/world %d/%d", rank, world);
+    if (world > KABC_MAX_PEERS) return set_error(KABC_ERR_INVALID_ARG, "at most %d ranks per job", KABC_MAX_PEERS);
     int ndev = 0;
     KABC_CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev == 0) return set_error(KABC_ERR_CUDA, "no CUDA device: libkissabc_cuda has no CPU fallback");
@@ -477,9 +478,19 @@ int kabc_ctx_create_dist(int device, uint64_t seed, int rank, int world, const c
     KABC_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     KABC_CUDA_TRY(cudaEventCreate(&ctx->ev0));
     KABC_CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    KABC_CUDA_TRY(cudaMalloc((void **)&ctx->xseq, sizeof(unsigned long long)));
+    KABC_CUDA_TRY(cudaMemset(ctx->xseq, 0, sizeof(unsigned long long)));
+    ctx->arena_attached = (world == 1);
+    *out = ctx;
+    return KABC_OK;
+}
+
+int kabc_ctx_create_dist(int device, uint64_t seed, int rank, int world, const char id[KABC_NCCL_ID_BYTES], kabc_ctx_t **out) {
+    kabc_ctx *ctx = nullptr;
+    if (int rc = ctx_create_common(device, seed, rank, world, &ctx)) return rc;
     if (world > 1) {
         int rc = nccl_comm_init(ctx, id);
-        if (rc) { delete ctx; return rc; }
+        if (rc) { kabc_ctx_destroy(ctx); return rc; }
     }
     *out = ctx;
     return KABC_OK;
@@ -489,11 +500,158 @@ int kabc_ctx_create(int device, uint64_t seed, kabc_ctx_t **out) {
     return kabc_ctx_create_dist(device, seed, 0, 1, nullptr, out);
 }
 
+int kabc_ctx_create_ranks(int device, uint64_t seed, int rank, int world, kabc_ctx_t **out) {
+    kabc_ctx *ctx = nullptr;
+    if (int rc = ctx_create_common(device, seed, rank, world, &ctx)) return rc;
+    ctx->host_exchange = true;
+    *out = ctx;
+    return KABC_OK;
+}
+
+} // extern "C"
+
+namespace kabc {
+// ------------------------------------------------------------------ peer arena
+static void arena_unmap(kabc_ctx *ctx) {
+    for (int r = 0; r < KABC_MAX_PEERS; ++r) {
+        if (r != ctx->rank && ctx->arena_map[r]) cudaIpcCloseMemHandle(ctx->arena_map[r]);
+        ctx->arena_map[r] = nullptr;
+    }
+    ctx->arena_attached = (ctx->world == 1);
+}
+
+static int arena_allocate(kabc_ctx *ctx, size_t total_bytes) {
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    arena_unmap(ctx);
+    if (ctx->arena) {
+        // peers unmap before the owner frees (cudaIpc contract): a host-side barrier sits between the two
+        if (ctx->comm) {
+            DevBuf<unsigned long long> one;
+            KABC_CUDA_TRY(one.alloc(1));
+            KABC_CUDA_TRY(cudaMemsetAsync(one.p, 0, 8, ctx->stream));
+            if (int rc = nccl_allreduce_sum_u64(ctx, one.p, 1)) return rc;
+            KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+    }
+    total_bytes = (total_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    cudaError_t e = cudaMalloc((void **)&ctx->arena, total_bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->trim(0);
+        e = cudaMalloc((void **)&ctx->arena, total_bytes);
+    }
+    if (e != cudaSuccess) { ctx->arena = nullptr; return set_error(KABC_ERR_CUDA, "peer arena allocation of %zu bytes failed: %s", total_bytes, cudaGetErrorString(e)); }
+    ctx->arena_bytes = total_bytes;
+    ctx->arena_top = KABC_ARENA_HEADER;
+    ctx->arena_users = 0;
+    KABC_CUDA_TRY(cudaMemset(ctx->arena, 0, KABC_ARENA_HEADER));
+    KABC_CUDA_TRY(cudaMemset(ctx->xseq, 0, sizeof(unsigned long long)));
+    KABC_CUDA_TRY(cudaDeviceSynchronize());
+    ctx->arena_map[ctx->rank] = ctx->arena;
+    return KABC_OK;
+}
+
+static int arena_open(kabc_ctx *ctx, const cudaIpcMemHandle_t *handles) {
+    for (int r = 0; r < ctx->world; ++r) {
+        if (r == ctx->rank) { ctx->arena_map[r] = ctx->arena; continue; }
+        void *m = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&m, handles[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            arena_unmap(ctx);
+            return set_error(KABC_ERR_CUDA, "cudaIpcOpenMemHandle of rank %d's arena failed: %s (peer access over NVLink is required)", r,
+                             cudaGetErrorString(e));
+        }
+        ctx->arena_map[r] = m;
+    }
+    ctx->arena_attached = true;
+    return KABC_OK;
+}
+
+int arena_reserve(kabc_ctx *ctx, size_t bytes) {
+    const size_t need = KABC_ARENA_HEADER + ((bytes + 255) & ~(size_t)255) + 256;
+    if (ctx->world == 1) return set_error(KABC_ERR_STATE, "single-rank contexts have no peer arena");
+    if (ctx->arena && ctx->arena_attached && ctx->arena_bytes >= need) return KABC_OK;
+    if (ctx->host_exchange)
+        return set_error(KABC_ERR_STATE, ctx->arena_attached ? "peer arena too small: need %zu bytes, have %zu (pass a larger size to kabc_ctx_arena_export)"
+                                                             : "peer arena not attached: call kabc_ctx_arena_export / kabc_ctx_arena_attach first (need %zu bytes, have %zu)",
+                         need, ctx->arena_bytes);
+    if (ctx->arena_users > 0) return set_error(KABC_ERR_STATE, "peer arena too small and still in use by another handle");
+    if (int rc = arena_allocate(ctx, need)) return rc;
+    // move the 64-byte cudaIpc handles through the NCCL communicator the context already owns
+    const int world = ctx->world;
+    std::vector<cudaIpcMemHandle_t> handles(world);
+    memset(handles.data(), 0, sizeof(cudaIpcMemHandle_t) * world);
+    KABC_CUDA_TRY(cudaIpcGetMemHandle(&handles[ctx->rank], ctx->arena));
+    DevBuf<unsigned char> dh;
+    KABC_CUDA_TRY(dh.alloc(sizeof(cudaIpcMemHandle_t) * world));
+    KABC_CUDA_TRY(cudaMemcpyAsync(dh.p + sizeof(cudaIpcMemHandle_t) * ctx->rank, &handles[ctx->rank], sizeof(cudaIpcMemHandle_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = nccl_allgather_inplace(ctx, dh.p, sizeof(cudaIpcMemHandle_t))) return rc;
+    KABC_CUDA_TRY(cudaMemcpyAsync(handles.data(), dh.p, sizeof(cudaIpcMemHandle_t) * world, cudaMemcpyDeviceToHost, ctx->stream));
+    KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return arena_open(ctx, handles.data());
+}
+
+int arena_alloc(kabc_ctx *ctx, size_t bytes, size_t *offset) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (ctx->arena_users == 0) {
+        ctx->arena_top = KABC_ARENA_HEADER;
+        if (int rc = arena_reserve(ctx, bytes)) return rc;
+    } else if (!ctx->arena || ctx->arena_top + bytes > ctx->arena_bytes) {
+        return set_error(KABC_ERR_STATE, "peer arena exhausted: destroy the other multi-rank handle first");
+    }
+    *offset = ctx->arena_top;
+    ctx->arena_top += bytes;
+    ctx->arena_users += 1;
+    return KABC_OK;
+}
+
+void arena_release(kabc_ctx *ctx) {
+    if (ctx->arena_users > 0) ctx->arena_users -= 1;
+    if (ctx->arena_users == 0) ctx->arena_top = KABC_ARENA_HEADER;
+}
+
+} // namespace kabc
+
+extern "C" {
+
+int kabc_ctx_arena_export(kabc_ctx_t *ctx, uint64_t bytes, char handle[KABC_IPC_HANDLE_BYTES]) {
+    if (!ctx || !handle) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == KABC_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    if (ctx->world == 1) return set_error(KABC_ERR_STATE, "single-rank contexts have no peer arena");
+    if (ctx->arena_users > 0) return set_error(KABC_ERR_STATE, "the peer arena is in use");
+    if (int rc = arena_allocate(ctx, KABC_ARENA_HEADER + (size_t)bytes + 512)) return rc;
+    cudaIpcMemHandle_t h;
+    KABC_CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->arena));
+    memcpy(handle, &h, sizeof h);
+    return KABC_OK;
+}
+
+int kabc_ctx_arena_attach(kabc_ctx_t *ctx, const char *handles) {
+    if (!ctx || !handles) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
+    if (!ctx->arena) return set_error(KABC_ERR_STATE, "kabc_ctx_arena_export must be called first");
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<cudaIpcMemHandle_t> hs(ctx->world);
+    memcpy(hs.data(), handles, sizeof(cudaIpcMemHandle_t) * ctx->world);
+    return arena_open(ctx, hs.data());
+}
+
 int kabc_ctx_destroy(kabc_ctx_t *ctx) {
     if (!ctx) return KABC_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->in_use_count() > 0 || ctx->arena_users > 0)
+        return set_error(KABC_ERR_STATE, "destroy the smc / ais handles of a context before the context");
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    arena_unmap(ctx);
     if (ctx->comm) nccl_comm_destroy(ctx);
-    for (auto &e : ctx->cache) cudaFree(e.p); // handles must be destroyed before their context
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->xseq) cudaFree(ctx->xseq);
+    for (auto &e : ctx->cache) cudaFree(e.p);
     ctx->cache.clear();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

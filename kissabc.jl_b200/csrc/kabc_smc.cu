@@ -1,25 +1,33 @@
 // kabc_smc.cu -- smc(prior, cost; ...) on device.  Restates src/smc.jl:92-206 of KissABC.jl 3.0.1:
-//   init                      :119-129   k_smc_init / k_smc_init_prior + k_smc_init_gk
-//   eps = quantile(Xs[alive]) :134       k_sel_hist<0>, k_sel_hist<1>, k_sel_final  (exact two-rank bucket select on
-//                                        FP64 keys + Statistics.jl type-7 interpolation)
-//   alive cut, flag, ESS      :135-142   k_alive_cut
-//   cyclic-tiling resample    :145-153   k_alive_cut (decision + scan), k_resample_scatter, k_resample_gather
-//   propose                   :160-167   k_smc_propose  (+ prior-MH pre-test :172-175, builds the work list)
-//   simulate + accept         :176-189   k_smc_simulate / k_smc_simulate_gk
+//   init                      :119-129   k_smc_init / k_smc_init_prior + k_smc_init_gk, k_smc_post_init
+//   eps = quantile(Xs[alive]) :134       k_sel x3 (exact two-rank bucket select on FP64 keys + Statistics.jl type-7
+//                                        interpolation); the first histogram of an iteration is accumulated by the
+//                                        WRITERS of X during the previous sweep, so the usual iteration needs one pass
+//   alive cut, flag, ESS      :135-142   k_cut
+//   cyclic-tiling resample    :145-153   k_cut (decision + scan), k_compact (table of the surviving rows)
+//   propose                   :160-167 } k_smc_sweep: ONE persistent kernel per sweep; a CTA alternates between proposing a
+//   prior-MH pre-test         :172-175 } tile of 256 particles (gathers through the resampling map, latency bound) and
+//   simulate + accept         :176-189 } simulating 256 queued survivors (issue bound), so that the two phases of different
+//                                        CTAs overlap on every SM and every simulating warp is full.
+//                                        (Lotka-Volterra / g-and-k: k_smc_propose -> work list -> k_smc_simulate_lv / _gk)
 //   retry / stop rules        :156-159,192-198   post_sweep()/post_iter() run by the LAST block of the sweep kernel
 // Every scalar that steers control flow lives in SmcCtrl in device memory; the host only reads `stop`.
-// State is SoA FP64: th[k*N+i], X[i], lpi[i], alive[i]; two copies (ping-pong): every iteration gathers
-// (resample) or copies (no resample) into the other copy, so the host always knows which copy is current.
 //
-// Multi-GPU (one process per GPU): the state is replicated, the sweep is sharded.  Rank r proposes/simulates/
-// accepts particles [r N/G, (r+1) N/G); the updated shard rows and four counters are all-gathered (NCCL over
-// NVLink) after each sweep; quantile, cut and resample are computed redundantly from identical replicas, so no
-// scalar ever needs a broadcast.  Philox counters are keyed by the GLOBAL particle id: results are bit-identical
-// for any G.
+// Layout.  The population is SHARDED: rank r of G owns the global particles [r P, (r+1) P), P = N/G, and holds only
+// their state: th[k*P + li] (SoA FP64), X[li], lpi[li], alive[li].  Before every sweep the owner writes the rows a sweep
+// may READ into its TABLE -- the surviving rows compacted in index order when the iteration resamples (the j-th alive
+// particle of the population is entry j - off[r] of rank r's table, off = exclusive scan of the per-rank alive counts),
+// all rows otherwise -- in the rank's peer arena (kabc_peer.cuh), theta as one AoS row per particle so that a partner
+// costs one 16/32-byte read.  The sweep reads rows only through the table of their owner (NVLink peer loads for the
+// other ranks): its own row idx[i] = idxalive[i mod n_alive] (the reference's cyclic tiling, :146-147) and the two
+// partners a, b (:163-164); it writes only the state of its own shard.  So a rank receives O(P) rows per sweep whatever
+// G is, the quantile / cut / scan work on the shard only, and the ranks meet in four flag barriers per iteration
+// (histogram + sweep counters, candidate keys, alive counts, table complete) -- no NCCL on the data path, no host.
+// Philox counters are keyed by the GLOBAL particle id: results are bit-identical for any G.
 #include <ctime>
 #include "kabc_host.hpp"
 #include "kabc_gk.cuh"
-#include "kabc_nccl.hpp"
+#include "kabc_peer.cuh"
 
 namespace kabc {
 
@@ -27,35 +35,47 @@ constexpr int SEL_LOG2_BINS = 12;
 constexpr int SEL_BINS = 1 << SEL_LOG2_BINS;
 constexpr int SEL_CAP = 4096; // candidates sorted exactly by one block
 constexpr int SEL_THREADS = 512;
-constexpr int SCAN_THREADS = 1024; // particles per block of the cut / scatter kernels
+constexpr int SEL_INSTANCES = 3;   // k_sel launches per iteration; whatever is left is finished by one block (rare)
+constexpr int SCAN_THREADS = 1024; // particles per block of the cut / compact kernels
+constexpr int CUT_THREADS = 256;
+constexpr int SWEEP_THREADS = 256;
+constexpr int QCAP = 2 * SWEEP_THREADS; // survivor queue of a sweep CTA
 
-struct RankPartial { // what a rank contributes to the sweep bookkeeping
-    unsigned long long accepted, work, events, minkey;
-    unsigned long long pushed; // records this rank left in every peer's inbox during the sweep (packed pushes)
+enum { SEL_HIST = 0, SEL_CAND = 1, SEL_KEYS = 2, SEL_FINAL = 3 };
+
+// what rank s contributes to a cross-rank step, pushed into slot [barrier parity][s] of EVERY rank's arena
+struct XSlot {
+    unsigned int hist[SEL_BINS];
+    unsigned long long cand[SEL_CAP];
+    unsigned long long v[16];
 };
+enum { XV_ACC = 0, XV_WORK, XV_EVENTS, XV_MINKEY, XV_MAXKEY, XV_BELOW, XV_ABOVE, XV_COUNT, XV_ERR };
 
 struct SmcCtrl {
     double eps, eps_prev, xmin, gamma;
-    unsigned long long xmin_key; // running minimum over the alive costs (as an ordered key)
+    double win;                  // relative width of the window [eps (1-win), eps] the sweep histograms for the next quantile
+    unsigned long long xmin_key; // min(Xs[alive]) as an ordered key, ref :136 -- exact, recomputed by every sweep
+    // two-rank selection: the alive keys inside [klo,khi] are `cnt`, `below` alive keys are smaller, r0/r1 are the ranks
     unsigned long long klo, khi, v0key, v1key;
-    long long below, cnt, r0, r1; // bucket-select bookkeeping
-    unsigned long long sel_below;  // alive keys under the guessed lower bound of pass 0
-    long long n_alive;            // number of alive particles (input of the next quantile)
-    long long ess;                // ESS = sum(alive) right after the cut (what the reference prints)
+    long long below, cnt, r0, r1;
+    unsigned long long h_klo, h_khi; // key range the histogram is accumulating (selection pass, or the running sweep)
+    int h_shift, sel_state;
+    long long n_alive; // number of alive particles (input of the next quantile)
+    long long ess;     // ESS = sum(alive) right after the cut (what the reference prints)
+    long long off[KABC_MAX_PEERS + 1]; // table entries [off[r], off[r+1]) live on rank r; off[G] = rows a sweep maps onto
     unsigned long long accepted, cost_evals, events;
-    unsigned long long sw_accepted, sw_events, sw_minkey; // per-sweep partials of this rank
+    unsigned long long sw_accepted, sw_work, sw_events, sw_minkey, sw_maxkey, sw_below, sw_above; // this rank, this sweep
     long long iteration;
-    unsigned int work_count, cand_count, epoch, lv_head;
-    unsigned int push_count; // rows k_smc_propose finalised and packed into the peers' inboxes this sweep (multi GPU)
-    unsigned int tk_hist, tk_final, tk_cut, tk_gather, tk_sim;
-    int flag, resample, stop, cur, err, sweeps, retry_done, resampled_log, sel_done, bounds_known;
+    unsigned int work_count, cand_count, epoch, lv_head, tile_head;
+    unsigned int tk_sel, tk_cut, tk_compact, tk_sim, tk_misc;
+    int flag, resample, stop, err, sweeps, retry_done, resampled_log;
     int honor_stop; // kabc_smc_run enqueues one iteration ahead: once `stop` is set the queued kernels do nothing
 };
 
 struct SmcParams { // launch constants
-    long long N;
-    int d;
-    double alpha, mcmc_tol, epstol, r_epstol, min_r_ess, max_stretch;
+    long long N, P, lo; // population, shard size, first global index of the shard
+    int d, TS;          // parameters, doubles per theta row of the table (d rounded up to 2 or 4 for vector loads)
+    double alpha, mcmc_tol, epstol, r_epstol, min_r_ess, max_stretch, sqrt_np;
     long long mcmc_retrys;
     int max_iterations;
     int rank, world;
@@ -63,37 +83,33 @@ struct SmcParams { // launch constants
 
 struct SmcTrace {
     long long *a, *b;
-    double *z, *lprob, *lpip, *xp, *thp;
+    double *z, *lprob, *lpip, *xp;
     unsigned char *dec;
 };
 
-constexpr int KABC_MAX_PEERS = 16;
-
 struct SmcBufs {
-    // the six state arrays live in ONE slab per rank: copy c at slab + c*(d+2)*N = [th (d*N) | X (N) | lpi (N)]
-    double *th[2], *X[2], *lpi[2];
-    // peer-memory replicas (multi GPU): peer[r] is rank r's slab mapped into this process (cudaIpc over NVLink);
-    // n_peers == 0 -> no direct pushes (single GPU, or the NCCL all-gather fallback)
-    double *peer[KABC_MAX_PEERS];
-    int n_peers;
-    int shard_rows; // 1: only X is replicated; theta/lpi rows are read from their owner's slab in k_smc_propose
-    // packed pushes: rows that are final after k_smc_propose are few and scattered, and as single 8-byte NVLink stores
-    // they cost one packet each.  They are written instead as dense records into an inbox inside every peer's slab
-    // (planes [index | th_0..th_{d-1} | X | lpi], one region per (sweep parity, source rank)), which k_apply_inbox
-    // scatters locally after the sweep barrier.
-    int packed;
-    long long inbox_off; // offset (doubles) of the inbox region inside a slab
+    double *th, *X, *lpi; // state of the shard
     unsigned char *alive;
-    double *thp, *lpip;
-    unsigned int *work, *idxalive, *blockcnt, *hist;
+    // peer-visible block of every rank (arena + the handle's offset; the local buffer when G = 1):
+    //   XSlot[2][G] | tab_th[P][TS] | tab_X[P] | tab_lpi[P] | tab_alive[P]
+    unsigned char *xb[KABC_MAX_PEERS];
+    long long o_th, o_X, o_lpi, o_alive; // byte offsets of the table planes inside xb[r]
+    double *thp, *lpip;                  // proposals [d][P] (work-list path and trace)
+    unsigned int *work, *blockcnt, *hist;
     unsigned long long *cand;
     SmcCtrl *ctrl;
-    RankPartial *partial; // [world]
     kabc_smc_log_t *log;
     long long log_cap;
     SmcTrace tr;
     int trace_on;
 };
+
+__device__ __forceinline__ XSlot *xslot(const SmcBufs &B, const SmcParams &P, int r, int set, int src) {
+    return reinterpret_cast<XSlot *>(B.xb[r]) + set * P.world + src;
+}
+__device__ __forceinline__ const double *tab_th(const SmcBufs &B, int r) { return reinterpret_cast<const double *>(B.xb[r] + B.o_th); }
+__device__ __forceinline__ const double *tab_X(const SmcBufs &B, int r) { return reinterpret_cast<const double *>(B.xb[r] + B.o_X); }
+__device__ __forceinline__ const double *tab_lpi(const SmcBufs &B, int r) { return reinterpret_cast<const double *>(B.xb[r] + B.o_lpi); }
 
 // an iteration queued behind a stop (or after an error) must leave the state untouched
 __device__ __forceinline__ bool smc_skip(const SmcCtrl *c) { return c->err || (c->honor_stop && c->stop); }
@@ -114,40 +130,75 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     }
     return v;
 }
-// true for exactly one block: the last one to arrive (its reads see every other block's writes)
-__device__ __forceinline__ bool last_block(unsigned int *ticket) {
-    __shared__ int s_last;
-    __threadfence();
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+__device__ __forceinline__ int sel_shift(unsigned long long klo, unsigned long long khi) {
+    const unsigned long long range = khi - klo;
+    const int bl = range ? 64 - __clzll((long long)range) : 0;
+    return bl > SEL_LOG2_BINS ? bl - SEL_LOG2_BINS : 0;
+}
+__device__ __forceinline__ void raise_peer_error(SmcCtrl *c) {
+    if (threadIdx.x == 0 && !c->err) c->err = KABC_ERR_PEER;
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) __threadfence();
-    return s_last;
+}
+
+// rank that holds table entry j (off is ascending, off[0] = 0) and the entry's index there
+__device__ __forceinline__ int locate(const long long *off, int G, long long j, long long &jl) {
+    int r = 0;
+    for (int q = 1; q < G; ++q) r += (j >= off[q]) ? 1 : 0;
+    jl = j - off[r];
+    return r;
+}
+
+// ------------------------------------------------------------------ what the writers of X do for the next quantile
+// Every alive particle's cost is final exactly once per sweep (in the propose phase if it does not reach the simulator,
+// in the accept otherwise).  At that point it is binned for the NEXT iteration's quantile over the window
+// [eps (1-win), eps] (every alive cost is < eps, ref :137), counted if it lies under / over the window, and folded into
+// the exact minimum of the alive costs (ref :136).
+struct FinalNote {
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    unsigned int below = 0, above = 0;
+};
+__device__ __forceinline__ void note_final(FinalNote &f, unsigned int *hist, unsigned long long klo, unsigned long long khi,
+                                           int shift, double X) {
+    const unsigned long long key = dkey(X);
+    f.kmin = key < f.kmin ? key : f.kmin;
+    f.kmax = key > f.kmax ? key : f.kmax;
+    if (key < klo) f.below += 1;
+    else if (key > khi) f.above += 1;
+    else atomicAdd(&hist[(key - klo) >> shift], 1u);
 }
 
 // ------------------------------------------------------------------ init, ref src/smc.jl:119-129
 template <int KIND, int PREC>
 __global__ void __launch_bounds__(256)
-k_smc_init(SmcBufs B, SmcParams P, DPriors pri, DModel m, RoundKeys rk, long long lo, long long hi) {
-    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long N = P.N;
+k_smc_init(SmcBufs B, SmcParams P, DPriors pri, DModel m, RoundKeys rk) {
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long Pn = P.P;
     unsigned long long key = ~0ull, ev_u = 0;
-    if (i < hi) {
-        Stream st(rk, ST_PRIOR, (uint32_t)i, 0u);
+    if (li < Pn) {
+        const uint32_t id = (uint32_t)(P.lo + li);
+        Stream st(rk, ST_PRIOR, id, 0u);
         bool ok = true;
 #pragma unroll 1
         for (int k = 0; k < P.d; ++k) {
             double x;
             ok &= prior1_sample(pri.p[k], st, x);
-            B.th[0][(long long)k * N + i] = x;
+            B.th[(long long)k * Pn + li] = x;
         }
         if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
         long long ev;
-        double *thv = B.th[0];
-        double X = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, [&](int k) { return thv[(long long)k * N + i]; }, ev);
-        B.X[0][i] = X;
-        B.lpi[0][i] = prior_logpdf_pushed(pri, [&](int k) { return thv[(long long)k * N + i]; });
-        B.alive[i] = 1;
+        double *thv = B.th;
+        double X = cost_thread<KIND, PREC>(m, rk, ST_COST_INIT, id, 0u, [&](int k) { return thv[(long long)k * Pn + li]; }, ev);
+        B.X[li] = X;
+        B.lpi[li] = prior_logpdf_pushed(pri, [&](int k) { return thv[(long long)k * Pn + li]; });
+        B.alive[li] = 1;
         key = dkey(X);
         ev_u = (unsigned long long)ev;
     }
@@ -159,34 +210,34 @@ k_smc_init(SmcBufs B, SmcParams P, DPriors pri, DModel m, RoundKeys rk, long lon
     }
 }
 
-__global__ void k_smc_init_prior(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi) {
-    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= hi) return;
-    const long long N = P.N;
-    Stream st(rk, ST_PRIOR, (uint32_t)i, 0u);
+__global__ void k_smc_init_prior(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk) {
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= P.P) return;
+    const long long Pn = P.P;
+    Stream st(rk, ST_PRIOR, (uint32_t)(P.lo + li), 0u);
     bool ok = true;
     for (int k = 0; k < P.d; ++k) {
         double x;
         ok &= prior1_sample(pri.p[k], st, x);
-        B.th[0][(long long)k * N + i] = x;
+        B.th[(long long)k * Pn + li] = x;
     }
     if (!ok) B.ctrl->err = KABC_ERR_INVALID_ARG;
-    double *thv = B.th[0];
-    B.lpi[0][i] = prior_logpdf_pushed(pri, [&](int k) { return thv[(long long)k * N + i]; });
-    B.alive[i] = 1;
+    double *thv = B.th;
+    B.lpi[li] = prior_logpdf_pushed(pri, [&](int k) { return thv[(long long)k * Pn + li]; });
+    B.alive[li] = 1;
 }
 
 template <int PREC>
 __global__ void __launch_bounds__(GK_THREADS)
-k_smc_init_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, long long lo, long long hi) {
+k_smc_init_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
-    const long long N = P.N;
-    for (long long i = lo + blockIdx.x; i < hi; i += gridDim.x) {
-        const double *th = B.th[0];
-        double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)i, 0u, pushk(m, 0, th[i]), pushk(m, 1, th[N + i]),
-                                    pushk(m, 2, th[2 * N + i]), pushk(m, 3, th[3 * N + i]), gk_smem);
+    const long long Pn = P.P;
+    for (long long li = blockIdx.x; li < Pn; li += gridDim.x) {
+        const double *th = B.th;
+        double c = cost_gk_block<PREC>(m, rk, ST_COST_INIT, (uint32_t)(P.lo + li), 0u, pushk(m, 0, th[li]), pushk(m, 1, th[Pn + li]),
+                                    pushk(m, 2, th[2 * Pn + li]), pushk(m, 3, th[3 * Pn + li]), gk_smem);
         if (threadIdx.x == 0) {
-            B.X[0][i] = c;
+            B.X[li] = c;
             atomicMin(&B.ctrl->sw_minkey, dkey(c));
         }
     }
@@ -201,63 +252,81 @@ __global__ void k_smc_reset(SmcBufs B, SmcParams P) {
         c->eps = dinf(); c->eps_prev = dinf();
         c->xmin_key = ~0ull; c->sw_minkey = ~0ull;
         c->n_alive = P.N; c->ess = P.N;
+        c->win = 0.5;
         c->cost_evals = (unsigned long long)P.N;
     }
 }
 
-// after the init kernels: fold this rank's partials (single GPU) or everybody's (after the all-gather)
-__global__ void k_smc_post_init(SmcBufs B, SmcParams P, int from_partials) {
-    SmcCtrl *c = B.ctrl;
-    if (from_partials) {
-        unsigned long long mk = ~0ull, ev = 0;
-        for (int r = 0; r < P.world; ++r) {
-            mk = B.partial[r].minkey < mk ? B.partial[r].minkey : mk;
-            ev += B.partial[r].events;
-        }
-        c->xmin_key = mk; c->events = ev;
-    } else {
-        c->xmin_key = c->sw_minkey; c->events = c->sw_events;
-    }
-    c->sw_minkey = ~0ull; c->sw_events = 0; c->sw_accepted = 0;
+// ranks r0, r1 of the two order statistics the type-7 quantile interpolates (Statistics.jl, ref :134) among n alive keys:
+// aleph = n*p + (1-p); j = clamp(trunc(aleph),1,n-1); gamma = clamp(aleph-j,0,1).  Thread 0 of one block.
+__device__ void sel_begin(SmcCtrl *c, const SmcParams &P, long long n) {
+    if (n <= 0) { c->err = KABC_ERR_DEGENERATE; return; }
+    const double aleph = xadd(xmul((double)n, P.alpha), xsub(1.0, P.alpha));
+    long long j = (long long)aleph;
+    if (j > n - 1) j = n - 1;
+    if (j < 1) j = 1;
+    double gamma = xsub(aleph, (double)j);
+    gamma = gamma < 0.0 ? 0.0 : (gamma > 1.0 ? 1.0 : gamma);
+    c->gamma = gamma;
+    c->r0 = (n == 1) ? 0 : j - 1; // 0-based rank of v[j]
+    c->r1 = (n == 1) ? 0 : j;     // 0-based rank of v[j+1]
 }
-__global__ void k_smc_write_partial(SmcBufs B, SmcParams P) {
+// the next selection pass histograms every alive key (nothing is known about them)
+__device__ void sel_restart_full(SmcCtrl *c) {
+    c->klo = 0; c->khi = ~0ull; c->below = 0; c->cnt = c->n_alive;
+    c->h_klo = 0; c->h_khi = ~0ull; c->h_shift = sel_shift(0, ~0ull);
+    c->sel_state = SEL_HIST;
+}
+
+// after the init kernels (and after kabc_smc_set_state): fold the ranks' minimum / event count / alive count
+__global__ void __launch_bounds__(32) k_smc_post_init(SmcBufs B, SmcParams P, XPeer x, int recount) {
     SmcCtrl *c = B.ctrl;
-    RankPartial p;
-    p.accepted = c->sw_accepted; p.work = c->work_count; p.events = c->sw_events; p.minkey = c->sw_minkey;
-    p.pushed = 0;
-    B.partial[P.rank] = p;
+    const int set = (int)((*x.seq + 1ull) & 1ull);
+    if (threadIdx.x < P.world) {
+        XSlot *s = xslot(B, P, threadIdx.x, set, P.rank);
+        s->v[XV_MINKEY] = c->sw_minkey; s->v[XV_EVENTS] = c->sw_events; s->v[XV_COUNT] = (unsigned long long)c->n_alive;
+        s->v[XV_ERR] = (unsigned long long)c->err;
+    }
+    if (!xbarrier(x)) raise_peer_error(c);
+    if (threadIdx.x == 0) {
+        unsigned long long mk = ~0ull, ev = 0, n = 0;
+        for (int r = 0; r < P.world; ++r) {
+            const XSlot *s = xslot(B, P, P.rank, set, r);
+            mk = s->v[XV_MINKEY] < mk ? s->v[XV_MINKEY] : mk;
+            ev += s->v[XV_EVENTS]; n += s->v[XV_COUNT];
+            if (!c->err && s->v[XV_ERR]) c->err = (int)s->v[XV_ERR]; // a prior that cannot be sampled on one rank stops all
+        }
+        c->xmin_key = mk;
+        if (recount) { c->n_alive = (long long)n; c->ess = (long long)n; }
+        else { c->events = ev; c->n_alive = P.N; c->ess = P.N; }
+        c->sw_minkey = ~0ull; c->sw_events = 0; c->sw_accepted = 0;
+        sel_begin(c, P, c->n_alive);
+        sel_restart_full(c);
+    }
 }
 
 // ------------------------------------------------------------------ quantile, ref src/smc.jl:134 (Statistics type 7)
 // Exact selection of the two adjacent order statistics v[j], v[j+1] by range narrowing: histogram the alive keys
-// inside [klo,khi] into 4096 equal-width key bins, keep the bins holding the two ranks, repeat; once at most
-// SEL_CAP keys remain they are compacted and sorted by one block.  Keys are the order-preserving u64 image of the
-// doubles, so bins, ranks and the result are exact (no floating point in the selection).
+// inside [klo,khi] into 4096 equal-width key bins (every rank its shard; the per-rank histograms are pushed to every
+// peer and summed redundantly), keep the bins holding the two ranks, repeat; once at most SEL_CAP keys remain they are
+// compacted, pushed to every rank and sorted by one block.  Keys are the order-preserving u64 image of the doubles, so
+// bins, ranks and the result are exact (no floating point in the selection).
 struct SelRange {
     unsigned long long klo, khi;
     long long below, cnt, r0, r1;
     int shift;
 };
-__device__ __forceinline__ int sel_shift(unsigned long long klo, unsigned long long khi) {
-    const unsigned long long range = khi - klo;
-    const int bl = range ? 64 - __clzll((long long)range) : 0;
-    return bl > SEL_LOG2_BINS ? bl - SEL_LOG2_BINS : 0;
-}
-// block-wide (SEL_THREADS threads): scan SEL_BINS counters, narrow the range to the bins holding ranks r0 and r1
-__device__ void sel_scan_narrow(const unsigned int *hist, bool hist_is_global, SelRange &R, unsigned int *s_scan,
-                                unsigned long long *s_res) {
-    constexpr int PER = SEL_BINS / SEL_THREADS;
-    unsigned int loc[PER], sum = 0;
+// block-wide (NT threads): loc[] = this thread's SEL_BINS/NT consecutive bin counts; narrows R to the bins holding r0, r1
+template <int NT>
+__device__ void sel_scan_narrow(const unsigned int (&loc)[SEL_BINS / NT], SelRange &R, unsigned int *s_scan, unsigned long long *s_res) {
+    constexpr int PER = SEL_BINS / NT;
+    unsigned int sum = 0;
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int bin = threadIdx.x * PER + q;
-        loc[q] = hist_is_global ? __ldcg(&hist[bin]) : hist[bin];
-        sum += loc[q];
-    }
+    for (int q = 0; q < PER; ++q) sum += loc[q];
     s_scan[threadIdx.x] = sum;
     if (threadIdx.x < 4) s_res[threadIdx.x] = 0;
     __syncthreads();
-    for (int o = 1; o < SEL_THREADS; o <<= 1) {
+    for (int o = 1; o < NT; o <<= 1) {
         unsigned int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0u;
         __syncthreads();
         s_scan[threadIdx.x] += v;
@@ -285,10 +354,82 @@ __device__ void sel_scan_narrow(const unsigned int *hist, bool hist_is_global, S
     __syncthreads();
 }
 
+// Executed by ONE block per rank (NT threads) once the shard's histogram over [h_klo,h_khi] is complete in B.hist:
+// exchange it (+ the scalars in v[], prepared by the caller in the own XSlot of every rank), sum, narrow, decide what the
+// next selection step is.  from_sweep: the histogram was accumulated by the sweep over the predicted window; the
+// numbers of alive keys under / over the window come with it and the prediction may have failed.
+// gmin/gmax (pass mode): extreme in-range keys over all ranks -- tighten the range (this is what ends runs of ties).
+template <int NT>
+__device__ void sel_after_hist(SmcBufs &B, const SmcParams &P, const XPeer &x, int set, bool from_sweep,
+                               unsigned long long below_sw, unsigned long long above_sw, unsigned long long gmin,
+                               unsigned long long gmax, unsigned int *s_scan, unsigned long long *s_res) {
+    constexpr int PER = SEL_BINS / NT;
+    SmcCtrl *c = B.ctrl;
+    unsigned int loc[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int bin = threadIdx.x * PER + q;
+        unsigned int s = 0;
+        for (int r = 0; r < P.world; ++r) s += xslot(B, P, P.rank, set, r)->hist[bin];
+        loc[q] = s;
+    }
+    SelRange R;
+    R.klo = c->h_klo; R.khi = c->h_khi; R.shift = c->h_shift; R.r0 = c->r0; R.r1 = c->r1;
+    R.below = from_sweep ? (long long)below_sw : c->below;
+    R.cnt = from_sweep ? c->n_alive - (long long)below_sw - (long long)above_sw : c->cnt;
+    const bool failed = from_sweep && (above_sw > 0 || R.r0 < (long long)below_sw);
+    __syncthreads();
+    if (failed) { // a rank lies outside the predicted window: histogram [true min, top] in the next pass
+        R.klo = c->xmin_key; R.khi = above_sw > 0 ? ~0ull : c->h_khi; R.below = 0; R.cnt = c->n_alive; R.shift = 1;
+        if (R.khi < R.klo) { R.klo = 0; R.khi = ~0ull; }
+    } else {
+        sel_scan_narrow<NT>(loc, R, s_scan, s_res);
+        if (!from_sweep) {
+            if (gmin > R.klo && gmin <= R.khi) R.klo = gmin;
+            if (gmax < R.khi && gmax >= R.klo) R.khi = gmax;
+        }
+    }
+    if (threadIdx.x == 0) {
+        c->klo = R.klo; c->khi = R.khi; c->below = R.below; c->cnt = R.cnt;
+        if (!failed && (R.shift == 0 || R.klo == R.khi)) { // bins were single keys (or one key is left): these ARE v[j], v[j+1]
+            c->v0key = R.klo; c->v1key = R.khi;
+            c->sel_state = SEL_KEYS;
+        } else if (!failed && R.cnt <= SEL_CAP) {
+            c->sel_state = SEL_CAND;
+        } else {
+            c->h_klo = R.klo; c->h_khi = R.khi; c->h_shift = sel_shift(R.klo, R.khi);
+            c->sel_state = SEL_HIST;
+        }
+    }
+    __syncthreads();
+}
+
+// closes the selection and opens the iteration, ref :132-141.  One thread.
+__device__ void sel_finalize(SmcCtrl *c) {
+    const double a = dunkey(c->v0key), b = dunkey(c->v1key), g = c->gamma;
+    double eps;
+    if (dfinite(a) && dfinite(b)) eps = xadd(a, xmul(g, xsub(b, a)));
+    else eps = xadd(xmul(xsub(1.0, g), a), xmul(g, b));
+    c->iteration += 1;
+    c->eps_prev = c->eps;
+    c->eps = eps;
+    c->xmin = dunkey(c->xmin_key);
+    c->flag = (eps > c->xmin) ? 0 : 1; // ref :136-141
+    c->sweeps = 0; c->retry_done = 0; c->accepted = 0; c->resampled_log = 0;
+    // window of the NEXT quantile: four times the last relative step of eps, at most the top binade
+    double win = 0.5;
+    if (dfinite(c->eps_prev) && c->eps_prev > 0.0 && eps > 0.0 && eps < c->eps_prev) {
+        win = xmul(4.0, xsub(1.0, xdiv(eps, c->eps_prev)));
+        win = win < 0.015625 ? 0.015625 : (win > 0.5 ? 0.5 : win);
+    }
+    c->win = win;
+    c->sel_state = SEL_FINAL;
+}
+
 // 4 consecutive particles per thread: one uchar4 + two double2 loads
 __device__ __forceinline__ void load4(const unsigned char *alive, const double *X, long long base, long long N,
                                       unsigned int (&a)[4], double (&x)[4]) {
-    if (base + 3 < N && (reinterpret_cast<unsigned long long>(X) & 15ull) == 0) {
+    if (base + 3 < N) {
         const uchar4 av = *reinterpret_cast<const uchar4 *>(alive + base);
         const double2 x0 = *reinterpret_cast<const double2 *>(X + base), x1 = *reinterpret_cast<const double2 *>(X + base + 2);
         a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
@@ -302,203 +443,184 @@ __device__ __forceinline__ void load4(const unsigned char *alive, const double *
     }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(SEL_THREADS) k_sel_hist(SmcBufs B, SmcParams P) {
-    __shared__ unsigned int sh[SEL_BINS];
-    __shared__ unsigned int s_scan[SEL_THREADS];
-    __shared__ unsigned long long s_res[4];
+// one histogram pass of block `blk` of `nblk` over the shard: alive keys inside [h_klo,h_khi] -> B.hist, extreme keys
+__device__ void sel_pass_hist(SmcBufs &B, const SmcParams &P, unsigned int *sh, int blk, int nblk) {
     SmcCtrl *c = B.ctrl;
-    if (smc_skip(c)) return;
-    SelRange R;
-    double gamma = 0.0;
-    unsigned long long klo_true = 0;
-    if (PASS == 0) {
-        const long long n = c->n_alive;
-        if (n <= 0) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) c->err = KABC_ERR_DEGENERATE;
-            return;
-        }
-        // aleph = n*p + (1-p); j = clamp(trunc(aleph),1,n-1); gamma = clamp(aleph-j,0,1)
-        const double aleph = xadd(xmul((double)n, P.alpha), xsub(1.0, P.alpha));
-        long long j = (long long)aleph;
-        if (j > n - 1) j = n - 1;
-        if (j < 1) j = 1;
-        gamma = xsub(aleph, (double)j);
-        gamma = gamma < 0.0 ? 0.0 : (gamma > 1.0 ? 1.0 : gamma);
-        R.r0 = (n == 1) ? 0 : j - 1; // 0-based rank of v[j]
-        R.r1 = (n == 1) ? 0 : j;     // 0-based rank of v[j+1]
-        klo_true = c->xmin_key;
-        R.klo = klo_true;
-        R.khi = ~0ull;
-        if (c->bounds_known && dfinite(c->eps)) {
-            R.khi = dkey(c->eps);
-            // guess: the new quantile sits in the top binade of the alive costs (it does for any alpha that is not
-            // tiny); keys under the guess are only counted.  A wrong guess is detected below and costs one more pass.
-            const unsigned long long g = dkey(xmul(c->eps, 0.5));
-            if (c->eps > 0.0 && g > R.klo && g < R.khi) R.klo = g;
-        }
-        if (R.khi < R.klo) { R.khi = ~0ull; R.klo = klo_true; }
-        R.below = 0; R.cnt = n;
-    } else {
-        if (c->sel_done || c->cnt <= SEL_CAP) return;
-        R.klo = c->klo; R.khi = c->khi; R.below = c->below; R.cnt = c->cnt; R.r0 = c->r0; R.r1 = c->r1;
-    }
-    R.shift = sel_shift(R.klo, R.khi);
+    const unsigned long long klo = c->h_klo, khi = c->h_khi;
+    const int shift = c->h_shift;
     for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) sh[q] = 0;
     __syncthreads();
-    const double *X = B.X[c->cur];
-    unsigned long long nbelow = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < P.N; base += stride) {
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    const long long stride = (long long)nblk * blockDim.x * 4;
+    for (long long base = ((long long)blk * blockDim.x + threadIdx.x) * 4; base < P.P; base += stride) {
         unsigned int a[4];
-        double x[4];
-        load4(B.alive, X, base, P.N, a, x);
+        double xv[4];
+        load4(B.alive, B.X, base, P.P, a, xv);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (!a[q]) continue;
-            const unsigned long long key = dkey(x[q]);
-            if (key >= R.klo && key <= R.khi) atomicAdd(&sh[(key - R.klo) >> R.shift], 1u);
-            else if (PASS == 0 && key < R.klo) nbelow += 1;
+            const unsigned long long key = dkey(xv[q]);
+            if (key >= klo && key <= khi) {
+                atomicAdd(&sh[(key - klo) >> shift], 1u);
+                kmin = key < kmin ? key : kmin;
+                kmax = key > kmax ? key : kmax;
+            }
         }
     }
-    if (PASS == 0) {
-        nbelow = warp_sum_u64(nbelow);
-        if ((threadIdx.x & 31) == 0 && nbelow) atomicAdd(&c->sel_below, nbelow);
+    kmin = warp_min_u64(kmin);
+    kmax = warp_max_u64(kmax);
+    if ((threadIdx.x & 31) == 0) {
+        if (kmin != ~0ull) atomicMin(&c->sw_minkey, kmin);
+        if (kmax != 0ull) atomicMax(&c->sw_maxkey, kmax);
     }
     __syncthreads();
     for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) {
         const unsigned int v = sh[q];
         if (v) atomicAdd(&B.hist[q], v);
     }
-    if (!last_block(&c->tk_hist)) return;
-    bool guess_failed = false;
-    if (PASS == 0) {
-        const long long below = (long long)c->sel_below;
-        if (R.r0 < below) { // a rank lies under the guessed bound: hand the whole range [true min, khi] to the next pass
-            guess_failed = true;
-            R.klo = klo_true; R.below = 0; R.cnt = c->n_alive; R.shift = 1;
-        } else {
-            R.below = below;
+}
+// one compaction pass: the alive keys inside [klo,khi] (at most SEL_CAP over all ranks) -> B.cand
+__device__ void sel_pass_cand(SmcBufs &B, const SmcParams &P, int blk, int nblk) {
+    SmcCtrl *c = B.ctrl;
+    const unsigned long long klo = c->klo, khi = c->khi;
+    const long long stride = (long long)nblk * blockDim.x * 4;
+    const long long nloop = (P.P + stride - 1) / stride;
+    for (long long it = 0; it < nloop; ++it) {
+        const long long base = it * stride + ((long long)blk * blockDim.x + threadIdx.x) * 4;
+        unsigned int a[4] = {0u, 0u, 0u, 0u};
+        double xv[4] = {0.0, 0.0, 0.0, 0.0};
+        if (base < P.P) load4(B.alive, B.X, base, P.P, a, xv);
+        unsigned long long keys[4];
+        bool ins[4], any = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            keys[q] = dkey(xv[q]);
+            ins[q] = a[q] && keys[q] >= klo && keys[q] <= khi;
+            any |= ins[q];
         }
-    }
-    if (!guess_failed) sel_scan_narrow(B.hist, true, R, s_scan, s_res);
-    for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) B.hist[q] = 0;
-    if (threadIdx.x == 0) {
-        c->tk_hist = 0;
-        c->sel_below = 0;
-        c->klo = R.klo; c->khi = R.khi; c->below = R.below; c->cnt = R.cnt; c->r0 = R.r0; c->r1 = R.r1;
-        c->sel_done = (R.shift == 0); // bins were single keys: klo/khi ARE v[j], v[j+1]
-        c->v0key = R.klo; c->v1key = R.khi;
-        if (PASS == 0) { // opens the iteration, ref :132-133
-            c->gamma = gamma;
-            c->iteration += 1;
-            c->eps_prev = c->eps;
-            c->sweeps = 0; c->retry_done = 0; c->accepted = 0; c->resampled_log = 0;
+        if (__ballot_sync(0xffffffffu, any) == 0) continue; // candidates are rare (<= 4096 of N)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool in = ins[q];
+            const unsigned int ball = __ballot_sync(0xffffffffu, in);
+            if (ball) {
+                const unsigned int lane = threadIdx.x & 31;
+                unsigned int pos = 0;
+                if (lane == 0) pos = atomicAdd(&c->cand_count, (unsigned int)__popc(ball));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const unsigned int at = pos + __popc(ball & ((1u << lane) - 1u));
+                if (in && at < SEL_CAP) B.cand[at] = keys[q];
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) k_sel_final(SmcBufs B, SmcParams P) {
-    __shared__ unsigned long long s_keys[SEL_CAP]; // candidates (sort path) or histogram (slow path)
-    __shared__ unsigned int s_scan[SEL_THREADS];
-    __shared__ unsigned long long s_res[4];
+// the last block of a selection step: publish the shard's contribution, meet the other ranks, consume.
+// s_buf: SEL_CAP u64 of shared memory.
+__device__ void sel_publish_consume(SmcBufs &B, const SmcParams &P, const XPeer &x, int st, unsigned long long *s_buf,
+                                    unsigned int *s_scan, unsigned long long *s_res) {
     SmcCtrl *c = B.ctrl;
-    if (smc_skip(c)) return;
-    const double *X = B.X[c->cur];
-    const bool compact = !c->sel_done && c->cnt <= SEL_CAP;
-    if (compact) {
-        const unsigned long long klo = c->klo, khi = c->khi;
-        const long long stride = (long long)gridDim.x * blockDim.x * 4;
-        const long long nloop = (P.N + stride - 1) / stride;
-        for (long long it = 0; it < nloop; ++it) {
-            const long long base = it * stride + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-            unsigned int a[4] = {0u, 0u, 0u, 0u};
-            double x[4] = {0.0, 0.0, 0.0, 0.0};
-            if (base < P.N) load4(B.alive, X, base, P.N, a, x);
-            unsigned long long keys[4];
-            bool ins[4], any = false;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                keys[q] = dkey(x[q]);
-                ins[q] = a[q] && keys[q] >= klo && keys[q] <= khi;
-                any |= ins[q];
-            }
-            if (__ballot_sync(0xffffffffu, any) == 0) continue; // candidates are rare (<= 4096 of N)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned long long key = keys[q];
-                const bool in = ins[q];
-                const unsigned int ball = __ballot_sync(0xffffffffu, in);
-                if (ball) {
-                    const unsigned int lane = threadIdx.x & 31;
-                    unsigned int pos = 0;
-                    if (lane == 0) pos = atomicAdd(&c->cand_count, (unsigned int)__popc(ball));
-                    pos = __shfl_sync(0xffffffffu, pos, 0);
-                    if (in) B.cand[pos + __popc(ball & ((1u << lane) - 1u))] = key;
-                }
-            }
+    const int set = (int)((*x.seq + 1ull) & 1ull);
+    if (st == SEL_HIST) {
+        for (int r = 0; r < P.world; ++r) {
+            XSlot *s = xslot(B, P, r, set, P.rank);
+            for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) s->hist[q] = __ldcg(&B.hist[q]);
+            if (threadIdx.x == 0) { s->v[XV_MINKEY] = c->sw_minkey; s->v[XV_MAXKEY] = c->sw_maxkey; }
         }
-    }
-    if (!last_block(&c->tk_final)) return;
-    unsigned long long v0, v1;
-    if (c->sel_done) {
-        v0 = c->v0key; v1 = c->v1key;
-    } else if (compact) {
-        const int n = (int)c->cnt;
+        __syncthreads();
+        for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) B.hist[q] = 0;
+        if (!xbarrier(x)) raise_peer_error(c);
+        unsigned long long gmin = ~0ull, gmax = 0ull;
+        for (int r = 0; r < P.world; ++r) {
+            const XSlot *s = xslot(B, P, P.rank, set, r);
+            gmin = s->v[XV_MINKEY] < gmin ? s->v[XV_MINKEY] : gmin;
+            gmax = s->v[XV_MAXKEY] > gmax ? s->v[XV_MAXKEY] : gmax;
+        }
+        if (threadIdx.x == 0) { c->sw_minkey = ~0ull; c->sw_maxkey = 0ull; }
+        sel_after_hist<SEL_THREADS>(B, P, x, set, false, 0, 0, gmin, gmax, s_scan, s_res);
+    } else { // SEL_CAND
+        const unsigned int n_loc = c->cand_count < (unsigned)SEL_CAP ? c->cand_count : (unsigned)SEL_CAP;
+        for (int r = 0; r < P.world; ++r) {
+            XSlot *s = xslot(B, P, r, set, P.rank);
+            for (unsigned int q = threadIdx.x; q < n_loc; q += blockDim.x) s->cand[q] = __ldcg(&B.cand[q]);
+            if (threadIdx.x == 0) s->v[XV_COUNT] = n_loc;
+        }
+        if (!xbarrier(x)) raise_peer_error(c);
+        // concatenate the ranks' lists, sort, pick
+        int n = 0;
+        for (int r = 0; r < P.world; ++r) {
+            const XSlot *s = xslot(B, P, P.rank, set, r);
+            const int nr = (int)s->v[XV_COUNT];
+            for (int q = threadIdx.x; q < nr; q += blockDim.x)
+                if (n + q < SEL_CAP) s_buf[n + q] = s->cand[q];
+            n += nr;
+        }
+        if (n != (int)c->cnt || n > SEL_CAP) { // cannot happen: the histogram counted exactly these keys
+            if (threadIdx.x == 0 && !c->err) c->err = KABC_ERR_STATE;
+            n = n > SEL_CAP ? SEL_CAP : n;
+        }
         int npad = 2;
         while (npad < n) npad <<= 1;
-        for (int q = threadIdx.x; q < npad; q += blockDim.x) s_keys[q] = q < n ? __ldcg(&B.cand[q]) : ~0ull;
+        __syncthreads();
+        for (int q = n + threadIdx.x; q < npad; q += blockDim.x) s_buf[q] = ~0ull;
         __syncthreads();
         for (int k = 2; k <= npad; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
                     const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
                     const bool up = (i & k) == 0;
-                    const unsigned long long a = s_keys[i], b = s_keys[l];
-                    if ((a > b) == up) { s_keys[i] = b; s_keys[l] = a; }
+                    const unsigned long long a = s_buf[i], b = s_buf[l];
+                    if ((a > b) == up) { s_buf[i] = b; s_buf[l] = a; }
                 }
                 __syncthreads();
             }
-        v0 = s_keys[c->r0 - c->below];
-        v1 = s_keys[c->r1 - c->below];
-    } else {
-        // rare slow path (massive ties / pathological spread): this block alone keeps narrowing over all N
-        SelRange R;
-        R.klo = c->klo; R.khi = c->khi; R.below = c->below; R.cnt = c->cnt; R.r0 = c->r0; R.r1 = c->r1;
-        unsigned int *sh = reinterpret_cast<unsigned int *>(s_keys);
-        for (;;) {
-            R.shift = sel_shift(R.klo, R.khi);
-            for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) sh[q] = 0;
-            __syncthreads();
-            for (long long i = threadIdx.x; i < P.N; i += blockDim.x) {
-                if (!B.alive[i]) continue;
-                const unsigned long long key = dkey(X[i]);
-                if (key >= R.klo && key <= R.khi) atomicAdd(&sh[(key - R.klo) >> R.shift], 1u);
-            }
-            __syncthreads();
-            const int shift = R.shift;
-            sel_scan_narrow(sh, false, R, s_scan, s_res);
-            if (shift == 0) break;
+        if (threadIdx.x == 0) {
+            long long i0 = c->r0 - c->below, i1 = c->r1 - c->below;
+            if (i0 < 0 || i0 >= n || i1 < 0 || i1 >= n) { if (!c->err) c->err = KABC_ERR_STATE; i0 = 0; i1 = 0; }
+            c->v0key = s_buf[i0];
+            c->v1key = s_buf[i1];
+            c->cand_count = 0;
+            c->sel_state = SEL_KEYS;
         }
-        v0 = R.klo; v1 = R.khi;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_sel(SmcBufs B, SmcParams P, XPeer x, int last_instance) {
+    __shared__ unsigned long long s_buf[SEL_CAP]; // histogram (u32 view) or candidate keys
+    __shared__ unsigned int s_scan[SEL_THREADS];
+    __shared__ unsigned long long s_res[4];
+    SmcCtrl *c = B.ctrl;
+    if (smc_skip(c)) return;
+    const int st = c->sel_state;
+    if (st == SEL_FINAL) return;
+    if (st == SEL_KEYS) { // decided at the end of the last sweep (one key left): only the bookkeeping remains
+        if (blockIdx.x == 0 && threadIdx.x == 0) sel_finalize(c);
+        return;
+    }
+    if (st == SEL_HIST) sel_pass_hist(B, P, reinterpret_cast<unsigned int *>(s_buf), blockIdx.x, gridDim.x);
+    else sel_pass_cand(B, P, blockIdx.x, gridDim.x);
+    if (!last_block(&c->tk_sel)) return;
+    sel_publish_consume(B, P, x, st, s_buf, s_scan, s_res);
+    if (last_instance) { // massive ties / pathological spread: this block alone keeps narrowing over its shard
+        for (;;) {
+            const int st2 = c->sel_state;
+            if (st2 == SEL_KEYS || c->err) break;
+            if (st2 == SEL_HIST) sel_pass_hist(B, P, reinterpret_cast<unsigned int *>(s_buf), 0, 1);
+            else sel_pass_cand(B, P, 0, 1);
+            __threadfence();
+            __syncthreads();
+            sel_publish_consume(B, P, x, st2, s_buf, s_scan, s_res);
+        }
     }
     if (threadIdx.x == 0) {
-        const double a = dunkey(v0), b = dunkey(v1), g = c->gamma;
-        double eps;
-        if (dfinite(a) && dfinite(b)) eps = xadd(a, xmul(g, xsub(b, a)));
-        else eps = xadd(xmul(xsub(1.0, g), a), xmul(g, b));
-        c->eps = eps;
-        c->xmin = dunkey(c->xmin_key);
-        c->flag = (eps > c->xmin) ? 0 : 1; // ref :136-141
-        c->cand_count = 0;
-        c->tk_final = 0;
-        c->sel_done = 0;
+        c->tk_sel = 0;
+        if (c->sel_state == SEL_KEYS && !c->err) sel_finalize(c);
     }
 }
 
 // ------------------------------------------------------------------ alive cut + ESS + resample decision, ref :136-147
-// block b owns particles [1024 b, 1024 b + 1024): 256 threads x 4 consecutive particles
-constexpr int CUT_THREADS = 256;
+// block b owns local particles [1024 b, 1024 b + 1024): 256 threads x 4 consecutive particles
 __device__ __forceinline__ unsigned int block_excl_scan_256(unsigned int v, unsigned int *s_w, unsigned int &total) {
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int incl = v;
@@ -526,16 +648,44 @@ __device__ __forceinline__ unsigned int block_excl_scan_256(unsigned int v, unsi
     return r;
 }
 
-__global__ void __launch_bounds__(CUT_THREADS) k_alive_cut(SmcBufs B, SmcParams P, int nblocks) {
+// what a sweep needs before it starts; thread 0 of the block that closed the previous step.  `resample`: the sweep maps
+// onto the compacted tables (offsets = scan of the ranks' alive counts in cnt[]), else onto all rows in place.
+__device__ void sweep_setup(SmcCtrl *c, const SmcParams &P, int resample, const unsigned long long *cnt) {
+    long long run = 0;
+    for (int r = 0; r < P.world; ++r) {
+        c->off[r] = run;
+        run += resample ? (long long)cnt[r] : P.P;
+    }
+    c->off[P.world] = run;
+    c->resample = resample;
+    c->sw_accepted = 0; c->sw_work = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->sw_maxkey = 0ull; c->sw_below = 0; c->sw_above = 0;
+    c->work_count = 0; c->lv_head = 0; c->tile_head = 0;
+    // window of the next quantile: every alive cost is < eps (<= with the flag), ref :137-139
+    const double eps = c->eps;
+    const unsigned long long khi = dkey(eps);
+    unsigned long long klo = 0;
+    if (dfinite(eps) && eps > 0.0) {
+        klo = dkey(xmul(eps, xsub(1.0, c->win)));
+        if (klo > khi) klo = 0;
+    }
+    c->h_klo = klo; c->h_khi = khi; c->h_shift = sel_shift(klo, khi);
+}
+
+__global__ void __launch_bounds__(CUT_THREADS) k_cut(SmcBufs B, SmcParams P, XPeer x, int nblocks) {
     __shared__ unsigned int s_w[33];
+    __shared__ unsigned long long s_cnt[KABC_MAX_PEERS];
     SmcCtrl *c = B.ctrl;
     if (smc_skip(c)) return;
-    const double *X = B.X[c->cur];
+    if (c->sel_state != SEL_FINAL) { // the selection did not finish (cannot happen: k_sel loops until it does)
+        if (blockIdx.x == 0 && threadIdx.x == 0 && !c->err) c->err = KABC_ERR_STATE;
+        return;
+    }
+    const double *X = B.X;
     const double eps = c->eps;
     const int flag = c->flag;
     const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
     unsigned int cnt = 0;
-    if (base + 3 < P.N && (reinterpret_cast<unsigned long long>(X) & 15ull) == 0) {
+    if (base + 3 < P.P) {
         const double2 x0 = *reinterpret_cast<const double2 *>(X + base), x1 = *reinterpret_cast<const double2 *>(X + base + 2);
         uchar4 a;
         a.x = flag ? (x0.x <= eps) : (x0.x < eps); a.y = flag ? (x0.y <= eps) : (x0.y < eps);
@@ -544,9 +694,9 @@ __global__ void __launch_bounds__(CUT_THREADS) k_alive_cut(SmcBufs B, SmcParams 
         cnt = a.x + a.y + a.z + a.w;
     } else {
         for (int q = 0; q < 4; ++q)
-            if (base + q < P.N) {
-                const double x = X[base + q];
-                const unsigned int a = flag ? (x <= eps) : (x < eps);
+            if (base + q < P.P) {
+                const double xv = X[base + q];
+                const unsigned int a = flag ? (xv <= eps) : (xv < eps);
                 B.alive[base + q] = (unsigned char)a;
                 cnt += a;
             }
@@ -555,7 +705,7 @@ __global__ void __launch_bounds__(CUT_THREADS) k_alive_cut(SmcBufs B, SmcParams 
     block_excl_scan_256(cnt, s_w, total);
     if (threadIdx.x == 0) B.blockcnt[blockIdx.x] = total;
     if (!last_block(&c->tk_cut)) return;
-    // last block: exclusive scan of the per-block counts (in place), total = ESS
+    // last block: exclusive scan of the per-block counts (in place); total = alive particles of the shard
     unsigned long long carry = 0;
     for (int b0 = 0; b0 < nblocks; b0 += CUT_THREADS) {
         const int q = b0 + threadIdx.x;
@@ -565,233 +715,78 @@ __global__ void __launch_bounds__(CUT_THREADS) k_alive_cut(SmcBufs B, SmcParams 
         if (q < nblocks) B.blockcnt[q] = (unsigned int)(carry + excl);
         carry += chunk;
     }
+    // all-gather of the G counts: global scan offsets + ESS
+    const int set = (int)((*x.seq + 1ull) & 1ull);
+    if (threadIdx.x < P.world) xslot(B, P, threadIdx.x, set, P.rank)->v[XV_COUNT] = carry;
+    if (!xbarrier(x)) raise_peer_error(c);
+    if (threadIdx.x < P.world) s_cnt[threadIdx.x] = xslot(B, P, P.rank, set, threadIdx.x)->v[XV_COUNT];
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const long long ess = (long long)carry;
+        long long ess = 0;
+        for (int r = 0; r < P.world; ++r) ess += (long long)s_cnt[r];
         c->ess = ess;
         c->tk_cut = 0;
-        c->bounds_known = 1; // from now on every alive cost is <= eps
         // ref :145  alpha*ESS <= nparticles*min_r_ess, FP64, exactly these operands
-        c->resample = xmul(P.alpha, (double)ess) <= xmul((double)P.N, P.min_r_ess);
-        if (c->resample && ess == 0) c->err = KABC_ERR_DEGENERATE;
-        c->n_alive = c->resample ? P.N : ess; // ref :151-152: after resampling everything is alive
-        if (c->resample) c->resampled_log = 1;
+        const int resample = xmul(P.alpha, (double)ess) <= xmul((double)P.N, P.min_r_ess);
+        if (resample && ess == 0) c->err = KABC_ERR_DEGENERATE;
+        c->n_alive = resample ? P.N : ess; // ref :151-152: after resampling everything is alive
+        if (resample) c->resampled_log = 1;
+        sweep_setup(c, P, resample, s_cnt);
     }
 }
 
-// idxalive = (1:N)[alive], ref :146; `alive .= true` (ref :152) is applied here as well
-__global__ void __launch_bounds__(CUT_THREADS) k_resample_scatter(SmcBufs B, SmcParams P) {
+// ------------------------------------------------------------------ the table a sweep reads, ref :146-152
+// resampling: entry (blockcnt[b] + rank inside the block) of the table <- the alive rows of the shard in index order
+// (idxalive = (1:N)[alive] restricted to the shard), then `alive .= true`; otherwise entry li <- row li.
+__global__ void __launch_bounds__(CUT_THREADS) k_compact(SmcBufs B, SmcParams P, XPeer x, int force_identity, int barrier) {
     __shared__ unsigned int s_w[33];
     SmcCtrl *c = B.ctrl;
-    if (smc_skip(c) || !c->resample) return;
+    if (smc_skip(c) || (!force_identity && c->retry_done)) return;
+    const int resample = force_identity ? 0 : c->resample;
+    const long long Pn = P.P;
     const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
+    double *t_th = reinterpret_cast<double *>(B.xb[P.rank] + B.o_th);
+    double *t_X = reinterpret_cast<double *>(B.xb[P.rank] + B.o_X);
+    double *t_lpi = reinterpret_cast<double *>(B.xb[P.rank] + B.o_lpi);
+    unsigned char *t_alive = B.xb[P.rank] + B.o_alive;
     unsigned int a[4] = {0u, 0u, 0u, 0u};
-    if (base + 3 < P.N) {
-        const uchar4 av = *reinterpret_cast<const uchar4 *>(B.alive + base);
-        a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
-        *reinterpret_cast<uchar4 *>(B.alive + base) = make_uchar4(1, 1, 1, 1);
-    } else {
-        for (int q = 0; q < 4; ++q)
-            if (base + q < P.N) { a[q] = B.alive[base + q]; B.alive[base + q] = 1; }
-    }
-    unsigned int total;
-    unsigned int pos = B.blockcnt[blockIdx.x] + block_excl_scan_256(a[0] + a[1] + a[2] + a[3], s_w, total);
-#pragma unroll
     for (int q = 0; q < 4; ++q)
-        if (a[q]) B.idxalive[pos++] = (unsigned int)(base + q);
-}
-
-// One row of the population, pushed into every peer replica of copy `dst` (multi GPU, peer memory over NVLink).
-// Every row of a copy has exactly ONE writer in the whole job -- its owner rank -- so the pushes need no ordering
-// against anything but the end-of-sweep barrier.
-template <int DM>
-__device__ __forceinline__ void push_row(const SmcBufs &B, const SmcParams &P, int dst, long long i, const double (&th_row)[DM],
-                                         double X, double lp) {
-    const long long N = P.N;
-    const long long base = (long long)dst * (P.d + 2) * N;
-    for (int r = 0; r < B.n_peers; ++r) {
-        if (r == P.rank) continue;
-        double *q = B.peer[r] + base;
-        q[(long long)P.d * N + i] = X;
-        if (B.shard_rows) continue;
-#pragma unroll
-        for (int k = 0; k < DM; ++k)
-            if (k < P.d) q[(long long)k * N + i] = th_row[k];
-        q[(long long)(P.d + 1) * N + i] = lp;
+        if (base + q < Pn) a[q] = B.alive[base + q];
+    unsigned int pos = 0;
+    if (resample) {
+        unsigned int total;
+        pos = B.blockcnt[blockIdx.x] + block_excl_scan_256(a[0] + a[1] + a[2] + a[3], s_w, total);
     }
-}
-
-// ------------------------------------------------------------------ resample gather + propose, ref :147-152, :160-167, :172-175
-// Reads the complete copy S = cur (rows through the resampling map idx[k] = idxalive[k mod n], ref :146-147, or the
-// identity when the reference does not resample) and writes copy D = cur^1: every owned particle's row is
-// materialised in D here (the physical gather of the reference, done by the owner only); particles that go on to the
-// simulator are appended to the work list and finalised by the sweep kernel, the others are final here and are
-// pushed to the peers.  Partner rows are read from S through the same map, so no rank ever needs another rank's D rows.
-template <int DM> // DM >= d: compile-time bound of the parameter loops (rows stay in registers)
-__global__ void __launch_bounds__(256, 5) // 48 registers: the kernel is latency-bound on its gathers, occupancy matters
-k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk, long long lo, long long hi, double sqrt_np) {
-    SmcCtrl *c = B.ctrl;
-    if (smc_skip(c) || c->retry_done) return;
-    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long N = P.N;
-    const int S = c->cur, D = S ^ 1;
-    const double *th = B.th[S];
-    const int resample = c->resample;
-    const unsigned int n_src = (unsigned int)c->ess;
-    const uint32_t epoch = c->epoch;
-    bool push = false, defer = false;
-    int dec = 0;
-    long long a = -1, b = -1;
-    double z = dnan(), lprob = dnan(), lpip = dnan();
-    if (i < hi) {
-        // the particle's own row after the (possible) resampling
-        const long long ri = resample ? (long long)B.idxalive[(unsigned int)i % n_src] : i;
-        const bool alive_i = resample ? true : (B.alive[i] != 0);
-        // where row r of copy S lives: the local replica, or (sharded rows) the slab of the rank that owns r
-        const long long per = N / P.world, sbase = (long long)S * (P.d + 2) * N;
-        auto src_of = [&](long long r) -> const double * {
-            return B.shard_rows ? B.peer[(int)(r / per)] + sbase : th;
-        };
-        double row[DM];
-        const double *own = src_of(ri);
 #pragma unroll
-        for (int k = 0; k < DM; ++k) {
-            row[k] = 0.0;
-            if (k < P.d) {
-                row[k] = own[(long long)k * N + ri];
-                B.th[D][(long long)k * N + i] = row[k];
-            }
-        }
-        const double Xi = B.X[S][ri], lpi_i = own[(long long)(P.d + 1) * N + ri];
-        B.X[D][i] = Xi;
-        B.lpi[D][i] = lpi_i;
-        if (alive_i) {
-            Stream st(rk, ST_PROPOSE, (uint32_t)i, epoch);
-            a = i; b = i;
-            while (a == i) a = (long long)index_of(st.next(), (uint32_t)N);
-            while (b == i || b == a) b = (long long)index_of(st.next(), (uint32_t)N);
-            const long long ra = resample ? (long long)B.idxalive[(unsigned int)a % n_src] : a;
-            const long long rb = resample ? (long long)B.idxalive[(unsigned int)b % n_src] : b;
-            z = next_normal(st);
-            const double sc = xdiv(xmul(P.max_stretch, z), sqrt_np);
-            const double *pa = src_of(ra), *pb = src_of(rb);
-#pragma unroll
-            for (int k = 0; k < DM; ++k) {
-                if (k < P.d)
-                    B.thp[(long long)k * N + i] = xadd(row[k], xmul(xsub(pb[(long long)k * N + rb], pa[(long long)k * N + ra]), sc));
-            }
-            const uint32_t wu = st.next();
-            const double *thp = B.thp;
-            lpip = prior_logpdf_pushed(pri, [&](int k) { return thp[(long long)k * N + i]; });
-            if (lpip < 0.0 && !dfinite(lpip)) dec = 1;
-            else {
-                // ref :174-175  lM = min(lpip - lpi + logcorr, 0); proceed iff log(rand) < lM.
-                // log(u) < 0 always (u < 1), so the logarithm is only evaluated when lM < 0 (or when tracing).
-                const double lM = fmin(xadd(xsub(lpip, lpi_i), 0.0), 0.0);
-                bool pass = true;
-                if (!(lM >= 0.0) || B.trace_on) {
-                    lprob = xlog(u01(wu));
-                    pass = lprob < lM;
-                }
-                if (!pass) dec = 2;
-                else { push = true; B.lpip[i] = lpip; }
-            }
-            if (B.trace_on && lprob != lprob) lprob = xlog(u01(wu));
-        }
-        // multi GPU: a row that is final here still has to reach the peers
-        if (!push && B.n_peers > 0) {
-            if (B.packed) defer = true;
-            else push_row<DM>(B, P, D, i, row, Xi, lpi_i);
-        }
-        if (B.trace_on) {
-            B.tr.a[i] = a; B.tr.b[i] = b; B.tr.z[i] = z; B.tr.lprob[i] = lprob; B.tr.lpip[i] = lpip;
-            B.tr.dec[i] = (unsigned char)dec; B.tr.xp[i] = dnan();
-            if (!alive_i) for (int k = 0; k < P.d; ++k) B.thp[(long long)k * N + i] = dnan();
-        }
+    for (int q = 0; q < 4; ++q) {
+        const long long li = base + q;
+        if (li >= Pn) continue;
+        if (resample && !a[q]) continue;
+        const long long e = resample ? (long long)pos++ : li;
+        for (int k = 0; k < P.d; ++k) t_th[e * P.TS + k] = B.th[(long long)k * Pn + li];
+        t_X[e] = B.X[li];
+        t_lpi[e] = B.lpi[li];
+        if (!resample) t_alive[e] = (unsigned char)a[q];
     }
-    // block-aggregated append to the work list: ONE global atomic per CTA (a per-warp atomic on the single counter
-    // serialises 32768 requests in L2 and was the top stall of this kernel)
-    __shared__ unsigned int s_cnt[8], s_base;
-    const unsigned int ball = __ballot_sync(0xffffffffu, push);
-    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) s_cnt[warp] = __popc(ball);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int tot = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
-        s_base = tot ? atomicAdd(&c->work_count, tot) : 0u;
-    }
-    __syncthreads();
-    if (push) B.work[s_base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)i;
-    if (B.packed) { // record j of this rank's stream into every peer's inbox: consecutive lanes -> consecutive slots
-        __syncthreads();
-        const unsigned int ball2 = __ballot_sync(0xffffffffu, defer);
-        if (lane == 0) s_cnt[warp] = __popc(ball2);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
-            s_base = tot ? atomicAdd(&c->push_count, tot) : 0u;
-        }
-        __syncthreads();
-        if (defer) {
-            const long long j = (long long)(s_base + s_cnt[warp] + __popc(ball2 & ((1u << lane) - 1u)));
-            const long long per = N / P.world;
-            const long long box = B.inbox_off + ((long long)(c->epoch & 1u) * P.world + P.rank) * per * (P.d + 3);
-            const double Xi = B.X[D][i], lpi_i = B.lpi[D][i]; // the row was written above (L1/L2 hit)
-            for (int r = 0; r < B.n_peers; ++r) {
-                if (r == P.rank) continue;
-                double *q = B.peer[r] + box;
-                q[j] = __longlong_as_double(i);
-                for (int k = 0; k < P.d; ++k) q[(long long)(1 + k) * per + j] = B.th[D][(long long)k * N + i];
-                q[(long long)(1 + P.d) * per + j] = Xi;
-                q[(long long)(2 + P.d) * per + j] = lpi_i;
-            }
-        }
-    }
-}
-
-// receiver side of the packed pushes: after the sweep barrier every rank scatters the records its peers left in its
-// inbox into copy D (local stores).  blockIdx.y = source rank.
-__global__ void __launch_bounds__(256) k_apply_inbox(SmcBufs B, SmcParams P) {
-    const SmcCtrl *c = B.ctrl;
-    if ((c->honor_stop && c->stop) || c->err || c->retry_done) return;
-    const int r = blockIdx.y;
-    if (r == P.rank) return;
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= (long long)B.partial[r].pushed) return;
-    const long long N = P.N, per = N / P.world;
-    const int D = c->cur ^ 1;
-    const double *q = B.peer[P.rank] + B.inbox_off + ((long long)(c->epoch & 1u) * P.world + r) * per * (P.d + 3);
-    const long long i = __double_as_longlong(q[j]);
-    for (int k = 0; k < P.d; ++k) B.th[D][(long long)k * N + i] = q[(long long)(1 + k) * per + j];
-    B.X[D][i] = q[(long long)(1 + P.d) * per + j];
-    B.lpi[D][i] = q[(long long)(2 + P.d) * per + j];
+    if (resample)
+        for (int q = 0; q < 4; ++q)
+            if (base + q < Pn) B.alive[base + q] = 1;
+    if (!barrier || P.world == 1) return;
+    if (!last_block(&c->tk_compact)) return;
+    if (!xbarrier(x)) raise_peer_error(c); // every table is complete before any rank's sweep reads it
+    if (threadIdx.x == 0) c->tk_compact = 0;
 }
 
 // ------------------------------------------------------------------ sweep / iteration bookkeeping
-// ref :192 (`accepted >= mcmc_tol*nparticles && break`): folds the sweep's counters (this rank's, or every rank's
-// after the all-gather) into the control block
-__device__ void post_sweep(SmcBufs &B, const SmcParams &P, bool from_partials) {
-    SmcCtrl *c = B.ctrl;
-    unsigned long long acc = c->sw_accepted, work = c->work_count, ev = c->sw_events, mk = c->sw_minkey;
-    if (from_partials) {
-        acc = 0; work = 0; ev = 0; mk = ~0ull;
-        for (int r = 0; r < P.world; ++r) {
-            acc += B.partial[r].accepted; work += B.partial[r].work; ev += B.partial[r].events;
-            mk = B.partial[r].minkey < mk ? B.partial[r].minkey : mk;
-        }
-    }
+// ref :192 (`accepted >= mcmc_tol*nparticles && break`): folds the sweep's counters of every rank into the control block
+__device__ void post_sweep(SmcCtrl *c, const SmcParams &P, unsigned long long acc, unsigned long long work, unsigned long long ev,
+                           unsigned long long mk) {
     c->accepted += acc;
     c->cost_evals += work;
     c->events += ev;
-    if (mk < c->xmin_key) c->xmin_key = mk;
-    c->sw_accepted = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->work_count = 0; c->lv_head = 0; c->push_count = 0;
+    c->xmin_key = mk; // every alive cost was seen by this sweep
     c->sweeps += 1;
     c->epoch += 1;
-    c->cur ^= 1;      // copy D is now complete on every rank
-    c->resample = 0;  // a retry sweep of the same iteration reads D as it is (identity map)
     if ((double)c->accepted >= xmul(P.mcmc_tol, (double)P.N)) c->retry_done = 1;
 }
 // closes an iteration, ref :194-198
@@ -812,111 +807,364 @@ __device__ void post_iter(SmcBufs &B, const SmcParams &P) {
         L.accepted = (long long)c->accepted; L.cost_evals = (long long)c->cost_evals; L.sweeps = c->sweeps;
     }
 }
-// what the last block of a sweep kernel does.  mode bit0: fold + close the sweep here (single GPU);
-// bit1: also close the iteration (no retries pending); bit2: publish this rank's partials (multi GPU)
-__device__ __forceinline__ void sweep_epilogue(SmcBufs &B, const SmcParams &P, int mode) {
-    if (threadIdx.x != 0) return;
+
+// What the last block (NT threads) of a sweep kernel does: exchange the sweep's counters and the histogram of the final
+// costs with the other ranks, close the sweep (and, close_iter, the iteration), and start the next iteration's quantile.
+template <int NT>
+__device__ void sweep_finish(SmcBufs &B, const SmcParams &P, const XPeer &x, int close_iter, unsigned int *s_scan,
+                             unsigned long long *s_res) {
     SmcCtrl *c = B.ctrl;
-    c->tk_sim = 0;
-    if (mode & 4) {
-        RankPartial p;
-        p.accepted = c->sw_accepted; p.work = c->work_count; p.events = c->sw_events; p.minkey = c->sw_minkey;
-        p.pushed = c->push_count;
-        B.partial[P.rank] = p;
+    const int set = (int)((*x.seq + 1ull) & 1ull);
+    for (int r = 0; r < P.world; ++r) {
+        XSlot *s = xslot(B, P, r, set, P.rank);
+        for (int q = threadIdx.x; q < SEL_BINS; q += NT) s->hist[q] = __ldcg(&B.hist[q]);
+        if (threadIdx.x == 0) {
+            s->v[XV_ACC] = c->sw_accepted; s->v[XV_WORK] = c->sw_work; s->v[XV_EVENTS] = c->sw_events;
+            s->v[XV_MINKEY] = c->sw_minkey; s->v[XV_MAXKEY] = c->sw_maxkey; s->v[XV_BELOW] = c->sw_below; s->v[XV_ABOVE] = c->sw_above;
+        }
     }
-    if (mode & 1) post_sweep(B, P, false);
-    if (mode & 2) post_iter(B, P);
-}
-__global__ void k_post_sweep_dist(SmcBufs B, SmcParams P, int close_iter) {
-    if (B.ctrl->honor_stop && B.ctrl->stop) return;
-    if (!(B.ctrl->err || B.ctrl->retry_done)) post_sweep(B, P, true);
-    if (close_iter) post_iter(B, P);
+    __syncthreads();
+    for (int q = threadIdx.x; q < SEL_BINS; q += NT) B.hist[q] = 0;
+    if (!xbarrier(x)) raise_peer_error(c);
+    unsigned long long acc = 0, work = 0, ev = 0, mk = ~0ull, below = 0, above = 0;
+    for (int r = 0; r < P.world; ++r) {
+        const XSlot *s = xslot(B, P, P.rank, set, r);
+        acc += s->v[XV_ACC]; work += s->v[XV_WORK]; ev += s->v[XV_EVENTS];
+        mk = s->v[XV_MINKEY] < mk ? s->v[XV_MINKEY] : mk;
+        below += s->v[XV_BELOW]; above += s->v[XV_ABOVE];
+    }
+    if (threadIdx.x == 0) {
+        c->tk_sim = 0;
+        post_sweep(c, P, acc, work, ev, mk);
+        if (close_iter) post_iter(B, P);
+        // the next step reads the state as it is now: a retry sweep of the same iteration through the identity map (ref
+        // :159: no second resampling), the next iteration through its quantile
+        sel_begin(c, P, c->n_alive);
+    }
+    __syncthreads();
+    // the histogram was taken over the window [h_klo,h_khi] sweep_setup chose; consume it BEFORE the window is re-armed
+    if (!c->err) sel_after_hist<NT>(B, P, x, set, true, below, above, 0, ~0ull, s_scan, s_res);
+    if (threadIdx.x == 0) {
+        unsigned long long none[KABC_MAX_PEERS] = {};
+        const int st = c->sel_state;
+        const unsigned long long hk0 = c->h_klo, hk1 = c->h_khi;
+        const int hs = c->h_shift;
+        sweep_setup(c, P, 0, none); // identity map + fresh counters for a possible retry sweep (same eps, same window)
+        if (st == SEL_HIST) { c->h_klo = hk0; c->h_khi = hk1; c->h_shift = hs; } // ... unless a selection pass is pending
+    }
 }
 __global__ void k_post_iter(SmcBufs B, SmcParams P) { post_iter(B, P); }
 __global__ void k_set_honor_stop(SmcBufs B, int v) { B.ctrl->honor_stop = v; }
 
-// ------------------------------------------------------------------ simulate + accept, ref :176-189
+// ------------------------------------------------------------------ propose, ref :147-152 (own row), :160-167, :172-175
+// One particle: its own row after the (possible) resampling -- table entry i mod n through the owners' tables -- goes
+// into the state of the shard; if it is alive, partners a, b (through the same map), stretch variate, proposal, prior,
+// prior-MH pre-test.  Returns true when the proposal goes on to the simulator.
 template <int DM>
-__device__ __forceinline__ void smc_accept(SmcBufs &B, const SmcParams &P, SmcCtrl *c, long long i, double Xp,
-                                           unsigned int &acc) {
-    const long long N = P.N;
-    const int D = c->cur ^ 1; // the copy this sweep writes (the row was pre-filled by k_smc_propose)
-    const bool reject = c->flag ? (Xp > c->eps) : (Xp >= c->eps);
-    double row[DM], Xf = 0.0, lpf = 0.0;
+struct Proposed {
+    double thp[DM], lpip, Xi;
+};
+template <int DM>
+__device__ __forceinline__ void load_row(const double *t, long long e, int TS, int d, double (&row)[DM]) {
+    if (DM == 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(t + e * 2);
+        row[0] = v.x; row[1] = v.y;
+    } else if (DM == 4 || DM == 3) {
+        const double2 v0 = *reinterpret_cast<const double2 *>(t + e * 4), v1 = *reinterpret_cast<const double2 *>(t + e * 4 + 2);
+        row[0] = v0.x; row[1] = v0.y; row[2] = v1.x;
+        if (DM == 4) row[DM - 1] = v1.y;
+    } else {
 #pragma unroll
-    for (int k = 0; k < DM; ++k) row[k] = 0.0;
-    if (!reject) {
-        lpf = B.lpip[i];
-        Xf = Xp;
+        for (int k = 0; k < DM; ++k) row[k] = k < d ? t[e * TS + k] : 0.0;
+    }
+}
+template <int DM>
+__device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParams &P, const SmcCtrl *c, const DPriors &pri,
+                                                const RoundKeys &rk, const long long *off, long long li, Proposed<DM> &out,
+                                                bool &alive_out) {
+    const long long Pn = P.P, i = P.lo + li;
+    const int G = P.world;
+    const int resample = c->resample;
+    const long long n_src = off[G];
+    const uint32_t epoch = c->epoch;
+    int dec = 0;
+    long long a = -1, b = -1;
+    double z = dnan(), lprob = dnan(), lpip = dnan();
+    bool pass = false;
+    // the particle's own row after the (possible) resampling
+    long long el;
+    const int ro = locate(off, G, resample ? (long long)((unsigned int)i % (unsigned int)n_src) : i, el);
+    double row[DM];
+    load_row<DM>(tab_th(B, ro), el, P.TS, P.d, row);
+    const double Xi = tab_X(B, ro)[el], lpi_i = tab_lpi(B, ro)[el];
+    const bool alive_i = resample ? true : (B.alive[li] != 0);
+    if (resample) {
 #pragma unroll
         for (int k = 0; k < DM; ++k)
-            if (k < P.d) {
-                row[k] = B.thp[(long long)k * N + i];
-                B.th[D][(long long)k * N + i] = row[k];
+            if (k < P.d) B.th[(long long)k * Pn + li] = row[k];
+        B.X[li] = Xi;
+        B.lpi[li] = lpi_i;
+    }
+    out.Xi = Xi;
+    alive_out = alive_i;
+    if (alive_i) {
+        Stream st(rk, ST_PROPOSE, (uint32_t)i, epoch);
+        a = i; b = i;
+        while (a == i) a = (long long)index_of(st.next(), (uint32_t)P.N);
+        while (b == i || b == a) b = (long long)index_of(st.next(), (uint32_t)P.N);
+        long long ea, eb;
+        const int ra = locate(off, G, resample ? (long long)((unsigned int)a % (unsigned int)n_src) : a, ea);
+        const int rb = locate(off, G, resample ? (long long)((unsigned int)b % (unsigned int)n_src) : b, eb);
+        double pa[DM], pb[DM];
+        load_row<DM>(tab_th(B, ra), ea, P.TS, P.d, pa);
+        load_row<DM>(tab_th(B, rb), eb, P.TS, P.d, pb);
+        z = next_normal(st);
+        const double sc = xdiv(xmul(P.max_stretch, z), P.sqrt_np);
+#pragma unroll
+        for (int k = 0; k < DM; ++k) out.thp[k] = k < P.d ? xadd(row[k], xmul(xsub(pb[k], pa[k]), sc)) : 0.0;
+        const uint32_t wu = st.next();
+        lpip = prior_logpdf_pushed(pri, [&](int k) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < DM; ++q) v = (q == k) ? out.thp[q] : v;
+            return v;
+        });
+        if (lpip < 0.0 && !dfinite(lpip)) dec = 1;
+        else {
+            // ref :174-175  lM = min(lpip - lpi + logcorr, 0); proceed iff log(rand) < lM.  Julia's min propagates NaN and
+            // `lprob < NaN` is false, so a NaN ratio skips the proposal.  log(u) < 0 always (u < 1), so the logarithm is
+            // only evaluated when lM < 0 (or when tracing).
+            const double dl = xadd(xsub(lpip, lpi_i), 0.0);
+            if (dl != dl) dec = 2;
+            else {
+                const double lM = fmin(dl, 0.0);
+                pass = true;
+                if (!(lM >= 0.0) || B.trace_on) {
+                    lprob = xlog(u01(wu));
+                    pass = lprob < lM;
+                }
+                if (!pass) dec = 2;
             }
-        B.X[D][i] = Xf;
-        B.lpi[D][i] = lpf;
-        acc = 1;
-    } else if (B.n_peers > 0) {
+        }
+        if (B.trace_on && lprob != lprob) lprob = xlog(u01(wu));
+        out.lpip = lpip;
+    }
+    if (B.trace_on) {
+        B.tr.a[i] = a; B.tr.b[i] = b; B.tr.z[i] = z; B.tr.lprob[i] = lprob; B.tr.lpip[i] = lpip;
+        B.tr.dec[i] = (unsigned char)dec; B.tr.xp[i] = dnan();
+        for (int k = 0; k < P.d; ++k) {
+            double v = dnan();
 #pragma unroll
-        for (int k = 0; k < DM; ++k)
-            if (k < P.d) row[k] = B.th[D][(long long)k * N + i];
-        Xf = B.X[D][i];
-        lpf = B.lpi[D][i];
+            for (int q = 0; q < DM; ++q) v = (alive_i && q == k) ? out.thp[q] : v;
+            B.thp[(long long)k * Pn + li] = v;
+        }
     }
-    // multi GPU: the final row (moved or not) goes straight into every peer's replica: NVLink stores that overlap
-    // with the other warps' simulation.  Kernel completion flushes them; the NCCL all-gather of the 32-byte partials
-    // that closes the sweep is the barrier after which the replicas are read again.
-    if (B.n_peers > 0) {
-        push_row<DM>(B, P, D, i, row, Xf, lpf);
-    }
-    if (B.trace_on) { B.tr.xp[i] = Xp; B.tr.dec[i] = reject ? 3 : 4; }
+    return pass;
 }
 
-template <int KIND, int PREC>
-__global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
-    SmcCtrl *c = B.ctrl;
-    if (smc_skip(c)) return;
-    if (c->retry_done) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
-        return;
+// ------------------------------------------------------------------ accept, ref :176-189
+template <typename F>
+__device__ __forceinline__ bool smc_accept(SmcBufs &B, const SmcParams &P, double eps, int flag, long long li, double Xp, double lpip,
+                                           F thp_of) {
+    const bool reject = flag ? (Xp > eps) : (Xp >= eps);
+    if (!reject) {
+        for (int k = 0; k < P.d; ++k) B.th[(long long)k * P.P + li] = thp_of(k);
+        B.X[li] = Xp;
+        B.lpi[li] = lpip;
     }
-    const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int nwork = c->work_count;
-    constexpr int DM = KIND == KABC_MODEL_LV_SSA ? 3 : (KIND == KABC_MODEL_DETERMINISTIC ? KABC_MAX_DIM : 2);
-    unsigned int nacc_w = 0;
-    unsigned long long e_w = 0, key_w = ~0ull;
-    if ((w & ~31u) < nwork) {
-        unsigned int acc = 0;
-        long long ev = 0;
-        unsigned long long key = ~0ull;
-        if (w < nwork) {
-            const long long i = B.work[w];
-            const long long N = P.N;
-            const double *thp = B.thp;
-            double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, [&](int k) { return thp[(long long)k * N + i]; }, ev);
-            smc_accept<DM>(B, P, c, i, Xp, acc);
-            if (acc) key = dkey(Xp);
-        }
-        nacc_w = __popc(__ballot_sync(0xffffffffu, acc));
-        e_w = (KIND == KABC_MODEL_LV_SSA) ? warp_sum_u64((unsigned long long)ev) : 0ull;
-        if (nacc_w) key_w = warp_min_u64(key);
-    }
-    // block-level fold of the sweep counters: one set of global atomics per CTA
-    __shared__ unsigned int s_acc;
-    __shared__ unsigned long long s_ev, s_key;
-    if (threadIdx.x == 0) { s_acc = 0; s_ev = 0; s_key = ~0ull; }
+    if (B.trace_on) { B.tr.xp[P.lo + li] = Xp; B.tr.dec[P.lo + li] = reject ? 3 : 4; }
+    return !reject;
+}
+
+// per-thread tallies of a sweep kernel -> one set of global atomics per CTA
+struct SweepTally {
+    unsigned int acc = 0, work = 0;
+    unsigned long long events = 0;
+    FinalNote f;
+};
+__device__ __forceinline__ void tally_flush(SmcCtrl *c, SweepTally &t) {
+    __shared__ unsigned int s_t[4];
+    __shared__ unsigned long long s_u[3];
+    if (threadIdx.x == 0) { s_t[0] = 0; s_t[1] = 0; s_t[2] = 0; s_t[3] = 0; s_u[0] = 0; s_u[1] = ~0ull; s_u[2] = 0ull; }
     __syncthreads();
+    const unsigned int acc = (unsigned int)warp_sum_u64(t.acc), work = (unsigned int)warp_sum_u64(t.work);
+    const unsigned int below = (unsigned int)warp_sum_u64(t.f.below), above = (unsigned int)warp_sum_u64(t.f.above);
+    const unsigned long long ev = warp_sum_u64(t.events), kmin = warp_min_u64(t.f.kmin), kmax = warp_max_u64(t.f.kmax);
     if ((threadIdx.x & 31) == 0) {
-        if (nacc_w) { atomicAdd(&s_acc, nacc_w); atomicMin(&s_key, key_w); }
-        if (e_w) atomicAdd(&s_ev, e_w);
+        if (acc) atomicAdd(&s_t[0], acc);
+        if (work) atomicAdd(&s_t[1], work);
+        if (below) atomicAdd(&s_t[2], below);
+        if (above) atomicAdd(&s_t[3], above);
+        if (ev) atomicAdd(&s_u[0], ev);
+        atomicMin(&s_u[1], kmin);
+        atomicMax(&s_u[2], kmax);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_acc) { atomicAdd(&c->sw_accepted, (unsigned long long)s_acc); atomicMin(&c->sw_minkey, s_key); }
-        if (s_ev) atomicAdd(&c->sw_events, s_ev);
+        if (s_t[0]) atomicAdd(&c->sw_accepted, (unsigned long long)s_t[0]);
+        if (s_t[1]) atomicAdd(&c->sw_work, (unsigned long long)s_t[1]);
+        if (s_t[2]) atomicAdd(&c->sw_below, (unsigned long long)s_t[2]);
+        if (s_t[3]) atomicAdd(&c->sw_above, (unsigned long long)s_t[3]);
+        if (s_u[0]) atomicAdd(&c->sw_events, s_u[0]);
+        if (s_u[1] != ~0ull) atomicMin(&c->sw_minkey, s_u[1]);
+        if (s_u[2] != 0ull) atomicMax(&c->sw_maxkey, s_u[2]);
     }
-    if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
+}
+
+// ------------------------------------------------------------------ the fused sweep (thread-per-particle simulators)
+// Persistent CTAs pull tiles of 256 particles.  Propose phase: one particle per thread; proposals that pass the prior
+// tests are queued in shared memory (block scan).  As soon as 256 are queued the CTA simulates them, one per thread, all
+// warps full; the remainder is flushed when the tiles run out.  A CTA in its propose phase waits on (peer) gathers while
+// the other CTAs of the SM keep the issue slots busy with their simulations.
+// Everything a thread does not need inside the simulator's inner loop lives in shared memory (sweep constants, tallies):
+// the kernel's register budget is the simulator's, which is what sets the occupancy of the issue-bound phase.
+struct SweepShared {
+    long long off[KABC_MAX_PEERS + 1];
+    double eps;
+    unsigned long long hklo, hkhi, kmin;
+    unsigned int acc, work, below, above, tile;
+    unsigned int cnt[SWEEP_THREADS / 32];
+    int flag, hshift;
+    uint32_t epoch;
+};
+__device__ __forceinline__ void note_final_shared(SweepShared &sh, unsigned int *hist, double X) {
+    const unsigned long long key = dkey(X);
+    atomicMin(&sh.kmin, key);
+    if (key < sh.hklo) atomicAdd(&sh.below, 1u);
+    else if (key > sh.hkhi) atomicAdd(&sh.above, 1u);
+    else atomicAdd(&hist[(key - sh.hklo) >> sh.hshift], 1u);
+}
+
+// MINB: CTAs per SM the register allocation must allow (6 -> 40 registers, 5 -> 48; neither spills inside the
+// simulators' draw loops); chosen at run time (KABC_SWEEP_CTAS) so that both can be measured
+template <int KIND, int PREC, int DM, int MINB>
+__global__ void __launch_bounds__(SWEEP_THREADS, MINB)
+k_smc_sweep(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys rk, int close_iter) {
+    extern __shared__ __align__(16) unsigned char q_raw[];
+    __shared__ SweepShared sh;
+    __shared__ unsigned int s_scan[SWEEP_THREADS];
+    __shared__ unsigned long long s_res[4];
+    SmcCtrl *c = B.ctrl;
+    if (smc_skip(c) || c->retry_done) return;
+    // queue planes: Xi[QCAP] | lpip[QCAP] | thp[d][QCAP] | li[QCAP]
+    double *q_x = reinterpret_cast<double *>(q_raw);
+    double *q_lp = q_x + QCAP;
+    double *q_th = q_lp + QCAP;
+    unsigned int *q_li = reinterpret_cast<unsigned int *>(q_th + (size_t)P.d * QCAP);
+    if (threadIdx.x <= P.world) sh.off[threadIdx.x] = c->off[threadIdx.x];
+    if (threadIdx.x == 0) {
+        sh.eps = c->eps; sh.flag = c->flag; sh.epoch = c->epoch;
+        sh.hklo = c->h_klo; sh.hkhi = c->h_khi; sh.hshift = c->h_shift;
+        sh.kmin = ~0ull; sh.acc = 0; sh.work = 0; sh.below = 0; sh.above = 0;
+    }
+    const long long ntiles = (P.P + SWEEP_THREADS - 1) / SWEEP_THREADS;
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int qn = 0; // queued survivors (uniform across the CTA)
+    bool more = true;
+    __syncthreads();
+    while (more || qn > 0) {
+        if (more) {
+            if (threadIdx.x == 0) sh.tile = atomicAdd(&c->tile_head, 1u);
+            __syncthreads();
+            const long long tile = sh.tile;
+            if (tile >= ntiles) more = false;
+            else {
+                const long long li = tile * SWEEP_THREADS + threadIdx.x;
+                Proposed<DM> pr;
+                bool pass = false, alive_i = false;
+                if (li < P.P) {
+                    pass = smc_propose_one<DM>(B, P, c, pri, rk, sh.off, li, pr, alive_i);
+                    if (alive_i && !pass) note_final_shared(sh, B.hist, pr.Xi);
+                }
+                const unsigned int ball = __ballot_sync(0xffffffffu, pass);
+                if (lane == 0) sh.cnt[warp] = __popc(ball);
+                __syncthreads();
+                unsigned int before = 0, tot = 0;
+#pragma unroll
+                for (int w = 0; w < SWEEP_THREADS / 32; ++w) {
+                    const unsigned int v = sh.cnt[w];
+                    before += (w < (int)warp) ? v : 0u;
+                    tot += v;
+                }
+                if (pass) {
+                    const unsigned int at = qn + before + __popc(ball & ((1u << lane) - 1u));
+                    q_li[at] = (unsigned int)li;
+                    q_x[at] = pr.Xi;
+                    q_lp[at] = pr.lpip;
+#pragma unroll
+                    for (int k = 0; k < DM; ++k)
+                        if (k < P.d) q_th[(size_t)k * QCAP + at] = pr.thp[k];
+                }
+                qn += tot;
+            }
+            __syncthreads();
+        }
+        if (qn >= SWEEP_THREADS || (!more && qn > 0)) {
+            const unsigned int take = qn < (unsigned)SWEEP_THREADS ? qn : (unsigned)SWEEP_THREADS;
+            const unsigned int at = qn - take + threadIdx.x;
+            if (threadIdx.x < take) {
+                const long long li = q_li[at];
+                long long ev = 0;
+                const double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch,
+                                                          [&](int k) { return q_th[(size_t)k * QCAP + at]; }, ev);
+                const bool ok = smc_accept(B, P, sh.eps, sh.flag, li, Xp, q_lp[at], [&](int k) { return q_th[(size_t)k * QCAP + at]; });
+                note_final_shared(sh, B.hist, ok ? Xp : q_x[at]);
+                const unsigned int okb = __ballot_sync(__activemask(), ok);
+                if (ok && (okb & ((1u << lane) - 1u)) == 0) atomicAdd(&sh.acc, (unsigned int)__popc(okb));
+            }
+            if (threadIdx.x == 0) sh.work += take;
+            qn -= take;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (sh.acc) atomicAdd(&c->sw_accepted, (unsigned long long)sh.acc);
+        if (sh.work) atomicAdd(&c->sw_work, (unsigned long long)sh.work);
+        if (sh.below) atomicAdd(&c->sw_below, (unsigned long long)sh.below);
+        if (sh.above) atomicAdd(&c->sw_above, (unsigned long long)sh.above);
+        if (sh.kmin != ~0ull) atomicMin(&c->sw_minkey, sh.kmin);
+    }
+    if (last_block(&c->tk_sim)) sweep_finish<SWEEP_THREADS>(B, P, x, close_iter, s_scan, s_res);
+}
+
+// ------------------------------------------------------------------ work-list path (Lotka-Volterra, g-and-k)
+template <int DM>
+__global__ void __launch_bounds__(256)
+k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk) {
+    __shared__ long long s_off[KABC_MAX_PEERS + 1];
+    SmcCtrl *c = B.ctrl;
+    if (smc_skip(c) || c->retry_done) return;
+    if (threadIdx.x <= P.world) s_off[threadIdx.x] = c->off[threadIdx.x];
+    __syncthreads();
+    const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    SweepTally tl;
+    bool pass = false, alive_i = false;
+    if (li < P.P) {
+        Proposed<DM> pr;
+        pass = smc_propose_one<DM>(B, P, c, pri, rk, s_off, li, pr, alive_i);
+        if (alive_i && !pass) note_final(tl.f, B.hist, c->h_klo, c->h_khi, c->h_shift, pr.Xi);
+        if (pass) {
+#pragma unroll
+            for (int k = 0; k < DM; ++k)
+                if (k < P.d) B.thp[(long long)k * P.P + li] = pr.thp[k];
+            B.lpip[li] = pr.lpip;
+        }
+    }
+    // block-aggregated append to the work list: ONE global atomic per CTA
+    __shared__ unsigned int s_cnt[8], s_base;
+    const unsigned int ball = __ballot_sync(0xffffffffu, pass);
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = __popc(ball);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
+        s_base = tot ? atomicAdd(&c->work_count, tot) : 0u;
+    }
+    __syncthreads();
+    if (pass) B.work[s_base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)li;
+    tally_flush(c, tl);
 }
 
 // Lotka-Volterra sweep: persistent lanes.  Event counts per trajectory differ by orders of magnitude, so a lane whose
@@ -925,22 +1173,23 @@ __global__ void __launch_bounds__(256) k_smc_simulate(SmcBufs B, SmcParams P, DM
 // not depend on the schedule.
 constexpr int LV_CHUNK = 32; // events between refill checks
 template <int PREC>
-__global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
+__global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
+    __shared__ unsigned int s_scan[256];
+    __shared__ unsigned long long s_res[4];
     SmcCtrl *c = B.ctrl;
-    if (smc_skip(c)) return;
-    if (c->retry_done) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
-        return;
-    }
+    if (smc_skip(c) || c->retry_done) return;
     const unsigned int nwork = c->work_count;
-    const long long N = P.N;
+    const long long Pn = P.P;
     const uint32_t epoch = c->epoch;
+    const double eps = c->eps;
+    const int flag = c->flag;
+    const unsigned long long hklo = c->h_klo, hkhi = c->h_khi;
+    const int hshift = c->h_shift;
     const unsigned int lane = threadIdx.x & 31;
     LvSim<PREC != KABC_F64> sim;
-    long long i = -1;
+    long long li = -1;
     bool have = false, exhausted = false;
-    unsigned int nacc = 0;
-    unsigned long long events = 0, key = ~0ull;
+    SweepTally tl;
     for (;;) {
         const unsigned int need = __ballot_sync(0xffffffffu, !have && !exhausted);
         if (need) {
@@ -950,8 +1199,9 @@ __global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P,
             if (!have && !exhausted) {
                 const unsigned int w = base + __popc(need & ((1u << lane) - 1u));
                 if (w < nwork) {
-                    i = B.work[w];
-                    sim.init(m, ST_COST, (uint32_t)i, epoch, pushk(m, 0, B.thp[i]), pushk(m, 1, B.thp[N + i]), pushk(m, 2, B.thp[2 * N + i]));
+                    li = B.work[w];
+                    sim.init(m, ST_COST, (uint32_t)(P.lo + li), epoch, pushk(m, 0, B.thp[li]), pushk(m, 1, B.thp[Pn + li]),
+                             pushk(m, 2, B.thp[2 * Pn + li]));
                     have = true;
                 } else {
                     exhausted = true;
@@ -965,60 +1215,59 @@ __global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P,
             if (!__ballot_sync(0xffffffffu, have && !fin)) break;
         }
         if (have && fin) {
-            unsigned int acc = 0;
-            const double Xp = sim.result();
-            smc_accept<3>(B, P, c, i, Xp, acc);
-            if (acc) { nacc += 1; const unsigned long long k2 = dkey(Xp); key = k2 < key ? k2 : key; }
-            events += (unsigned long long)sim.ev;
+            const double Xp = sim.result(), Xold = B.X[li];
+            const double *thp = B.thp;
+            const bool ok = smc_accept(B, P, eps, flag, li, Xp, B.lpip[li], [&](int k) { return thp[(long long)k * Pn + li]; });
+            tl.work += 1;
+            tl.acc += ok ? 1u : 0u;
+            tl.events += (unsigned long long)sim.ev;
+            note_final(tl.f, B.hist, hklo, hkhi, hshift, ok ? Xp : Xold);
             have = false;
         }
     }
-    nacc = (unsigned int)warp_sum_u64(nacc);
-    events = warp_sum_u64(events);
-    key = warp_min_u64(key);
-    if (lane == 0) {
-        if (nacc) { atomicAdd(&c->sw_accepted, (unsigned long long)nacc); atomicMin(&c->sw_minkey, key); }
-        if (events) atomicAdd(&c->sw_events, events);
-    }
-    if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
+    tally_flush(c, tl);
+    if (last_block(&c->tk_sim)) sweep_finish<256>(B, P, x, close_iter, s_scan, s_res);
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk, int mode) {
+__global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
+    __shared__ unsigned int s_scan[GK_THREADS];
+    __shared__ unsigned long long s_res[4];
     SmcCtrl *c = B.ctrl;
-    if (smc_skip(c)) return;
-    if (c->retry_done) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && (mode & 2)) post_iter(B, P);
-        return;
-    }
+    if (smc_skip(c) || c->retry_done) return;
     const unsigned int nwork = c->work_count;
-    const long long N = P.N;
+    const long long Pn = P.P;
+    const double eps = c->eps;
+    const int flag = c->flag;
+    SweepTally tl;
     for (unsigned int w = blockIdx.x; w < nwork; w += gridDim.x) {
-        const long long i = B.work[w];
+        const long long li = B.work[w];
         const double *thp = B.thp;
-        double Xp = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)i, c->epoch, pushk(m, 0, thp[i]), pushk(m, 1, thp[N + i]),
-                                     pushk(m, 2, thp[2 * N + i]), pushk(m, 3, thp[3 * N + i]), gk_smem);
+        double Xp = cost_gk_block<PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), c->epoch, pushk(m, 0, thp[li]), pushk(m, 1, thp[Pn + li]),
+                                     pushk(m, 2, thp[2 * Pn + li]), pushk(m, 3, thp[3 * Pn + li]), gk_smem);
         if (threadIdx.x == 0) {
-            unsigned int acc = 0;
-            smc_accept<4>(B, P, c, i, Xp, acc);
-            if (acc) { atomicAdd(&c->sw_accepted, 1ull); atomicMin(&c->sw_minkey, dkey(Xp)); }
+            const double Xold = B.X[li];
+            const bool ok = smc_accept(B, P, eps, flag, li, Xp, B.lpip[li], [&](int k) { return thp[(long long)k * Pn + li]; });
+            tl.work += 1;
+            tl.acc += ok ? 1u : 0u;
+            note_final(tl.f, B.hist, c->h_klo, c->h_khi, c->h_shift, ok ? Xp : Xold);
         }
     }
-    if (last_block(&c->tk_sim)) sweep_epilogue(B, P, mode);
+    tally_flush(c, tl);
+    if (last_block(&c->tk_sim)) sweep_finish<GK_THREADS>(B, P, x, close_iter, s_scan, s_res);
 }
 
-// recount after kabc_smc_set_state: alive count and the running minimum
-__global__ void k_recount(SmcBufs B, long long N) {
+// recount after kabc_smc_set_state: alive count and minimum of the shard (k_smc_post_init folds the ranks)
+__global__ void k_recount(SmcBufs B, SmcParams P) {
     __shared__ unsigned long long s_n, s_min;
     if (threadIdx.x == 0) { s_n = 0; s_min = ~0ull; }
     __syncthreads();
-    const double *X = B.X[B.ctrl->cur];
     unsigned long long n = 0, mk = ~0ull;
-    for (long long i = threadIdx.x; i < N; i += blockDim.x)
+    for (long long i = threadIdx.x; i < P.P; i += blockDim.x)
         if (B.alive[i]) {
             n += 1;
-            const unsigned long long k = dkey(X[i]);
+            const unsigned long long k = dkey(B.X[i]);
             mk = k < mk ? k : mk;
         }
     n = warp_sum_u64(n);
@@ -1026,9 +1275,30 @@ __global__ void k_recount(SmcBufs B, long long N) {
     if ((threadIdx.x & 31) == 0) { atomicAdd(&s_n, n); atomicMin(&s_min, mk); }
     __syncthreads();
     if (threadIdx.x == 0) {
-        B.ctrl->n_alive = (long long)s_n; B.ctrl->ess = (long long)s_n;
-        B.ctrl->xmin_key = s_min; B.ctrl->bounds_known = 0;
+        B.ctrl->n_alive = (long long)s_n;
+        B.ctrl->sw_minkey = s_min;
+        B.ctrl->sw_events = 0;
     }
+    for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) B.hist[q] = 0;
+}
+
+// the whole population (rows of every rank, read from the identity tables) in the caller's layout: theta[k*N + i], ...
+__global__ void __launch_bounds__(256) k_gather_full(SmcBufs B, SmcParams P, XPeer x, double *th, double *X, double *lpi,
+                                                     unsigned char *alive) {
+    const long long N = P.N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / P.P);
+        const long long e = i - (long long)r * P.P;
+        const double *t = tab_th(B, r);
+        if (th) for (int k = 0; k < P.d; ++k) th[(long long)k * N + i] = t[e * P.TS + k];
+        if (X) X[i] = tab_X(B, r)[e];
+        if (lpi) lpi[i] = tab_lpi(B, r)[e];
+        if (alive) alive[i] = (B.xb[r] + B.o_alive)[e];
+    }
+    if (P.world == 1) return;
+    if (!last_block(&B.ctrl->tk_misc)) return;
+    if (!xbarrier(x)) raise_peer_error(B.ctrl); // nobody rebuilds a table another rank is still reading
+    if (threadIdx.x == 0) B.ctrl->tk_misc = 0;
 }
 
 } // namespace kabc
@@ -1043,27 +1313,27 @@ struct kabc_smc {
     SmcParams P;
     kabc_smc_config_t cfg;
     SmcBufs B;
-    DevBuf<double> slab, thp, lpip; // slab = both copies of [th | X | lpi]
-    std::vector<void *> peer_maps;  // cudaIpcOpenMemHandle mappings to close
-    bool p2p = false;               // accepted rows are pushed into the peers' slabs (else: NCCL all-gather)
-    DevBuf<unsigned char> alive;
-    DevBuf<unsigned int> work, idxalive, blockcnt, hist;
+    XPeer X;
+    DevBuf<double> state, thp, lpip; // state = [th (d*P) | X (P) | lpi (P)]
+    DevBuf<unsigned char> alive, xlocal; // xlocal: the peer-visible block when there are no peers (G = 1)
+    bool in_arena = false;
+    DevBuf<unsigned int> work, blockcnt, hist;
     DevBuf<unsigned long long> cand;
     DevBuf<SmcCtrl> ctrl;
-    DevBuf<RankPartial> partial;
     DevBuf<kabc_smc_log_t> log;
     // trace
     DevBuf<long long> ta, tb;
     DevBuf<double> tz, tlprob, tlpip, txp;
     DevBuf<unsigned char> tdec;
     SmcCtrl *h_ctrl = nullptr; // pinned
-    long long lo = 0, hi = 0;  // owned particle range [lo,hi) of this rank
-    int cur = 0;               // host mirror of ctrl->cur (flips once per iteration)
     bool inited = false;
+    bool fused = true;         // thread-per-particle simulators run inside k_smc_sweep
     long long launches = 0;
     int nblocks_scan = 0;
-    // one whole iteration (cut + sweep, all control flow on the device) captured as a CUDA graph: a single launch instead
-    // of 7-9, so the short selection kernels run back to back even when the host is not ahead of the device
+    int sweep_blocks = 0;
+    size_t sweep_smem = 0;
+    // one whole iteration (selection + cut + table + sweep, all control flow on the device) captured as a CUDA graph: a
+    // single launch instead of six, so the short kernels run back to back even when the host is not ahead of the device
     cudaGraphExec_t iter_graph = nullptr;
     int graph_kernels = 0;
     bool graph_ok = true;
@@ -1095,116 +1365,69 @@ static int smc_check_cfg(const kabc_smc_config_t *cfg, int d) {
 
 #define SMC_LAUNCHED(s, n) do { (s)->launches += (n); (s)->ctx->launches += (n); } while (0)
 
-template <int KIND>
-static void smc_launch_init_t(kabc_smc *s) {
-    const long long n = s->hi - s->lo;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    if (s->model.precision == KABC_F64)
-        k_smc_init<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk, s->lo, s->hi);
-    else
-        k_smc_init<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk, s->lo, s->hi);
-    SMC_LAUNCHED(s, 1);
+static inline int table_stride(int d) { return d <= 2 ? 2 : (d <= 4 ? 4 : d); }
+static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+// layout of the peer-visible block of a handle (identical on every rank)
+struct XLayout { size_t o_th, o_X, o_lpi, o_alive, bytes; };
+static XLayout smc_xlayout(long long P, int d, int world) {
+    XLayout L;
+    size_t o = align256(sizeof(XSlot) * 2 * (size_t)world);
+    L.o_th = o; o += align256((size_t)P * table_stride(d) * 8);
+    L.o_X = o; o += align256((size_t)P * 8);
+    L.o_lpi = o; o += align256((size_t)P * 8);
+    L.o_alive = o; o += align256((size_t)P);
+    L.bytes = o;
+    return L;
 }
 
 template <int KIND>
-static void smc_launch_sim_t(kabc_smc *s, int mode) {
-    const long long n = s->hi - s->lo;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+static void smc_launch_init_t(kabc_smc *s) {
+    const unsigned blocks = (unsigned)((s->P.P + 255) / 256);
     if (s->model.precision == KABC_F64)
-        k_smc_simulate<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk, mode);
+        k_smc_init<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk);
     else
-        k_smc_simulate<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->model, s->ctx->rk, mode);
+        k_smc_init<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk);
     SMC_LAUNCHED(s, 1);
+}
+
+// the fused sweep kernel of a model: pointer (for occupancy / attributes) and launch
+typedef void (*sweep_fn_t)(SmcBufs, SmcParams, XPeer, DPriors, DModel, RoundKeys, int);
+static int smc_sweep_min_ctas() {
+    static const int v = [] { const char *e = getenv("KABC_SWEEP_CTAS"); return (e && e[0] == '5') ? 5 : 6; }();
+    return v;
+}
+template <int KIND>
+static sweep_fn_t smc_sweep_fn_t(int prec, int d) {
+    if (KIND == KABC_MODEL_DETERMINISTIC && d > 2)
+        return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, KABC_MAX_DIM, 1> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, KABC_MAX_DIM, 1>;
+    if (KIND == KABC_MODEL_DETERMINISTIC || KIND == KABC_MODEL_SOCKS)
+        return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, 2, 5> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, 2, 5>;
+    if (smc_sweep_min_ctas() == 5)
+        return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, 2, 5> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, 2, 5>;
+    return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, 2, 6> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, 2, 6>;
+}
+static sweep_fn_t smc_sweep_fn(const kabc_smc *s) {
+    const int prec = s->model.precision, d = s->P.d;
+    switch (s->model.kind) {
+    case KABC_MODEL_NORMAL_MEANSTD: return smc_sweep_fn_t<KABC_MODEL_NORMAL_MEANSTD>(prec, d);
+    case KABC_MODEL_MA2_AUTOCOV: return smc_sweep_fn_t<KABC_MODEL_MA2_AUTOCOV>(prec, d);
+    case KABC_MODEL_DETERMINISTIC: return smc_sweep_fn_t<KABC_MODEL_DETERMINISTIC>(prec, d);
+    case KABC_MODEL_SOCKS: return smc_sweep_fn_t<KABC_MODEL_SOCKS>(prec, d);
+    default: return nullptr;
+    }
 }
 
 static int smc_gk_grid(kabc_smc *s, size_t &smem) {
     smem = gk_smem_bytes(s->model.n_draws, s->model.precision);
     long long cap = (long long)s->ctx->sm_count * gk_blocks_per_sm(s->model.n_draws, s->model.precision);
-    long long n = s->hi - s->lo;
+    long long n = s->P.P;
     return (int)(n < cap ? n : cap);
-}
-
-// all-gather of the per-rank partials and -- unless the rows were already pushed through peer memory -- of the
-// ranks' shards of state copy `cur` (theta planes, X, lpi)
-static int smc_allgather_state(kabc_smc *s, int cur, bool rows) {
-    kabc_ctx *ctx = s->ctx;
-    const long long N = s->P.N, per = N / ctx->world;
-    if (int rc = nccl_group_start()) return rc;
-    if (rows) {
-        for (int k = 0; k < s->P.d; ++k)
-            if (int rc = nccl_allgather_inplace(ctx, s->B.th[cur] + (long long)k * N, (size_t)per * 8)) return rc;
-        if (int rc = nccl_allgather_inplace(ctx, s->B.X[cur], (size_t)per * 8)) return rc;
-        if (int rc = nccl_allgather_inplace(ctx, s->B.lpi[cur], (size_t)per * 8)) return rc;
-    }
-    if (int rc = nccl_allgather_inplace(ctx, s->B.partial, sizeof(RankPartial))) return rc;
-    if (int rc = nccl_group_end()) return rc;
-    return KABC_OK;
-}
-
-// Map every peer's state slab into this process (cudaIpc; NVLink P2P).  The 64-byte handles travel through the
-// NCCL communicator the context already owns, so the host language needs no extra plumbing.  On any failure the
-// handle stays in the all-gather mode (s->p2p = false): same results, more traffic.
-static int smc_attach_peers(kabc_smc *s) {
-    kabc_ctx *ctx = s->ctx;
-    const int world = ctx->world;
-    s->p2p = false;
-    s->B.n_peers = 0;
-    if (world == 1 || world > KABC_MAX_PEERS) return KABC_OK;
-    const char *env = getenv("KABC_NO_P2P");
-    const bool want = !(env && env[0] == '1');
-    std::vector<cudaIpcMemHandle_t> handles(world);
-    memset(handles.data(), 0, sizeof(cudaIpcMemHandle_t) * world);
-    int ok = want ? 1 : 0;
-    if (ok && cudaIpcGetMemHandle(&handles[ctx->rank], s->slab.p) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-    DevBuf<unsigned char> dh;
-    DevBuf<unsigned long long> dok;
-    KABC_CUDA_TRY(dh.alloc(sizeof(cudaIpcMemHandle_t) * world));
-    KABC_CUDA_TRY(dok.alloc(1));
-    KABC_CUDA_TRY(cudaMemcpyAsync(dh.p + sizeof(cudaIpcMemHandle_t) * ctx->rank, &handles[ctx->rank], sizeof(cudaIpcMemHandle_t),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    if (int rc = nccl_allgather_inplace(ctx, dh.p, sizeof(cudaIpcMemHandle_t))) return rc;
-    KABC_CUDA_TRY(cudaMemcpyAsync(handles.data(), dh.p, sizeof(cudaIpcMemHandle_t) * world, cudaMemcpyDeviceToHost, ctx->stream));
-    KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    std::vector<void *> maps(world, nullptr);
-    for (int r = 0; ok && r < world; ++r) {
-        if (r == ctx->rank) { maps[r] = s->slab.p; continue; }
-        if (cudaIpcOpenMemHandle(&maps[r], handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-    }
-    // every rank must take the same path: agree through a sum
-    unsigned long long okv = (unsigned long long)ok;
-    KABC_CUDA_TRY(cudaMemcpyAsync(dok.p, &okv, 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (int rc = nccl_allreduce_sum_u64(ctx, dok.p, 1)) return rc;
-    KABC_CUDA_TRY(cudaMemcpyAsync(&okv, dok.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    KABC_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if ((int)okv == world) {
-        for (int r = 0; r < world; ++r) {
-            s->B.peer[r] = (double *)maps[r];
-            if (r != ctx->rank) s->peer_maps.push_back(maps[r]);
-        }
-        s->B.n_peers = world;
-        s->p2p = true;
-        // measured on 4 x B200: fine-grained remote partner reads cost more than replicating the rows
-        // (propose 311 us vs 165 us at 2^22 particles), so full-row replication is the default
-        const char *e2 = getenv("KABC_SHARD_ROWS");
-        s->B.shard_rows = (e2 && e2[0] == '1') ? 1 : 0;
-        // measured on B200s (2^20 particles per GPU): at 2 GPUs the direct row stores are as fast (0.925 vs 0.926 ms per
-        // iteration), at 4 GPUs the packed records win (propose 128 us vs 165 us, 0.98 vs 1.01 ms per iteration)
-        const char *e3 = getenv("KABC_PACKED_PUSH");
-        const bool want_packed = e3 ? (e3[0] == '1') : (world >= 4);
-        s->B.packed = (!s->B.shard_rows && want_packed) ? 1 : 0;
-        s->B.inbox_off = 2 * (long long)(s->P.d + 2) * s->P.N;
-    } else {
-        for (int r = 0; r < world; ++r)
-            if (r != ctx->rank && maps[r]) cudaIpcCloseMemHandle(maps[r]);
-    }
-    return KABC_OK;
 }
 
 static int smc_enqueue_init(kabc_smc *s) {
     kabc_ctx *ctx = s->ctx;
     k_smc_reset<<<4, 1024, 0, ctx->stream>>>(s->B, s->P);
     SMC_LAUNCHED(s, 1);
-    s->cur = 0;
     switch (s->model.kind) {
     case KABC_MODEL_NORMAL_MEANSTD: smc_launch_init_t<KABC_MODEL_NORMAL_MEANSTD>(s); break;
     case KABC_MODEL_MA2_AUTOCOV: smc_launch_init_t<KABC_MODEL_MA2_AUTOCOV>(s); break;
@@ -1212,116 +1435,76 @@ static int smc_enqueue_init(kabc_smc *s) {
     case KABC_MODEL_DETERMINISTIC: smc_launch_init_t<KABC_MODEL_DETERMINISTIC>(s); break;
     case KABC_MODEL_SOCKS: smc_launch_init_t<KABC_MODEL_SOCKS>(s); break;
     case KABC_MODEL_GK_OCTILE: {
-        const long long n = s->hi - s->lo;
-        k_smc_init_prior<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi);
+        k_smc_init_prior<<<(unsigned)((s->P.P + 255) / 256), 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
         size_t smem;
         int grid = smc_gk_grid(s, smem);
-        if (s->model.precision == KABC_F64) {
-            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_init_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_smc_init_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, s->lo, s->hi);
-        } else {
-            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_init_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_smc_init_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, s->lo, s->hi);
-        }
+        if (s->model.precision == KABC_F64)
+            k_smc_init_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
+        else
+            k_smc_init_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk);
         SMC_LAUNCHED(s, 2);
         break;
     }
     }
     KABC_CUDA_TRY(cudaGetLastError());
-    if (ctx->world > 1) {
-        k_smc_write_partial<<<1, 1, 0, ctx->stream>>>(s->B, s->P);
-        if (int rc = smc_allgather_state(s, 0, true)) return rc;
-        KABC_CUDA_TRY(cudaMemsetAsync(s->B.alive, 1, (size_t)s->P.N, ctx->stream));
-        k_smc_post_init<<<1, 1, 0, ctx->stream>>>(s->B, s->P, 1);
-        SMC_LAUNCHED(s, 2);
-    } else {
-        k_smc_post_init<<<1, 1, 0, ctx->stream>>>(s->B, s->P, 0);
-        SMC_LAUNCHED(s, 1);
-    }
+    k_smc_post_init<<<1, 32, 0, ctx->stream>>>(s->B, s->P, s->X, 0);
+    SMC_LAUNCHED(s, 1);
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
 
-// one MCMC sweep: propose -> (work list) -> simulate+accept (+ bookkeeping in the last block)
+// the table a sweep reads + one MCMC sweep (+ bookkeeping and the next quantile's first histogram in its last block)
 static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     kabc_ctx *ctx = s->ctx;
-    const long long n = s->hi - s->lo;
-    const bool dist = ctx->world > 1;
-    const int mode = dist ? 4 : (1 | (close_iter ? 2 : 0));
-    {
-        const unsigned pb = (unsigned)((n + 255) / 256);
-        const double sq = sqrt((double)s->P.d);
-        if (s->P.d <= 2) k_smc_propose<2><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi, sq);
-        else if (s->P.d <= 4) k_smc_propose<4><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi, sq);
-        else k_smc_propose<KABC_MAX_DIM><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk, s->lo, s->hi, sq);
-    }
+    const int ci = close_iter ? 1 : 0;
+    k_compact<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P, s->X, 0, 1);
     SMC_LAUNCHED(s, 1);
     s->mark();
-    switch (s->model.kind) {
-    case KABC_MODEL_NORMAL_MEANSTD: smc_launch_sim_t<KABC_MODEL_NORMAL_MEANSTD>(s, mode); break;
-    case KABC_MODEL_MA2_AUTOCOV: smc_launch_sim_t<KABC_MODEL_MA2_AUTOCOV>(s, mode); break;
-    case KABC_MODEL_LV_SSA: {
-        long long nb = (n + 255) / 256, cap = (long long)ctx->sm_count * 8;
-        const unsigned blocks = (unsigned)(nb < cap ? nb : cap);
-        if (s->model.precision == KABC_F64)
-            k_smc_simulate_lv<KABC_F64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
-        else
-            k_smc_simulate_lv<KABC_F32_ACC64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
+    if (s->fused) {
+        sweep_fn_t fn = smc_sweep_fn(s);
+        fn<<<s->sweep_blocks, SWEEP_THREADS, s->sweep_smem, ctx->stream>>>(s->B, s->P, s->X, s->pri, s->model, ctx->rk, ci);
         SMC_LAUNCHED(s, 1);
-        break;
-    }
-    case KABC_MODEL_DETERMINISTIC: smc_launch_sim_t<KABC_MODEL_DETERMINISTIC>(s, mode); break;
-    case KABC_MODEL_SOCKS: smc_launch_sim_t<KABC_MODEL_SOCKS>(s, mode); break;
-    case KABC_MODEL_GK_OCTILE: {
-        size_t smem;
-        int grid = smc_gk_grid(s, smem);
-        if (s->model.precision == KABC_F64) {
-            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_smc_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
+    } else {
+        const unsigned pb = (unsigned)((s->P.P + 255) / 256);
+        if (s->model.kind == KABC_MODEL_LV_SSA) {
+            k_smc_propose<3><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+            s->mark();
+            long long cap = (long long)ctx->sm_count * 8;
+            const unsigned blocks = (unsigned)((long long)pb < cap ? (long long)pb : cap);
+            if (s->model.precision == KABC_F64)
+                k_smc_simulate_lv<KABC_F64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
+            else
+                k_smc_simulate_lv<KABC_F32_ACC64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
         } else {
-            KABC_CUDA_TRY(cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_smc_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->model, ctx->rk, mode);
+            k_smc_propose<4><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+            s->mark();
+            size_t smem;
+            int grid = smc_gk_grid(s, smem);
+            if (s->model.precision == KABC_F64)
+                k_smc_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
+            else
+                k_smc_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
         }
-        SMC_LAUNCHED(s, 1);
-        break;
-    }
+        SMC_LAUNCHED(s, 2);
     }
     s->mark();
-    if (dist) {
-        // barrier + counters; without peer memory also the rows this rank wrote into copy D
-        if (int rc = smc_allgather_state(s, s->cur ^ 1, !s->p2p)) return rc;
-        if (s->B.packed) {
-            const dim3 grid((unsigned)((n + 255) / 256), (unsigned)ctx->world);
-            k_apply_inbox<<<grid, 256, 0, ctx->stream>>>(s->B, s->P);
-            SMC_LAUNCHED(s, 1);
-        }
-        k_post_sweep_dist<<<1, 1, 0, ctx->stream>>>(s->B, s->P, close_iter ? 1 : 0);
-        SMC_LAUNCHED(s, 1);
-        s->mark();
-    }
-    s->cur ^= 1; // host mirror of ctrl->cur: every executed sweep writes the other copy
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
 
 static int smc_enqueue_cut(kabc_smc *s) {
     kabc_ctx *ctx = s->ctx;
-    const long long N = s->P.N;
-    int sel_blocks = (int)((N + SEL_THREADS * 16 - 1) / (SEL_THREADS * 16));
+    int sel_blocks = (int)((s->P.P + SEL_THREADS * 16 - 1) / (SEL_THREADS * 16));
     if (sel_blocks > ctx->sm_count * 2) sel_blocks = ctx->sm_count * 2;
     if (sel_blocks < 1) sel_blocks = 1;
     s->mark();
-    k_sel_hist<0><<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
+    for (int q = 0; q < SEL_INSTANCES; ++q) {
+        k_sel<<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P, s->X, q == SEL_INSTANCES - 1);
+        s->mark();
+    }
+    k_cut<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P, s->X, s->nblocks_scan);
     s->mark();
-    k_sel_hist<1><<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
-    s->mark();
-    k_sel_final<<<sel_blocks, SEL_THREADS, 0, ctx->stream>>>(s->B, s->P);
-    s->mark();
-    k_alive_cut<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P, s->nblocks_scan);
-    s->mark();
-    k_resample_scatter<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P);
-    s->mark();
-    SMC_LAUNCHED(s, 5);
+    SMC_LAUNCHED(s, SEL_INSTANCES + 1);
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
 }
@@ -1336,6 +1519,8 @@ static int smc_ctrl_error(kabc_smc *s) {
     switch (s->h_ctrl->err) {
     case 0: return KABC_OK;
     case KABC_ERR_DEGENERATE: return set_error(KABC_ERR_DEGENERATE, "no alive particles left (ESS = 0): cannot resample");
+    case KABC_ERR_PEER: return set_error(KABC_ERR_PEER, "a rank of the job did not reach a cross-rank barrier in time");
+    case KABC_ERR_STATE: return set_error(KABC_ERR_STATE, "internal: the quantile selection lost track of its candidates");
     default: return set_error(s->h_ctrl->err, "prior sampling failed (truncation too extreme)");
     }
 }
@@ -1348,7 +1533,8 @@ static int smc_enqueue_iteration(kabc_smc *s) {
     for (long long r = 0; r < retry_n; ++r) {
         if (int rc = smc_enqueue_sweep(s, false)) return rc;
         if (r + 1 < retry_n) {
-            // ref :192 -- leave the retry loop as soon as enough moves were accepted
+            // ref :192 -- leave the retry loop as soon as enough moves were accepted (the counters are replicated, so
+            // every rank takes the same decision)
             if (int rc = smc_read_ctrl(s)) return rc;
             if (s->h_ctrl->err || s->h_ctrl->retry_done) break;
         }
@@ -1365,16 +1551,14 @@ static void smc_drop_graph(kabc_smc *s) {
 }
 
 // enqueue one iteration: through the captured graph when the launch sequence is fixed (no retry sweeps, which need the
-// host between sweeps; no NCCL row all-gather, whose buffers alternate), else kernel by kernel
+// host between sweeps), else kernel by kernel
 static int smc_launch_iteration(kabc_smc *s) {
     kabc_ctx *ctx = s->ctx;
     static const bool env_off = [] { const char *e = getenv("KABC_NO_GRAPH"); return e && e[0] == '1'; }();
-    const bool eligible = s->graph_ok && !env_off && !s->prof && s->P.mcmc_retrys == 0 &&
-                          s->model.kind != KABC_MODEL_GK_OCTILE && (ctx->world == 1 || s->p2p);
+    const bool eligible = s->graph_ok && !env_off && !s->prof && s->P.mcmc_retrys == 0;
     if (!eligible) return smc_enqueue_iteration(s);
     if (!s->iter_graph) {
         const long long l0 = s->launches, c0 = ctx->launches;
-        const int cur0 = s->cur;
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
         int rc = KABC_OK;
@@ -1383,7 +1567,7 @@ static int smc_launch_iteration(kabc_smc *s) {
             e = cudaStreamEndCapture(ctx->stream, &g);
         }
         s->graph_kernels = (int)(s->launches - l0);
-        s->launches = l0; ctx->launches = c0; s->cur = cur0; // nothing ran yet
+        s->launches = l0; ctx->launches = c0; // nothing ran yet
         if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&s->iter_graph, g, 0);
         if (g) cudaGraphDestroy(g);
         if (e != cudaSuccess || rc) { // capture not possible here: fall back for good
@@ -1395,11 +1579,15 @@ static int smc_launch_iteration(kabc_smc *s) {
     }
     KABC_CUDA_TRY(cudaGraphLaunch(s->iter_graph, ctx->stream));
     SMC_LAUNCHED(s, s->graph_kernels);
-    s->cur ^= 1;
     return KABC_OK;
 }
 
 extern "C" {
+
+uint64_t kabc_smc_arena_bytes(int64_t nparticles, int d, int world) {
+    if (world < 1 || nparticles < 1 || d < 1) return 0;
+    return (uint64_t)smc_xlayout((nparticles + world - 1) / world, d, world).bytes + 4096;
+}
 
 int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_model_t *model,
                     const kabc_smc_config_t *cfg, kabc_smc_t **out) {
@@ -1414,54 +1602,78 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     if (ctx->world > 1 && N % ctx->world) return set_error(KABC_ERR_INVALID_ARG, "nparticles must be a multiple of the number of ranks");
     KABC_CUDA_TRY(cudaSetDevice(ctx->device));
     kabc_smc *s = new kabc_smc();
+    const long long Pn = N / ctx->world;
     s->ctx = ctx; s->pri = pri; s->model = m; s->cfg = *cfg;
-    s->P.N = N; s->P.d = d; s->P.alpha = cfg->alpha; s->P.mcmc_tol = cfg->mcmc_tol; s->P.epstol = cfg->epstol;
+    s->P.N = N; s->P.P = Pn; s->P.lo = Pn * ctx->rank; s->P.d = d; s->P.TS = table_stride(d);
+    s->P.alpha = cfg->alpha; s->P.mcmc_tol = cfg->mcmc_tol; s->P.epstol = cfg->epstol;
     s->P.r_epstol = cfg->r_epstol; s->P.min_r_ess = cfg->min_r_ess; s->P.max_stretch = cfg->max_stretch;
+    s->P.sqrt_np = sqrt((double)d);
     s->P.mcmc_retrys = cfg->mcmc_retrys; s->P.max_iterations = cfg->max_iterations;
     s->P.rank = ctx->rank; s->P.world = ctx->world;
-    s->lo = N / ctx->world * ctx->rank;
-    s->hi = N / ctx->world * (ctx->rank + 1);
-    s->nblocks_scan = (int)((N + SCAN_THREADS - 1) / SCAN_THREADS);
-    const size_t nd = (size_t)N * d;
+    s->X = make_xpeer(ctx);
+    s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
+    s->fused = (m.kind != KABC_MODEL_LV_SSA && m.kind != KABC_MODEL_GK_OCTILE);
+    const size_t nd = (size_t)Pn * d;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    const size_t copy_elems = nd + 2 * (size_t)N; // [th | X | lpi]
-    // multi GPU: + the inbox of the packed pushes, 2 sweep parities x world sources x (N/world) records of d+3 doubles
-    if (ctx->world > 1) A(s->slab.alloc(2 * copy_elems + 2 * (size_t)N * (d + 3))); // peer-mapped slabs are not recycled
-    else A(s->slab.alloc(ctx, 2 * copy_elems));
-    A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, N));
-    A(s->alive.alloc(ctx, N)); A(s->work.alloc(ctx, N)); A(s->idxalive.alloc(ctx, N)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
-    A(s->hist.alloc(ctx, SEL_BINS)); A(s->cand.alloc(ctx, SEL_CAP)); A(s->ctrl.alloc(ctx, 1)); A(s->partial.alloc(ctx, ctx->world));
+    // peer-visible block: out of the context's arena (multi rank), else a plain cached buffer
+    const XLayout L = smc_xlayout(Pn, d, ctx->world);
+    memset(s->B.xb, 0, sizeof s->B.xb);
+    if (ctx->world > 1) {
+        size_t off = 0;
+        if (int rc = arena_alloc(ctx, L.bytes, &off)) { delete s; return rc; }
+        s->in_arena = true;
+        s->X = make_xpeer(ctx); // the arena may just have been (re)mapped
+        for (int r = 0; r < ctx->world; ++r) s->B.xb[r] = (unsigned char *)ctx->arena_map[r] + off;
+    } else {
+        A(s->xlocal.alloc(ctx, L.bytes));
+        s->B.xb[0] = s->xlocal.p;
+    }
+    s->B.o_th = (long long)L.o_th; s->B.o_X = (long long)L.o_X; s->B.o_lpi = (long long)L.o_lpi; s->B.o_alive = (long long)L.o_alive;
+    A(s->state.alloc(ctx, nd + 2 * (size_t)Pn));
+    if (!s->fused) { A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, Pn)); A(s->work.alloc(ctx, Pn)); }
+    A(s->alive.alloc(ctx, Pn)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
+    A(s->hist.alloc(ctx, SEL_BINS)); A(s->cand.alloc(ctx, SEL_CAP)); A(s->ctrl.alloc(ctx, 1));
     const long long log_cap = 1 << 14;
     A(s->log.alloc(ctx, log_cap));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_ctrl, sizeof(SmcCtrl));
     if (e != cudaSuccess) {
+        if (s->in_arena) arena_release(ctx);
         delete s;
         return set_error(KABC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
     memset(s->h_ctrl, 0, sizeof(SmcCtrl));
-    for (int c = 0; c < 2; ++c) {
-        s->B.th[c] = s->slab.p + (size_t)c * copy_elems;
-        s->B.X[c] = s->B.th[c] + nd;
-        s->B.lpi[c] = s->B.X[c] + N;
-    }
-    memset(s->B.peer, 0, sizeof s->B.peer);
-    s->B.n_peers = 0;
-    s->B.shard_rows = 0;
-    s->B.packed = 0;
-    s->B.inbox_off = 0;
-    s->B.alive = s->alive.p; s->B.thp = s->thp.p;
-    s->B.lpip = s->lpip.p; s->B.work = s->work.p; s->B.idxalive = s->idxalive.p; s->B.blockcnt = s->blockcnt.p;
-    s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p; s->B.partial = s->partial.p;
+    s->B.th = s->state.p; s->B.X = s->state.p + nd; s->B.lpi = s->B.X + Pn;
+    s->B.alive = s->alive.p; s->B.thp = s->thp.p; s->B.lpip = s->lpip.p; s->B.work = s->work.p;
+    s->B.blockcnt = s->blockcnt.p; s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p;
     s->B.log = s->log.p; s->B.log_cap = log_cap;
     memset(&s->B.tr, 0, sizeof s->B.tr);
     s->B.trace_on = 0;
-    KABC_CUDA_TRY(cudaMemsetAsync(s->ctrl.p, 0, sizeof(SmcCtrl), ctx->stream));
-    if (int rc = smc_attach_peers(s)) {
-        std::string keep = g_last_error;
+    cudaError_t e2 = cudaMemsetAsync(s->ctrl.p, 0, sizeof(SmcCtrl), ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->hist.p, 0, sizeof(unsigned int) * SEL_BINS, ctx->stream);
+    // launch geometry of the sweep
+    if (e2 == cudaSuccess && s->fused) {
+        sweep_fn_t fn = smc_sweep_fn(s);
+        s->sweep_smem = (size_t)QCAP * (8 + 8 + 8 * (size_t)d + 4);
+        if (s->sweep_smem > 48 * 1024) e2 = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sweep_smem);
+        int per_sm = 0;
+        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, SWEEP_THREADS, s->sweep_smem);
+        if (per_sm < 1) per_sm = 1;
+        const long long ntiles = (Pn + SWEEP_THREADS - 1) / SWEEP_THREADS, cap = (long long)ctx->sm_count * per_sm;
+        s->sweep_blocks = (int)(ntiles < cap ? ntiles : cap);
+    } else if (e2 == cudaSuccess && m.kind == KABC_MODEL_GK_OCTILE) {
+        const int smem = (int)gk_smem_bytes(m.n_draws, m.precision);
+        if (m.precision == KABC_F64) {
+            e2 = cudaFuncSetAttribute(k_smc_init_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        } else {
+            e2 = cudaFuncSetAttribute(k_smc_init_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_smc_simulate_gk<KABC_F32_ACC64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        }
+    }
+    if (e2 != cudaSuccess) {
         kabc_smc_destroy(s);
-        g_last_error = keep;
-        return rc;
+        return set_error(KABC_ERR_CUDA, "smc handle setup failed: %s", cudaGetErrorString(e2));
     }
     *out = s;
     return KABC_OK;
@@ -1472,7 +1684,7 @@ int kabc_smc_destroy(kabc_smc_t *s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     smc_drop_graph(s);
-    for (void *m : s->peer_maps) cudaIpcCloseMemHandle(m);
+    if (s->in_arena) arena_release(s->ctx);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     delete s;
     return KABC_OK;
@@ -1522,6 +1734,34 @@ int kabc_smc_iterate_n(kabc_smc_t *s, int n, int ignore_stop, int *done, float *
     return KABC_OK;
 }
 
+// n iterations, each preceded by an L2 flush (a memset of flush_bytes, outside the timed region), all enqueued without a
+// host round trip; out_ms[i] = device time of iteration i between two events on the launching stream
+int kabc_smc_bench_steps(kabc_smc_t *s, int n, uint64_t flush_bytes, float *out_ms) {
+    if (!s || n < 0 || !out_ms) return set_error(KABC_ERR_INVALID_ARG, "bad argument");
+    if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_smc_init must be called first");
+    kabc_ctx *ctx = s->ctx;
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
+    DevBuf<unsigned char> flush;
+    if (flush_bytes) KABC_CUDA_TRY(flush.alloc(ctx, (size_t)flush_bytes));
+    std::vector<cudaEvent_t> ev(2 * (size_t)n);
+    for (auto &e : ev) KABC_CUDA_TRY(cudaEventCreate(&e));
+    int rc = KABC_OK;
+    for (int it = 0; it < n && !rc; ++it) {
+        if (flush_bytes) KABC_CUDA_TRY(cudaMemsetAsync(flush.p, it & 0xff, (size_t)flush_bytes, ctx->stream));
+        KABC_CUDA_TRY(cudaEventRecord(ev[2 * it], ctx->stream));
+        rc = smc_launch_iteration(s);
+        KABC_CUDA_TRY(cudaEventRecord(ev[2 * it + 1], ctx->stream));
+    }
+    if (!rc) rc = smc_read_ctrl(s);
+    if (!rc) rc = smc_ctrl_error(s);
+    for (int it = 0; it < n; ++it) {
+        out_ms[it] = 0.f;
+        if (!rc) cudaEventElapsedTime(&out_ms[it], ev[2 * it], ev[2 * it + 1]);
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 int kabc_smc_profile_iteration(kabc_smc_t *s, float *out_us, int cap, int *out_n) {
     if (!s || !out_us || !out_n) return set_error(KABC_ERR_INVALID_ARG, "NULL argument");
     if (!s->inited) return set_error(KABC_ERR_STATE, "kabc_smc_init must be called first");
@@ -1545,34 +1785,53 @@ int kabc_smc_profile_iteration(kabc_smc_t *s, float *out_us, int cap, int *out_n
 
 int kabc_smc_get_state(kabc_smc_t *s, double *theta, double *X, double *lpi, uint8_t *alive) {
     if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
-    KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
-    const int cur = s->cur;
-    if (s->B.shard_rows && s->inited) {
-        // theta / lpi rows are only valid on their owner: assemble the full state (collective: every rank calls this)
-        if (int rc = smc_allgather_state(s, cur, true)) return rc;
-    }
+    kabc_ctx *ctx = s->ctx;
+    KABC_CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t N = (size_t)s->P.N;
-    cudaStream_t st = s->ctx->stream;
-    if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(theta, s->B.th[cur], 8 * N * s->P.d, cudaMemcpyDeviceToHost, st));
-    if (X) KABC_CUDA_TRY(cudaMemcpyAsync(X, s->B.X[cur], 8 * N, cudaMemcpyDeviceToHost, st));
-    if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(lpi, s->B.lpi[cur], 8 * N, cudaMemcpyDeviceToHost, st));
-    if (alive) KABC_CUDA_TRY(cudaMemcpyAsync(alive, s->B.alive, N, cudaMemcpyDeviceToHost, st));
+    const int d = s->P.d;
+    cudaStream_t st = ctx->stream;
+    if (ctx->world == 1) {
+        if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(theta, s->B.th, 8 * N * d, cudaMemcpyDeviceToHost, st));
+        if (X) KABC_CUDA_TRY(cudaMemcpyAsync(X, s->B.X, 8 * N, cudaMemcpyDeviceToHost, st));
+        if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(lpi, s->B.lpi, 8 * N, cudaMemcpyDeviceToHost, st));
+        if (alive) KABC_CUDA_TRY(cudaMemcpyAsync(alive, s->B.alive, N, cudaMemcpyDeviceToHost, st));
+        KABC_CUDA_TRY(cudaStreamSynchronize(st));
+        return KABC_OK;
+    }
+    // multi rank (collective: every rank calls this): every rank publishes its rows in its table, then reads all tables
+    DevBuf<double> g_th, g_X, g_lpi;
+    DevBuf<unsigned char> g_alive;
+    if (theta) KABC_CUDA_TRY(g_th.alloc(ctx, N * d));
+    if (X) KABC_CUDA_TRY(g_X.alloc(ctx, N));
+    if (lpi) KABC_CUDA_TRY(g_lpi.alloc(ctx, N));
+    if (alive) KABC_CUDA_TRY(g_alive.alloc(ctx, N));
+    k_compact<<<s->nblocks_scan, CUT_THREADS, 0, st>>>(s->B, s->P, s->X, 1, 1);
+    k_gather_full<<<ctx->sm_count * 4, 256, 0, st>>>(s->B, s->P, s->X, g_th.p, g_X.p, g_lpi.p, g_alive.p);
+    SMC_LAUNCHED(s, 2);
+    KABC_CUDA_TRY(cudaGetLastError());
+    if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(theta, g_th.p, 8 * N * d, cudaMemcpyDeviceToHost, st));
+    if (X) KABC_CUDA_TRY(cudaMemcpyAsync(X, g_X.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(lpi, g_lpi.p, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (alive) KABC_CUDA_TRY(cudaMemcpyAsync(alive, g_alive.p, N, cudaMemcpyDeviceToHost, st));
     KABC_CUDA_TRY(cudaStreamSynchronize(st));
-    return KABC_OK;
+    if (int rc = smc_read_ctrl(s)) return rc;
+    return smc_ctrl_error(s);
 }
 
 int kabc_smc_set_state(kabc_smc_t *s, const double *theta, const double *X, const double *lpi, const uint8_t *alive) {
     if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
-    const int cur = s->cur;
-    const size_t N = (size_t)s->P.N;
+    const size_t N = (size_t)s->P.N, Pn = (size_t)s->P.P, lo = (size_t)s->P.lo;
     cudaStream_t st = s->ctx->stream;
-    if (theta) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.th[cur], theta, 8 * N * s->P.d, cudaMemcpyHostToDevice, st));
-    if (X) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.X[cur], X, 8 * N, cudaMemcpyHostToDevice, st));
-    if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.lpi[cur], lpi, 8 * N, cudaMemcpyHostToDevice, st));
-    if (alive) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.alive, alive, N, cudaMemcpyHostToDevice, st));
-    k_recount<<<1, 1024, 0, st>>>(s->B, s->P.N);
-    SMC_LAUNCHED(s, 1);
+    if (theta)
+        for (int k = 0; k < s->P.d; ++k)
+            KABC_CUDA_TRY(cudaMemcpyAsync(s->B.th + (size_t)k * Pn, theta + (size_t)k * N + lo, 8 * Pn, cudaMemcpyHostToDevice, st));
+    if (X) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.X, X + lo, 8 * Pn, cudaMemcpyHostToDevice, st));
+    if (lpi) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.lpi, lpi + lo, 8 * Pn, cudaMemcpyHostToDevice, st));
+    if (alive) KABC_CUDA_TRY(cudaMemcpyAsync(s->B.alive, alive + lo, Pn, cudaMemcpyHostToDevice, st));
+    k_recount<<<1, 1024, 0, st>>>(s->B, s->P);
+    k_smc_post_init<<<1, 32, 0, st>>>(s->B, s->P, s->X, 1);
+    SMC_LAUNCHED(s, 2);
     KABC_CUDA_TRY(cudaStreamSynchronize(st));
     return KABC_OK;
 }
@@ -1612,6 +1871,7 @@ int64_t kabc_smc_kernel_launches(kabc_smc_t *s) { return s ? s->launches : -1; }
 
 int kabc_smc_trace_enable(kabc_smc_t *s, int on) {
     if (!s) return set_error(KABC_ERR_INVALID_ARG, "smc is NULL");
+    if (on && s->ctx->world > 1) return set_error(KABC_ERR_STATE, "the replay trace is a single-rank facility");
     KABC_CUDA_TRY(cudaSetDevice(s->ctx->device));
     KABC_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
     if (on && !s->ta.p) {
@@ -1619,8 +1879,9 @@ int kabc_smc_trace_enable(kabc_smc_t *s, int on) {
         KABC_CUDA_TRY(s->ta.alloc(N)); KABC_CUDA_TRY(s->tb.alloc(N)); KABC_CUDA_TRY(s->tz.alloc(N));
         KABC_CUDA_TRY(s->tlprob.alloc(N)); KABC_CUDA_TRY(s->tlpip.alloc(N)); KABC_CUDA_TRY(s->txp.alloc(N));
         KABC_CUDA_TRY(s->tdec.alloc(N));
+        if (!s->thp.p) { KABC_CUDA_TRY(s->thp.alloc(s->ctx, N * s->P.d)); s->B.thp = s->thp.p; }
         s->B.tr.a = s->ta.p; s->B.tr.b = s->tb.p; s->B.tr.z = s->tz.p; s->B.tr.lprob = s->tlprob.p;
-        s->B.tr.lpip = s->tlpip.p; s->B.tr.xp = s->txp.p; s->B.tr.dec = s->tdec.p; s->B.tr.thp = s->thp.p;
+        s->B.tr.lpip = s->tlpip.p; s->B.tr.xp = s->txp.p; s->B.tr.dec = s->tdec.p;
     }
     s->B.trace_on = on ? 1 : 0;
     smc_drop_graph(s); // the captured launches hold SmcBufs by value
@@ -1664,7 +1925,7 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
     } else if (!rc) {
         // One iteration is always queued AHEAD of the one whose `stop` flag the host is waiting for, so kernel
         // launches and the flag read-back overlap with device work.  The look-ahead iteration does nothing on the
-        // device when `stop` was set (smc_skip), and the host then takes its buffer flip back.
+        // device when `stop` was set (smc_skip).
         cudaStream_t st = ctx->stream;
         SmcCtrl *slots = nullptr;
         cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -1691,7 +1952,6 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
             const SmcCtrl &c = slots[k & 1];
             if (c.err || c.stop) {
                 cudaEventSynchronize(ev[(k + 1) & 1]); // the look-ahead iteration was skipped on the device
-                s->cur ^= 1;                             // ... so its host-side buffer flip is undone
                 break;
             }
         }
@@ -1702,6 +1962,9 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
         if (slots) cudaFreeHost(slots);
     }
     const double t3 = now();
+    double eps_out = 0;
+    long long it_out = 0, evals_out = 0;
+    if (!rc) { eps_out = s->h_ctrl->eps; it_out = s->h_ctrl->iteration; evals_out = (long long)s->h_ctrl->cost_evals; }
     if (!rc) rc = kabc_smc_get_state(s, out_theta, out_cost, nullptr, out_alive);
     if (!rc && out_theta) { // ref src/smc.jl:200: the returned particles are push_p(prior, .)
         const long long N = s->P.N;
@@ -1710,9 +1973,9 @@ int kabc_smc_run(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kabc_m
                 for (long long i = 0; i < N; ++i) out_theta[(long long)k * N + i] = nearbyint(out_theta[(long long)k * N + i]);
     }
     if (!rc) {
-        if (out_eps) *out_eps = s->h_ctrl->eps;
-        if (out_iterations) *out_iterations = s->h_ctrl->iteration;
-        if (out_cost_evals) *out_cost_evals = (int64_t)s->h_ctrl->cost_evals;
+        if (out_eps) *out_eps = eps_out;
+        if (out_iterations) *out_iterations = it_out;
+        if (out_cost_evals) *out_cost_evals = evals_out;
         if (log && log_cap > 0 && kabc_smc_get_log(s, log, log_cap) < 0) rc = set_error(KABC_ERR_CUDA, "log copy failed");
     }
     const double t4 = now();

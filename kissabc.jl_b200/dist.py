@@ -41,14 +41,31 @@ def broadcast_id(make_id: Callable[[], bytes], rank: int, device=None) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def make_context(seed: int, device_index: Optional[int] = None):
-    """Context for this process: single-GPU when WORLD_SIZE is 1, else a rank of a NCCL communicator.
-    torch.distributed must already be initialised when WORLD_SIZE > 1."""
+def gloo_exchange(group=None) -> Callable[[bytes], list]:
+    """all_gather(bytes) -> list[bytes] over torch.distributed (any backend that moves CPU objects)."""
+    import torch.distributed as dist
+
+    def ex(raw: bytes):
+        out = [None] * dist.get_world_size(group)
+        dist.all_gather_object(out, raw, group=group)
+        return out
+    return ex
+
+
+def make_context(seed: int, device_index: Optional[int] = None, arena_bytes: int = 0):
+    """Context for this process: single-GPU when WORLD_SIZE is 1, else a rank of the job.
+    torch.distributed must already be initialised when WORLD_SIZE > 1.  With the nccl backend the 128-byte NCCL id is
+    broadcast and the context exchanges its peer arena by itself; with any other backend (gloo: also several ranks on ONE
+    GPU) the arena handles travel through torch.distributed and `arena_bytes` must cover the largest handle
+    (kabc_smc_arena_bytes / kabc_ais_arena_bytes)."""
     from .api import Context
     rank, world, local = env_rank_world()
     dev = local if device_index is None else device_index
     if world == 1:
         return Context(device=dev, seed=seed)
     import torch
-    nid = broadcast_id(Context.nccl_unique_id, rank, device=torch.device("cuda", dev))
-    return Context(device=dev, seed=seed, rank=rank, world=world, nccl_id=nid)
+    import torch.distributed as dist
+    if dist.get_backend() == "nccl":
+        nid = broadcast_id(Context.nccl_unique_id, rank, device=torch.device("cuda", dev))
+        return Context(device=dev, seed=seed, rank=rank, world=world, nccl_id=nid)
+    return Context(device=dev, seed=seed, rank=rank, world=world, exchange=gloo_exchange(), arena_bytes=arena_bytes)

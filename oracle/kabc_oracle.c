@@ -799,7 +799,8 @@ static void smc_sweep(kor_smc_t *s, uint32_t e, int64_t lo, int64_t hi, int64_t 
         double lpip = kor_prior_logpdf(s->prior, d, thp);
         s->tlpip[i] = lpip;
         if (lpip < 0 && !isfinite(lpip)) { s->tdec[i] = 1; continue; }
-        double lM = fmin((lpip - s->lpi[i]) + 0.0, 0.0);
+        double dl = (lpip - s->lpi[i]) + 0.0;
+        double lM = dl != dl ? dl : fmin(dl, 0.0); /* Julia's min propagates NaN (C's fmin does not): `lprob < NaN` skips, ref :174-175 */
         if (!(s->tlprob[i] < lM)) { s->tdec[i] = 2; continue; }
         double Xp;
         if (s->override_xp) Xp = s->override_xp[i];

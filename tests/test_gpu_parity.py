@@ -226,6 +226,30 @@ def test_smc_f64_whole_run_bit_exact(oracle, kabc, ctx, name, N, cfg):
     assert any(r["resampled"] for r in dlog)
 
 
+@pytest.mark.parametrize("seed,alpha", [(51, 0.75), (64, 0.75), (51, 0.6), (78, 0.9)])
+def test_smc_flag_uses_the_current_minimum(oracle, kabc, seed, alpha):
+    """ref src/smc.jl:136: `flag` compares eps with minimum(Xs[alive]) of the CURRENT population.  With a discrete prior and a
+    deterministic cost the particle holding the minimum can move to a higher cost: a running minimum goes stale, the
+    `<=` branch is missed, every alive particle dies and the run degenerates (these seeds did, found with the oracle)."""
+    O, k = oracle, kabc
+    c2 = k.Context(device=0, seed=seed)
+    cfg = dict(nparticles=10, alpha=alpha, max_iterations=30)
+    osmc = O.Smc(seed, O.make_priors([("duniform", 0, 10)]), O.make_model(O.DETERMINISTIC, 0, target=(1.5,), param=(1.0,)), O.smc_config(**cfg))
+    dsmc = k.SmcSession(c2, k.Factored(k.DiscreteUniform(0, 10)), k.Deterministic(1, 1.5), k.smc_config(**cfg))
+    osmc.init(); dsmc.init()
+    flags = []
+    for it in range(30):
+        so, sd = osmc.iterate(), dsmc.iterate()
+        _compare_smc_state(osmc, dsmc, f"seed {seed} iteration {it + 1}")
+        flags.append(dsmc.scalars()["flag"])
+        assert so == sd
+        if so:
+            break
+    assert 1 in flags
+    dsmc.close()
+    c2.close()
+
+
 def test_smc_trace_matches_oracle(oracle, kabc, ctx):
     """Replay hook: partner indices, variates, proposals and per-particle decisions of one sweep."""
     cfg = dict(nparticles=3000, alpha=0.8, min_r_ess=0.3, max_iterations=10)
@@ -474,6 +498,21 @@ def test_abcde_pfilter_reference_style(kabc, ctx):
         kabc.ABCDE(pri, kabc.Deterministic(0, 1.5), 0.01, alpha=1.0, ctx=ctx)
     with pytest.raises(kabc.KissABCError):
         kabc.pfilter(pri, kabc.Deterministic(0, 1.5), 100, q=0.0, ctx=ctx)
+
+
+def test_ais_accept_errors_are_surfaced(kabc, ctx):
+    """ref src/types.jl:69-70: accept() raises "starting sample invalid." when the CURRENT state of the moving walker has a
+    non-finite log-density (reachable through set_state); the device reports it as KABC_ERR_STATE with the same message."""
+    prior = kabc.Factored(kabc.Uniform(1, 3), kabc.Truncated(kabc.Normal(0, 0.1), 0, 100))
+    a = kabc.AisSession(ctx, prior, kabc.NormalMeanStd(100, precision="f64"), kabc.ais_config(32, 1, scale=0.05))
+    a.init()
+    th, lp, ll = a.state()
+    ll[5] = -np.inf
+    a.set_state(th, lp, ll)
+    with pytest.raises(kabc.KissABCError) as ei:
+        a.sweep(1)
+    assert ei.value.code == 6 and str(ei.value) == "starting sample invalid."
+    a.close()
 
 
 def test_ais_errors(kabc, ctx):
