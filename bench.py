@@ -8,11 +8,17 @@ epsilon quantile -> alive cut -> resample -> propose -> simulate+distance -> acc
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload normal_smc|ma2_smc|gk_ais|lv_smc]
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference algorithm's CPU implementation (the C
-oracle restatement, all host threads) on a bounded sample of the same workload: Julia is not installed here.
+oracle restatement, all host threads) on the same workload: Julia is not installed here.
+
+Timing: the K timed steps are enqueued back to back on the library's stream, each preceded by an L2 flush (a 256 MiB
+device memset) that lies OUTSIDE the step's pair of CUDA events; `value` = evaluations of all ranks / max over ranks of the
+summed event times.  The roofline of the dominant kernel uses its own event-timed duration (kabc_smc_profile_iteration,
+warm) and the executed thread-instructions per evaluation MEASURED with ncu (profiles/instr_table.json).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -27,11 +33,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 SEED = 0x4B49535341424300
-# algorithmic thread-instructions per unit of work: SURVEY.md section 8(d), fixed table (do not re-tune per run)
-W_INSTR = {"normal_smc": 2.7e4, "ma2_smc": 3.0e3, "gk_ais": 6.7e5, "lv_smc": 52.0}
+# SURVEY.md section 8(d) pre-implementation estimate of the algorithmic thread-instructions per unit of work: only used when
+# profiles/instr_table.json has no MEASURED figure for the workload (the line then says so)
+W_SURVEY = {"normal_smc": 2.7e4, "ma2_smc": 3.0e3, "gk_ais": 6.7e5, "lv_smc": 52.0}
+WORKLOADS = list(W_SURVEY)
 # algorithmic state bytes per cost evaluation of an smc sweep at d parameters: 8(3d+1)+1 read, 8(d+2) written
 STATE_BYTES = lambda d: 8 * (3 * d + 1) + 1 + 8 * (d + 2)  # noqa: E731
 EPS_TARGET = {"normal_smc": 0.0111, "ma2_smc": 0.1, "lv_smc": None, "gk_ais": None}
+FLUSH_BYTES = 256 << 20  # > 126 MB L2
 
 
 def measured_peaks():
@@ -42,11 +51,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def traffic_bytes(name, prec):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture (profiles/ncu_top_kernels_r1.txt); None for workloads without a capture."""
-    if name == "normal_smc" and prec == "f32":
-        return 41.03e6 + 13.58e6
+def instr_table(name, prec):
+    """Executed thread-instructions per unit of work of the dominant kernel, measured with ncu (smsp__thread_inst_executed.sum
+    of one launch / units that launch processed), with the issue-slot and pipe utilisation and DRAM bytes of the same capture.
+    profiles/instr_table.json is written by scripts/ncu_instr_table.py and committed with the profile it comes from."""
+    p = os.path.join(ROOT, "profiles", "instr_table.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            t = json.load(f)
+        return t.get(f"{name}/{prec}")
     return None
 
 
@@ -111,16 +124,22 @@ def oracle_objects(O, name):
             O.make_model(O.LV_SSA, 0, LV_TARGET_X + LV_TARGET_Y, (50, 100, 30, 16, 20000)), 3)
 
 
-def cpu_baseline(name, budget_s=12.0, threads=None):
+# particles / walkers of the CPU legs.  The headline workload runs at the device arm's own size (2^20 particles: ~1.5 s of CPU
+# work per step on 16 threads); the heavier simulators run on a bounded sample, as the contract allows.
+REF_PARTICLES = {"normal_smc": 1 << 20, "ma2_smc": 1 << 20, "lv_smc": 1 << 13, "gk_ais": 1 << 10}
+
+
+def cpu_baseline(name, budget_s=14.0, threads=None):
     """The oracle (CPU restatement of the reference algorithm, FP64, OpenMP over particles exactly where the
     reference threads: src/smc.jl:122,168) timed on a bounded sample of the workload."""
     from oracle import oracle as O
     O.build()
     threads = threads or os.cpu_count() or 1
     pri, mod, d = oracle_objects(O, name)
+    n = REF_PARTICLES[name]
     if name == "gk_ais":
-        nw, sweeps = 256, 0
-        a = O.Ais(SEED, pri, mod, O.ais_config(nw, 1, scale=0.5), nthreads=threads)
+        sweeps = 0
+        a = O.Ais(SEED, pri, mod, O.ais_config(n, 1, scale=0.5), nthreads=threads)
         a.init()
         e0 = a.counters()["cost_evals"]
         t0 = time.perf_counter()
@@ -128,9 +147,8 @@ def cpu_baseline(name, budget_s=12.0, threads=None):
             a.sweep(); sweeps += 1
         dt = time.perf_counter() - t0
         evals = a.counters()["cost_evals"] - e0
-        return dict(value=evals / dt, unit="cost evals/s", cores=threads, kind="port",
-                    sample=f"oracle AIS({nw}) red/black sweeps of the g-and-k model for {dt:.1f}s ({sweeps} sweeps, {evals} evals), FP64, OpenMP")
-    n = {"normal_smc": 1 << 14, "ma2_smc": 1 << 16, "lv_smc": 1 << 11}[name]
+        return dict(value=evals / dt, unit="cost evals/s", cores=threads, kind="port", precision="f64",
+                    sample=f"oracle AIS({n}) red/black sweeps of the g-and-k model for {dt:.1f}s ({sweeps} sweeps, {evals} evals), FP64, OpenMP x{threads}")
     s = O.Smc(SEED, pri, mod, O.smc_config(nparticles=n), nthreads=threads)
     t0 = time.perf_counter()
     s.init()
@@ -139,17 +157,14 @@ def cpu_baseline(name, budget_s=12.0, threads=None):
         s.iterate(); its += 1
     dt = time.perf_counter() - t0
     evals = s.scalars()["cost_evals"]
-    return dict(value=evals / dt, unit="cost evals/s", cores=threads, kind="port",
-                sample=f"oracle smc, {n} particles, init + {its} iterations in {dt:.1f}s ({evals} evals), FP64, OpenMP x{threads}")
-
-
-REF_PARTICLES = {"normal_smc": 1 << 14, "ma2_smc": 1 << 16, "lv_smc": 1 << 11, "gk_ais": 256}
+    return dict(value=evals / dt, unit="cost evals/s", cores=threads, kind="port", precision="f64",
+                sample=f"oracle smc, {n} particles, init + {its} iterations in {dt:.1f}s ({evals} evals), FP64 (the device arm draws in FP32), OpenMP x{threads}")
 
 
 def run_reference(args):
     """Reference arm: the reference algorithm's CPU implementation (C oracle, all host threads) on the SAME step
-    definition as the device arm -- one smc iteration (or one AIS sweep) -- over a bounded sample of the workload
-    (REF_PARTICLES particles instead of 2^20).  W warm-up steps, then exactly K timed steps."""
+    definition as the device arm -- one smc iteration (or one AIS sweep) at the device arm's per-GPU population (2^20
+    particles for the headline workload).  W warm-up steps, then exactly K timed steps (fewer only if the time cap hits)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -158,7 +173,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     name = args.workload
     pri, mod, d = oracle_objects(O, name)
-    n = REF_PARTICLES[name]
+    n = REF_PARTICLES[name] if args.log2_particles is None else 1 << args.log2_particles
     t_all = time.perf_counter()
     if name == "gk_ais":
         obj = O.Ais(SEED, pri, mod, O.ais_config(n, 1, scale=0.5), nthreads=threads)
@@ -168,7 +183,7 @@ def run_reference(args):
         obj = O.Smc(SEED, pri, mod, O.smc_config(nparticles=n), nthreads=threads)
         obj.init()
         step, evals_now = obj.iterate, lambda: obj.scalars()["cost_evals"]
-    max_s = args.ref_budget * (args.steps + args.warmup) if args.ref_budget else 150.0
+    max_s = args.ref_budget * (args.steps + args.warmup) if args.ref_budget else 170.0
     for _ in range(args.warmup):
         step()
     e0, t0, done = evals_now(), time.perf_counter(), 0
@@ -178,16 +193,154 @@ def run_reference(args):
             break
     dt = time.perf_counter() - t0
     v = (evals_now() - e0) / dt
-    base = dict(value=v, unit="cost evals/s", cores=threads, kind="port",
-                sample=f"oracle, {n} particles/walkers, {done} timed steps in {dt:.1f}s, FP64, OpenMP x{threads}")
-    out = {"impl": "reference", "metric": "cost evals/sec", "value": v, "unit": "cost evals/s", "n_gpus": args.gpus,
+    same = (name in ("normal_smc", "ma2_smc")) and n == 1 << 20
+    base = dict(value=v, unit="cost evals/s", cores=threads, kind="port", precision="f64",
+                sample=f"oracle, {n} particles/walkers, {done} timed steps in {dt:.1f}s, FP64 (the device arm draws in FP32), OpenMP x{threads}")
+    out = {"impl": "reference", "metric": "cost evals/sec", "value": v, "unit": "cost evals/s", "n_gpus": 0, "gpus_arg": args.gpus,
            "steps": done, "warmup": args.warmup, "ms_per_step": dt / max(done, 1) * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": name, "particles": n,
-                      "note": "CPU restatement of the reference (C oracle), not Julia: julia is not installed"},
+           "config": {"workload": name, "particles_per_gpu": n, "particles_total": n, "same_config_as_device_arm_at_1_gpu": same,
+                      "note": "CPU restatement of the reference (C oracle, FP64, polynomial Box-Muller), not Julia: julia is not "
+                              "installed; at N > 1 GPUs the CPU arm still runs the per-GPU population"},
            "cpu_baseline": base, "e2e": {"value": v, "unit": "cost evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t_all}
     print(json.dumps(out))
+
+
+def state_digest(th, X, lpi, alive):
+    h = hashlib.sha256()
+    for a in (th, X, lpi):
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(alive, dtype=np.uint8).tobytes())
+    return h.hexdigest()
+
+
+def guard(k, ctx, world):
+    """Before anything is timed: a small smc run on ALL ranks of this job (F64 simulator, 2^14 particles, 6 iterations) must
+    reproduce, on every rank, the committed digest of the same run (tests/golden/bench_guard.json, generated on the CPU by the
+    oracle).  A multi-rank schedule that loses a row, a barrier or a counter cannot pass."""
+    with open(os.path.join(ROOT, "tests", "golden", "bench_guard.json")) as f:
+        g = json.load(f)
+    prior, cost = k.workloads.normal("f64", g["n_draws"])
+    s = k.SmcSession(ctx, prior, cost, k.smc_config(nparticles=g["nparticles"], max_iterations=g["iterations"]))
+    s.init()
+    for _ in range(g["iterations"]):
+        s.iterate()
+    th, X, lpi, alive = s.state()
+    sc = s.scalars()
+    s.close()
+    ok = (state_digest(th, X, lpi, alive) == g["sha256"] and sc["eps"] == g["eps"] and sc["cost_evals"] == g["cost_evals"]
+          and sc["accepted"] == g["accepted"])
+    return ok, {"ok": ok, "ranks": world, "particles": g["nparticles"], "iterations": g["iterations"], "eps": sc["eps"],
+                "sha256": g["sha256"][:16], "against": "tests/golden/bench_guard.json (CPU oracle)"}
+
+
+def roofline_of(name, prec, d, units, evals, ms_total, kernel_us, units_per_launch, sm_count, world, clocks, peaks, peak_src, is_ais):
+    """Issue roofline of the dominant kernel.  achieved = measured thread-instructions per unit x units one launch processes /
+    the kernel's event-timed duration; peak = SMs x 4 schedulers x 32 lanes x f_clk (sampled under load)."""
+    f_clk = ((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    r_issue = sm_count * 4 * 32 * f_clk  # one GPU: the kernel figures are per launch = per rank
+    t = instr_table(name, prec)
+    w = t["thread_inst_per_unit"] if t else W_SURVEY[name]
+    out = {"bound": "issue",
+           "kernel": "k_ais_simulate*" if is_ais else ("k_smc_simulate_lv / _gk" if name in ("lv_smc", "gk_ais") else "k_smc_sweep<model,precision> (fused propose + simulate + accept)"),
+           "unit": "T thread-instr/s (SM issue slots: SMs x 4 x 32 x f_clk at the sampled clock, one GPU)",
+           "peak": r_issue / 1e12, "w_instr_per_unit": w,
+           "w_source": (t["source"] if t else "SURVEY.md 8(d) pre-implementation estimate (no ncu capture of this workload yet)"),
+           "unit_of_work": "SSA event" if name == "lv_smc" else "cost eval"}
+    if kernel_us and units_per_launch:
+        ach = units_per_launch * w / (kernel_us * 1e-6)
+        out.update({"achieved": ach / 1e12, "frac": ach / r_issue, "kernel_us": kernel_us, "units_per_launch": units_per_launch})
+    else:
+        out.update({"achieved": None, "frac": None, "kernel_us": None})
+    ach_step = units * w / (ms_total * 1e-3) / world
+    out["frac_step"] = ach_step / r_issue  # the same work over the whole step (selection, cut, table, barriers included)
+    if t:
+        out.update({"issue_active": t.get("issue_active_pct"), "binding_pipe": t.get("binding_pipe"),
+                    "traffic": t.get("dram_bytes_per_launch"), "ncu_commit": t.get("commit")})
+    else:
+        out.update({"issue_active": None, "binding_pipe": None, "traffic": None})
+    hbm_bytes = evals * STATE_BYTES(d)
+    out["hbm"] = {"achieved": hbm_bytes / (ms_total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
+                  "frac": hbm_bytes / (ms_total * 1e-3) / 1e9 / (peaks["hbm_gbs"] * world), "peak_source": peak_src,
+                  "note": "state sweep bytes only: the path is instruction-bound, not HBM-bound (SURVEY.md 8d)"}
+    return out
+
+
+def time_workload(k, ctx, name, prec, n_per_gpu, world, steps, warmup, dist_mod, dev):
+    """W warm-up + K timed steps of one workload; returns the raw measurements (identical code for the headline and the extras)."""
+    import torch
+    prior, cost, d = workload_objects(k, name, prec)
+    N = n_per_gpu * world
+    is_ais = name == "gk_ais"
+    if is_ais:
+        sess = k.AisSession(ctx, prior, cost, k.ais_config(N, 1, scale=0.5))
+    else:
+        sess = k.SmcSession(ctx, prior, cost, k.smc_config(nparticles=N, epstol=0.0))
+    sess.init()
+
+    def evals_now():
+        return sess.counters()["cost_evals"] if is_ais else sess.scalars()["cost_evals"]
+
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev) if is_ais else None
+
+    def run(nsteps):
+        if not is_ais:
+            return sess.bench_steps(nsteps, FLUSH_BYTES)
+        ms = []
+        for _ in range(nsteps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms.append(sess.sweep(1))
+        return np.array(ms)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist_mod is not None:
+            dist_mod.barrier()
+        torch.cuda.synchronize()
+
+    run(warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()  # before the barrier: nothing of rank 0 sits between the barrier and the timed region
+    barrier()
+    l0, e0 = sess.kernel_launches(), evals_now()
+    ev0 = 0 if is_ais else sess.scalars()["events"]
+    t_wall0 = time.perf_counter()
+    ms = run(steps)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    evals = evals_now() - e0
+    launches = sess.kernel_launches() - l0
+    events = 0 if is_ais else sess.scalars()["events"] - ev0
+    ms_rank = float(ms.sum())
+    per_rank = [ms_rank]
+    if dist_mod is not None:
+        t = torch.tensor([ms_rank], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist_mod.all_gather(allr, t)
+        per_rank = [float(x.item()) for x in allr]
+    ms_total = max(per_rank)
+    # warm per-kernel times of a few more iterations: the dominant kernel's own event-timed duration
+    kernel_us, units_per_launch, ktimes = None, None, None
+    if not is_ais:
+        acc, n_prof = {}, 4
+        e1 = evals_now()
+        ev1 = sess.scalars()["events"]
+        for _ in range(n_prof):
+            for kk, v in sess.profile_iteration().items():
+                acc[kk] = acc.get(kk, 0.0) + v / n_prof
+        ktimes = {kk: round(v, 1) for kk, v in acc.items()}
+        kernel_us = acc.get("sweep", acc.get("simulate"))
+        per_launch_evals = (evals_now() - e1) / n_prof / world
+        units_per_launch = (sess.scalars()["events"] - ev1) / n_prof / world if name == "lv_smc" else per_launch_evals
+    sess.close()
+    return dict(d=d, N=N, is_ais=is_ais, evals=int(evals), events=int(events), launches=int(launches), ms_total=ms_total,
+                per_rank_ms=per_rank, wall=wall, clocks=clocks, kernel_us=kernel_us, units_per_launch=units_per_launch,
+                kernel_times_us=ktimes, prior=prior, cost=cost)
 
 
 def main():
@@ -196,11 +349,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="normal_smc", choices=list(W_INSTR))
+    ap.add_argument("--workload", default="normal_smc", choices=WORKLOADS)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--log2-particles", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the MA(2) / g-and-k / Lotka-Volterra sub-lines")
+    ap.add_argument("--no-guard", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=0.0, help="seconds of CPU work per reference step (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -223,74 +378,42 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     name = args.workload
-    prior, cost, d = workload_objects(k, name, args.precision)
     log2n = args.log2_particles or (18 if name == "gk_ais" else 20)
     n_per_gpu = 1 << log2n
-    N = n_per_gpu * world  # weak scaling: per-GPU work fixed
 
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(k.Context.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        ctx = k.Context(device=local_rank, seed=SEED, rank=rank, world=world, nccl_id=bytes(idt.cpu().numpy().tobytes()))
+        ctx = k.dist.make_context(SEED, device_index=local_rank)
     else:
         ctx = k.Context(device=local_rank, seed=SEED)
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # ---- guard: the N-rank schedule reproduces the committed single-rank result before anything is timed
+    guard_info = None
+    if not args.no_guard:
+        ok, guard_info = guard(k, ctx, world)
+        flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+        if dist is not None:
+            dist.all_reduce(flag)
+        if int(flag.item()) != 0:
+            if rank == 0:
+                print(json.dumps({"error": "multi-rank guard failed: the smc state of this job differs from the committed single-rank digest",
+                                  "guard": guard_info}))
+            sys.exit(3)
 
+    m = time_workload(k, ctx, name, args.precision, n_per_gpu, world, args.steps, args.warmup, dist, dev)
+    d, N, is_ais = m["d"], m["N"], m["is_ais"]
+    ms_total, evals, events = m["ms_total"], m["evals"], m["events"]
+    value = evals / (ms_total * 1e-3)  # the counters are global (folded over the ranks at every sweep)
+
+    # ---- end to end through the public API (host buffers in, host buffers out).  smc: a whole run to the target
+    # epsilon, every rank calls it (the call is collective), timed on the host as the max over ranks.
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    is_ais = name == "gk_ais"
-    if is_ais:
-        sess = k.AisSession(ctx, prior, cost, k.ais_config(N, 1, scale=0.5))
-    else:
-        sess = k.SmcSession(ctx, prior, cost, k.smc_config(nparticles=N, epstol=0.0))
-    sess.init()
-
-    def evals_now():
-        return sess.counters()["cost_evals"] if is_ais else sess.scalars()["cost_evals"]
-
-    def step():
-        flush.zero_()  # L2 flush between timed iterations (outside the event-timed region)
-        torch.cuda.synchronize()
-        if is_ais:
-            return sess.sweep(1)
-        return sess.iterate_n(1, ignore_stop=True)[1]
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0, e0 = sess.kernel_launches(), evals_now()
-    ev0 = 0 if is_ais else sess.scalars()["events"]
-    t_wall0 = time.perf_counter()
-    ms_total = 0.0
-    for _ in range(args.steps):
-        ms_total += step()
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    evals = evals_now() - e0
-    launches = sess.kernel_launches() - l0
-    events = 0 if is_ais else sess.scalars()["events"] - ev0
-
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    # with the replicated-state design every rank reports the same global counter
-    value = evals / (ms_total * 1e-3)
-
-    # ---- end to end through the public API (host buffers in, host buffers out).  smc: a whole run to the target
-    # epsilon, every rank calls it (the call is collective), timed on the host as the max over ranks.
     e2e = None
+    prior, cost = m["prior"], m["cost"]
     if not args.no_e2e and not is_ais:
         import ctypes as C
         eps_t = EPS_TARGET[name]
@@ -299,7 +422,6 @@ def main():
             kw["epstol"] = eps_t
         else:
             kw["max_iterations"] = 30
-        sess.close()  # give the buffers back to the context cache
         k.smc(prior, cost, **kw)  # warm the call path (allocations, lazy module load)
         barrier()
         t0 = time.perf_counter()
@@ -314,16 +436,35 @@ def main():
         d2h = N * (8 * d + 1 + 8) + 56 * res.iterations
         e2e = {"value": res.cost_evals / dt, "unit": "cost evals/s", "h2d_bytes_per_step": h2d / max(res.iterations, 1),
                "d2h_bytes_per_step": d2h / max(res.iterations, 1),
-               "call": "kissabc_jl_b200.smc(prior, cost, nparticles=N, epstol=target) on every rank",
+               "call": "kissabc_jl_b200.smc(prior, cost, nparticles=N, epstol=target) on every rank (every rank receives the whole result)",
                "iterations": res.iterations, "cost_evals": res.cost_evals, "eps": res.eps, "time_s": dt, "eps_target": eps_t}
-    elif not args.no_e2e and world == 1 and is_ais:
-        sess.close()
+    elif not args.no_e2e and is_ais:
         post = k.ApproxKernelizedPosterior(prior, cost, 0.5)
+        barrier()
         t0 = time.perf_counter()
         _, cnt = k.sample(post, k.AIS(N), N, ntransitions=2, ctx=ctx, return_counters=True)
+        barrier()
         dt = time.perf_counter() - t0
         e2e = {"value": cnt["cost_evals"] / dt, "unit": "cost evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": N * 8 * d,
                "call": "kissabc_jl_b200.sample(ApproxKernelizedPosterior(...), AIS(N), N, ntransitions=2)", "time_s": dt}
+
+    # ---- the other simulators of BASELINE.json in the same run (1 GPU): same timing code, fewer steps
+    extra = {}
+    peaks, peak_src = measured_peaks()
+    sm_count = ctx.sm_count()
+    if not args.no_extra and world == 1 and name == "normal_smc":
+        for wl, lg, st in (("ma2_smc", 20, 20), ("lv_smc", 20, 6), ("gk_ais", 18, 3)):
+            try:
+                x = time_workload(k, ctx, wl, "f32", 1 << lg, 1, st, 3, None, dev)
+                units = x["events"] if wl == "lv_smc" else x["evals"]
+                extra[wl] = {"value": x["evals"] / (x["ms_total"] * 1e-3), "unit": "cost evals/s", "ms_per_step": x["ms_total"] / st,
+                             "steps": st, "particles": x["N"], "gpu_launches": x["launches"], "kernel_times_us": x["kernel_times_us"],
+                             "roofline": roofline_of(wl, "f32", x["d"], units, x["evals"], x["ms_total"], x["kernel_us"], x["units_per_launch"],
+                                                     sm_count, 1, x["clocks"], peaks, peak_src, x["is_ais"])}
+                if wl == "lv_smc":
+                    extra[wl]["ssa_events_per_s"] = x["events"] / (x["ms_total"] * 1e-3)
+            except Exception as exc:  # an extra line must never take the headline down
+                extra[wl] = {"error": str(exc)[:300]}
 
     if rank != 0:
         if dist is not None:
@@ -331,42 +472,30 @@ def main():
             dist.destroy_process_group()
         return
 
-    peaks, peak_src = measured_peaks()
-    sm_count = ctx.sm_count()
-    f_clk = (clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
-    r_issue = sm_count * 4 * 32 * f_clk * world
     units = events if name == "lv_smc" else evals
-    achieved_instr = units * W_INSTR[name] / (ms_total * 1e-3)
-    hbm_bytes = evals * STATE_BYTES(d)
-    roofline = {
-        "bound": "issue", "kernel": "k_ais_simulate*" if is_ais else "k_smc_simulate<model,precision>",
-        "achieved": achieved_instr / 1e12, "peak": r_issue / 1e12, "unit": "T thread-instr/s (SM issue slots: SMs x 4 x 32 x f_clk at the sampled clock)",
-        "frac": achieved_instr / r_issue, "traffic": traffic_bytes(name, args.precision),
-        "w_instr_per_unit": W_INSTR[name], "unit_of_work": "SSA event" if name == "lv_smc" else "cost eval",
-        "hbm": {"achieved": hbm_bytes / (ms_total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
-                "frac": hbm_bytes / (ms_total * 1e-3) / 1e9 / (peaks["hbm_gbs"] * world), "peak_source": peak_src,
-                "note": "state sweep bytes only: the path is instruction-bound, not HBM-bound (SURVEY.md 8d)"},
-    }
+    roofline = roofline_of(name, args.precision, d, units, evals, ms_total, m["kernel_us"], m["units_per_launch"], sm_count, world,
+                           m["clocks"], peaks, peak_src, is_ais)
     out = {
         "metric": "cost evals/sec", "value": value, "unit": "cost evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 simulator draws, f64 state/distance/accept" if args.precision == "f32" else "f64",
         "data": "synthetic",
         "config": {"workload": name, "particles_per_gpu": n_per_gpu, "particles_total": N, "precision": args.precision,
-                   "l2": "flushed between timed steps (256 MiB write, outside the event-timed region)",
+                   "l2": "flushed before every timed step (256 MiB device memset on the same stream, outside the step's event pair)",
                    "step": "one AIS red/black sweep" if is_ais else "one smc iteration (quantile, cut, resample, propose, simulate, accept)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s_timed_region": wall,
-        "cost_evals_timed": int(evals),
+        "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": roofline, "kernel_times_us": m["kernel_times_us"],
+        "per_rank_ms_per_step": [x / args.steps for x in m["per_rank_ms"]], "wall_s_timed_region": m["wall"],
+        "cost_evals_timed": evals, "guard": guard_info,
     }
     if name == "lv_smc":
         out["ssa_events_per_s"] = events / (ms_total * 1e-3)
-
     if e2e is not None:
         out["e2e"] = e2e
         if "eps_target" in e2e:
             out["smc_time_to_eps_s"] = e2e["time_s"]
             out["eps_target"] = e2e["eps_target"]
-
+    if extra:
+        out["extra_workloads"] = extra
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(name)
     print(json.dumps(out))

@@ -45,7 +45,12 @@ void kor_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 /* stream = (seed ; block j, id, epoch, stream-tag); words are consumed in order */
-enum { ST_PRIOR = 1, ST_PROPOSE = 2, ST_COST = 3, ST_ACCEPT = 4, ST_COST_INIT = 5 };
+enum { ST_PRIOR = 1, ST_PROPOSE = 2, ST_COST = 3, ST_ACCEPT = 4, ST_COST_INIT = 5, ST_SERIAL = 6 };
+/* SERIAL mode (kor_smc_set_serial / kor_ais_set_serial): every variate of a run comes from ONE word stream
+ * (seed ; tag SERIAL, id 0, epoch 0), consumed in the order the REFERENCE consumes its single `rng` -- init draws of all
+ * particles, then all initial costs, then per sweep all proposals in particle order, then all costs in particle order
+ * (ref src/smc.jl:119-123,160-191).  julia/PhiloxRNG.jl implements the same word stream as an AbstractRNG, so that the
+ * unmodified KissABC.jl can be run on it and compared with this mode (julia/make_ref_fixtures.jl, tests/test_ref_fixtures.py). */
 typedef struct {
     uint32_t key[2], ctr[4], buf[4];
     int pos;
@@ -385,10 +390,10 @@ static double cost_normal(const kor_model_t *m, stream_t *s0, const double *th) 
     double z[4];
     double stackbuf[1024];
     double *x = n <= 1024 ? stackbuf : (double *)malloc(sizeof(double) * (size_t)n);
-    stream_t s = *s0;
+    stream_t *s = s0; /* the draws are consumed once and kept (two passes over x[]) */
     double sum = 0.0;
     for (int j = 0; j < n; j += 4) {
-        uint32_t w0 = next_u32(&s), w1 = next_u32(&s), w2 = next_u32(&s), w3 = next_u32(&s);
+        uint32_t w0 = next_u32(s), w1 = next_u32(s), w2 = next_u32(s), w3 = next_u32(s);
         kor_normal_pair(w0, w1, &z[0], &z[1]);
         kor_normal_pair(w2, w3, &z[2], &z[3]);
         for (int q = 0; q < 4 && j + q < n; ++q) {
@@ -599,21 +604,24 @@ static double cost_socks(const kor_model_t *m, stream_t *s, const double *th) {
     return fabs(pairs - m->target[0]) + fabs(odds - m->target[1]);
 }
 
+static double cost_on_stream(const kor_model_t *m, stream_t *s, const double *th) {
+    g_last_events = 0;
+    switch (m->kind) {
+    case KOR_MODEL_NORMAL_MEANSTD: return cost_normal(m, s, th);
+    case KOR_MODEL_MA2_AUTOCOV: return cost_ma2(m, s, th);
+    case KOR_MODEL_GK_OCTILE: return cost_gk(m, s, th);
+    case KOR_MODEL_LV_SSA: return cost_lv(m, s, th);
+    case KOR_MODEL_DETERMINISTIC: return cost_det(m, s, th);
+    case KOR_MODEL_SOCKS: return cost_socks(m, s, th);
+    }
+    return NAN;
+}
 static double cost_dispatch(const kor_model_t *m, uint64_t seed, uint32_t tag, int d, const double *th,
                             uint32_t id, uint32_t epoch) {
     (void)d;
     stream_t s;
     stream_init(&s, seed, tag, id, epoch);
-    g_last_events = 0;
-    switch (m->kind) {
-    case KOR_MODEL_NORMAL_MEANSTD: return cost_normal(m, &s, th);
-    case KOR_MODEL_MA2_AUTOCOV: return cost_ma2(m, &s, th);
-    case KOR_MODEL_GK_OCTILE: return cost_gk(m, &s, th);
-    case KOR_MODEL_LV_SSA: return cost_lv(m, &s, th);
-    case KOR_MODEL_DETERMINISTIC: return cost_det(m, &s, th);
-    case KOR_MODEL_SOCKS: return cost_socks(m, &s, th);
-    }
-    return NAN;
+    return cost_on_stream(m, &s, th);
 }
 double kor_cost(const kor_model_t *model, uint64_t seed, int d, const double *theta, uint32_t id, uint32_t epoch) {
     return cost_dispatch(model, seed, ST_COST, d, theta, id, epoch);
@@ -682,6 +690,8 @@ struct kor_smc {
     const double *override_xp;
     kor_smc_log_t *log;
     int64_t nlog, caplog;
+    int serial;   /* 1: one word stream in the reference's consumption order (see ST_SERIAL) */
+    stream_t ser;
 };
 
 int kor_smc_create(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model,
@@ -728,6 +738,11 @@ void kor_smc_destroy(kor_smc_t *s) {
     free(s->tdec); free(s->log); free(s);
 }
 void kor_smc_set_cost_override(kor_smc_t *s, const double *xp) { s->override_xp = xp; }
+void kor_smc_set_serial(kor_smc_t *s) {
+    s->serial = 1;
+    s->nthreads = 1;
+    stream_init(&s->ser, s->seed, ST_SERIAL, 0, 0);
+}
 
 /* ref: src/smc.jl:119-129 */
 int kor_smc_init(kor_smc_t *s) {
@@ -735,8 +750,21 @@ int kor_smc_init(kor_smc_t *s) {
     const int d = s->d;
     int bad = 0;
     int64_t events = 0;
+    if (s->serial) { /* ref :119-125: all prior draws, then all costs, on the one stream */
+        for (int64_t i = 0; i < N; ++i)
+            for (int k = 0; k < d; ++k) bad |= prior1_sample(&s->prior[k], &s->ser, &s->th[(int64_t)k * N + i]);
+        for (int64_t i = 0; i < N; ++i) {
+            double th[16];
+            for (int k = 0; k < d; ++k) th[k] = s->th[(int64_t)k * N + i];
+            kor_push_p(s->prior, d, th, th);
+            s->X[i] = cost_on_stream(&s->model, &s->ser, th);
+            events += g_last_events;
+            s->lpi[i] = kor_prior_logpdf(s->prior, d, th);
+            s->alive[i] = 1;
+        }
+    }
 #pragma omp parallel for schedule(dynamic, 64) num_threads(s->nthreads) reduction(| : bad) reduction(+ : events)
-    for (int64_t i = 0; i < N; ++i) {
+    for (int64_t i = s->serial ? N : 0; i < N; ++i) {
         double th[16];
         bad |= kor_prior_sample(s->seed, s->prior, d, (uint32_t)i, 0, th);
         for (int k = 0; k < d; ++k) s->th[(int64_t)k * N + i] = th[k];
@@ -774,8 +802,10 @@ static void smc_sweep(kor_smc_t *s, uint32_t e, int64_t lo, int64_t hi, int64_t 
         s->tz[i] = s->tlprob[i] = s->tlpip[i] = s->txp[i] = NAN;
         for (int k = 0; k < d; ++k) s->thp[(int64_t)k * N + i] = NAN;
         if (!s->alive[i]) continue;
-        stream_t st;
-        stream_init(&st, s->seed, ST_PROPOSE, (uint32_t)i, e);
+        stream_t st0, *stp = &st0;
+        if (s->serial) stp = &s->ser;
+        else stream_init(&st0, s->seed, ST_PROPOSE, (uint32_t)i, e);
+#define st (*stp)
         int64_t a = i, b = i;
         while (a == i) a = kor_index(next_u32(&st), (uint32_t)N);
         while (b == i || b == a) b = kor_index(next_u32(&st), (uint32_t)N);
@@ -786,6 +816,7 @@ static void smc_sweep(kor_smc_t *s, uint32_t e, int64_t lo, int64_t hi, int64_t 
             s->thp[(int64_t)k * N + i] = t[i] + (t[b] - t[a]) * sc;
         }
         s->tlprob[i] = kor_log(next_uniform(&st));
+#undef st
         s->ta[i] = a; s->tb[i] = b; s->tz[i] = z;
     }
     /* phase B (ref :168-191) */
@@ -805,7 +836,7 @@ static void smc_sweep(kor_smc_t *s, uint32_t e, int64_t lo, int64_t hi, int64_t 
         double Xp;
         if (s->override_xp) Xp = s->override_xp[i];
         else {
-            Xp = cost_dispatch(&s->model, s->seed, ST_COST, d, thp, (uint32_t)i, e);
+            Xp = s->serial ? cost_on_stream(&s->model, &s->ser, thp) : cost_dispatch(&s->model, s->seed, ST_COST, d, thp, (uint32_t)i, e);
             events += g_last_events;
         }
         evals += 1;
@@ -978,7 +1009,15 @@ struct kor_ais {
     int64_t *ta, *tb, *tc;
     double *tcorr, *thp, *tlpp, *tllp, *te;
     int64_t cost_evals, accepted, sweeps, retries;
+    int serial;   /* 1: one word stream in the reference's consumption order (see ST_SERIAL) */
+    stream_t ser;
+    int err;      /* accept() raised, ref src/types.jl:69-70: 1 "ld_correction is invalid", 2 "starting sample invalid." */
 };
+void kor_ais_set_serial(kor_ais_t *s) {
+    s->serial = 1;
+    s->nthreads = 1;
+    stream_init(&s->ser, s->seed, ST_SERIAL, 0, 0);
+}
 
 int kor_ais_create(uint64_t seed, const kor_prior_t *prior, int d, const kor_model_t *model,
                    const kor_ais_config_t *cfg, int nthreads, kor_ais_t **out) {
@@ -1019,7 +1058,7 @@ static void ais_loglike(kor_ais_t *s, const double *xraw, uint32_t tag, uint32_t
     double p = kor_prior_logpdf(s->prior, s->d, x);
     double l = s->cfg.posterior == 1 ? -p : p;
     if (isfinite(p)) {
-        double c = cost_dispatch(&s->model, s->seed, tag, s->d, x, id, epoch);
+        double c = s->serial ? cost_on_stream(&s->model, &s->ser, x) : cost_dispatch(&s->model, s->seed, tag, s->d, x, id, epoch);
         if (s->cfg.posterior == 1) l = c;
         else {
             double q = c / s->cfg.scale;
@@ -1043,8 +1082,29 @@ int kor_ais_init(kor_ais_t *s) {
     int64_t cap = budget + 1; /* per-walker retries beyond this always exhaust the budget */
     int64_t retries = 0, evals_total = 0;
     int bad = 0;
+    s->err = 0;
+    if (s->serial) { /* ref src/KissABC.jl:50-61 in its own order: all draws, all log-densities, then the retry loop walker by walker */
+        for (int64_t i = 0; i < N; ++i)
+            for (int k = 0; k < d; ++k) bad |= prior1_sample(&s->prior[k], &s->ser, &s->th[(int64_t)k * N + i]);
+        for (int64_t i = 0; i < N; ++i) {
+            double th[16];
+            int evals = 0;
+            for (int k = 0; k < d; ++k) th[k] = s->th[(int64_t)k * N + i];
+            ais_loglike(s, th, ST_COST_INIT, (uint32_t)i, 0, &s->lp[i], &s->ll[i], &evals);
+            evals_total += evals;
+        }
+        for (int64_t i = 0; i < N; ++i)
+            while (!ais_valid(s, s->lp[i], s->ll[i]) && retries <= budget) {
+                double th[16];
+                int evals = 0;
+                for (int k = 0; k < d; ++k) { bad |= prior1_sample(&s->prior[k], &s->ser, &th[k]); s->th[(int64_t)k * N + i] = th[k]; }
+                ais_loglike(s, th, ST_COST_INIT, (uint32_t)i, 0, &s->lp[i], &s->ll[i], &evals);
+                evals_total += evals;
+                retries += 1;
+            }
+    }
 #pragma omp parallel for schedule(dynamic, 16) num_threads(s->nthreads) reduction(+ : retries, evals_total) reduction(| : bad)
-    for (int64_t i = 0; i < N; ++i) {
+    for (int64_t i = s->serial ? N : 0; i < N; ++i) {
         double th[16], lp = 0, ll = 0;
         int evals = 0;
         int64_t t = 0;
@@ -1078,8 +1138,10 @@ static int64_t draw_idx(stream_t *st, int64_t lo, int64_t n) { return lo + (int6
 static int ais_transition_from(kor_ais_t *s, const double *src, int64_t i, int64_t lo, int64_t n, uint32_t epoch) {
     const int64_t N = s->N;
     const int d = s->d;
-    stream_t st;
-    stream_init(&st, s->seed, ST_PROPOSE, (uint32_t)i, epoch);
+    stream_t st0, *stp = &st0;
+    if (s->serial) stp = &s->ser;
+    else stream_init(&st0, s->seed, ST_PROPOSE, (uint32_t)i, epoch);
+#define st (*stp)
     double p[16], xi[16];
     for (int k = 0; k < d; ++k) xi[k] = src[(int64_t)k * N + i];
     double corr = 0.0;
@@ -1124,17 +1186,29 @@ static int ais_transition_from(kor_ais_t *s, const double *src, int64_t i, int64
             p[k] = xi[k] + W;
         }
     }
+#undef st
     double lpp, llp;
     int evals = 0;
     ais_loglike(s, p, ST_COST, (uint32_t)i, epoch, &lpp, &llp, &evals);
-    /* ref: src/types.jl:69-74 */
+    /* ref: src/types.jl:69-74.  accept() raises on a non-finite correction or an invalid CURRENT state before it looks at the
+     * proposal; the run is then void (kor_ais_sweep / run_* return the error) */
+    if (!isfinite(corr)) {
+#pragma omp critical
+        if (!s->err) s->err = 1;
+    } else if (!ais_valid(s, s->lp[i], s->ll[i])) {
+#pragma omp critical
+        if (!s->err) s->err = 2;
+    }
     int dec;
     double e = NAN;
     if (!ais_valid(s, lpp, llp)) dec = 0;
     else {
-        stream_t sa;
-        stream_init(&sa, s->seed, ST_ACCEPT, (uint32_t)i, epoch);
+        stream_t sa0, *sap = &sa0;
+        if (s->serial) sap = &s->ser;
+        else stream_init(&sa0, s->seed, ST_ACCEPT, (uint32_t)i, epoch);
+#define sa (*sap)
         e = next_exp(&sa);
+#undef sa
         if (s->cfg.posterior == 1) { /* ref: src/types.jl:101-103 */
             double lW = (corr + lpp) - s->lp[i];
             double lW2 = fmax(s->cfg.scale, s->ll[i]) - llp;
@@ -1174,6 +1248,7 @@ int kor_ais_sweep(kor_ais_t *s) {
 #pragma omp parallel for schedule(dynamic, 16) num_threads(s->nthreads)
     for (int64_t i = h; i < N; ++i) ais_transition_from(s, s->th, i, 0, h, e0 + 1);
     s->sweeps += 1;
+    if (s->err) return fail(s->err == 1 ? "ld_correction is invalid" : "starting sample invalid.");
     return 0;
 }
 

@@ -136,6 +136,9 @@ int kor_smc_sweep_commit(kor_smc_t *s, int64_t acc, int64_t evals, int64_t event
 int kor_smc_finish(kor_smc_t *s, int *stop);
 /* replay hook: costs for the NEXT sweeps are taken from xp[i] instead of simulated (NULL = off) */
 void kor_smc_set_cost_override(kor_smc_t *s, const double *xp);
+/* every variate from ONE word stream (seed; tag 6, id 0, epoch 0) in the reference's own consumption order: what the unmodified
+ * KissABC.smc consumes from julia/PhiloxRNG.jl (call before kor_smc_init) */
+void kor_smc_set_serial(kor_smc_t *s);
 void kor_smc_get_state(const kor_smc_t *s, double *theta_soa, double *X, double *lpi, uint8_t *alive);
 void kor_smc_set_state(kor_smc_t *s, const double *theta_soa, const double *X, const double *lpi, const uint8_t *alive);
 void kor_smc_get_scalars(const kor_smc_t *s, double *eps, int32_t *flag, int64_t *iteration, int64_t *n_alive,
@@ -158,6 +161,7 @@ int kor_ais_transition(kor_ais_t *s, int64_t i, int64_t cand_lo, int64_t cand_n,
 int kor_ais_sweep(kor_ais_t *s);
 /* whole runs: out_samples is SoA d x nsamples */
 int kor_ais_run_sequential(kor_ais_t *s, double *out_samples); /* reference schedule, KissABC.jl:66-80 */
+void kor_ais_set_serial(kor_ais_t *s); /* as kor_smc_set_serial, for kor_ais_init + kor_ais_transition (call before kor_ais_init) */
 int kor_ais_run_parallel(kor_ais_t *s, double *out_samples);   /* red/black schedule of the device path */
 void kor_ais_get_state(const kor_ais_t *s, double *theta_soa, double *lp, double *ll);
 void kor_ais_set_state(kor_ais_t *s, const double *theta_soa, const double *lp, const double *ll);

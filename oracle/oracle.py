@@ -132,6 +132,8 @@ def lib():
     L.kor_smc_sweep_commit.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.kor_smc_finish.argtypes = [vp, C.POINTER(C.c_int)]
     L.kor_smc_set_cost_override.argtypes = [vp, dp]
+    L.kor_smc_set_serial.argtypes = [vp]
+    L.kor_ais_set_serial.argtypes = [vp]
     L.kor_smc_get_state.argtypes = [vp, dp, dp, dp, u8p]
     L.kor_smc_set_state.argtypes = [vp, dp, dp, dp, u8p]
     L.kor_smc_get_scalars.argtypes = [vp, dp, C.POINTER(C.c_int32), i64p, i64p, i64p, i64p, i64p]
@@ -288,6 +290,10 @@ class Smc:
         except Exception:
             pass
 
+    def set_serial(self):
+        """one word stream in the reference's consumption order (julia/PhiloxRNG.jl replays); call before init()"""
+        self.L.kor_smc_set_serial(self.h)
+
     def init(self):
         if self.L.kor_smc_init(self.h):
             raise OracleError(self.L.kor_last_error().decode())
@@ -384,6 +390,9 @@ class Ais:
     def _chk(self, rc):
         if rc:
             raise OracleError(self.L.kor_last_error().decode())
+
+    def set_serial(self):
+        self.L.kor_ais_set_serial(self.h)
 
     def init(self):
         self._chk(self.L.kor_ais_init(self.h))

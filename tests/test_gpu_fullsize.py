@@ -17,15 +17,17 @@ def _type7(v_sorted, p):
     return a + g * (b - a) if np.isfinite(a) and np.isfinite(b) else (1.0 - g) * a + g * b
 
 
-@pytest.mark.parametrize("wl,cfg", [("normal_smc", dict()), ("ma2_smc", dict(alpha=0.7, min_r_ess=0.3))])
+# lv_smc = BASELINE.json config 5 at its full size (Lotka-Volterra SSA, 3 rates, 2^20 particles)
+@pytest.mark.parametrize("wl,cfg", [("normal_smc", dict()), ("ma2_smc", dict(alpha=0.7, min_r_ess=0.3)), ("lv_smc", dict())])
 def test_smc_iteration_properties_at_2_pow_20(kabc, ctx, wl, cfg):
     prior, cost = kabc.workloads.WORKLOADS[wl]("f32")
+    d = len(prior)
     alpha = cfg.get("alpha", 0.95)
     s = kabc.SmcSession(ctx, prior, cost, kabc.smc_config(nparticles=N, **cfg))
     s.trace_enable(True)
     s.init()
     th, X, lpi, alive = s.state()
-    assert alive.all() and th.shape == (2, N)
+    assert alive.all() and th.shape == (d, N)
     lp_dev = ctx.prior_logpdf(prior, th)
     assert (lp_dev.view(np.uint64) == lpi.view(np.uint64)).all()            # lpi = logpdf(prior, theta), ref :125
     evals = N
@@ -60,7 +62,7 @@ def test_smc_iteration_properties_at_2_pow_20(kabc, ctx, wl, cfg):
         assert (a[live] >= 0).all() and (a[live] < N).all() and (b[live] < N).all()
         # proposal arithmetic: theta_i + (theta_b - theta_a) * (max_stretch*z/sqrt(Np)), same operation order
         src = th0[:, idx]
-        scl = (2.0 * z[live]) / np.sqrt(2.0)
+        scl = (2.0 * z[live]) / np.sqrt(float(d))
         thp = src[:, live] + (src[:, b[live]] - src[:, a[live]]) * scl
         assert (thp.view(np.uint64) == tr["theta_p"][:, live].view(np.uint64)).all()
         # accept rule: Xp < eps (<= when flag); rows of accepted particles are the proposals, the others are the gathered rows
@@ -125,3 +127,55 @@ def test_ais_fullsize_sweep_properties(kabc, ctx):
     assert ((-t["e"][valid & first] <= lW[valid & first]) == acc[valid & first]).all()
     Z = np.exp(t["corr"][t["move"] == 1])
     assert (Z > 1 / 3 - 1e-9).all() and (Z < 3 + 1e-9).all()
+
+
+def test_gk_ais_fullsize_sweep_with_oracle_slice(oracle, kabc, ctx):
+    """BASELINE.json config 4 at its full size: g-and-k (4 parameters, 10^4 draws, octile distance), AIS with 2^18 walkers, one
+    red/black sweep.  Invariants of the whole ensemble from the device's own trace, plus 256 walkers re-evaluated by the
+    oracle: cost of the recorded proposal on the walker's own Philox stream (F32 tolerance) and the accept rule."""
+    import ctypes as C
+    from common import SEED, models
+    from test_gpu_parity import F32_TOL
+    O = oracle
+    Nw = 1 << 18
+    prior, cost = kabc.workloads.gk("f32")
+    scale = 0.5
+    a = kabc.AisSession(ctx, prior, cost, kabc.ais_config(Nw, 1, scale=scale))
+    a.trace_enable(True)
+    a.init()
+    th0, lp0, ll0 = a.state()
+    assert th0.shape == (4, Nw) and np.isfinite(lp0 + ll0).all()
+    a.sweep(1)
+    th, lp, ll = a.state()
+    t = a.trace()
+    cn = a.counters()
+    h = Nw // 2
+    i = np.arange(Nw)
+    comp_lo = np.where(i < h, h, 0)
+    for key, need in (("a", t["move"] >= 1), ("b", t["move"] >= 2), ("c", t["move"] == 3)):
+        p = t[key]
+        assert ((p[need] >= comp_lo[need]) & (p[need] < comp_lo[need] + h)).all()
+    frac = np.bincount(t["move"], minlength=4)[1:] / Nw
+    assert np.allclose(frac, [4 / 7, 2 / 7, 1 / 7], atol=0.005)
+    acc = t["decision"] == 2
+    valid = t["decision"] > 0
+    assert cn["cost_evals"] == Nw + int(np.isfinite(t["lp_p"]).sum())          # one evaluation per in-support proposal
+    assert cn["accepted"] == int(acc.sum()) and acc.sum() > 0
+    # accepted walkers hold their proposal, the others did not move
+    assert (np.where(acc, t["theta_p"], th0).view(np.uint64) == th.view(np.uint64)).all()
+    first = i < h
+    lW = (t["corr"] + (t["lp_p"] + t["ll_p"])) - (lp0 + ll0)
+    assert ((-t["e"][valid & first] <= lW[valid & first]) == acc[valid & first]).all()
+    # oracle slice: 256 walkers of the first colour whose proposal reached the simulator
+    M = models(O, kabc)["gk"]
+    m = M["omodel"]()
+    pick = np.nonzero(valid & first)[0][:: max(1, int((valid & first).sum()) // 256)][:256]
+    atol, rtol = F32_TOL["gk"]
+    for w in pick:
+        tp = np.ascontiguousarray(t["theta_p"][:, w])
+        c = O.lib().kor_cost(C.byref(m), SEED, 4, tp.ctypes.data_as(C.POINTER(C.c_double)), int(w), 0)  # epoch 0 = first half-step
+        ll_ref = -0.5 * (c / scale) ** 2
+        ll_dev = t["ll_p"][w]
+        c_dev = scale * np.sqrt(-2.0 * ll_dev)
+        assert abs(c_dev - c) <= atol + rtol * abs(c) + 1e-9, (w, c_dev, c)
+        assert np.isfinite(ll_ref)
