@@ -172,7 +172,7 @@ k_ais_init(AisBufs B, AisParams P, XPeer x, DPriors pri, DModel m, RoundKeys rk)
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, (PREC == KABC_F64 ? 1 : 3))
 k_ais_init_gk(AisBufs B, AisParams P, XPeer x, DPriors pri, DModel m, RoundKeys rk) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
     const AisOwn own = ais_own(P.N, P.rank, P.world);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) k_ais_simulate(AisBufs B, AisParams P, XP
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS) k_ais_simulate_gk(AisBufs B, AisParams P, XPeer x, DModel m, RoundKeys rk, int colour) {
+__global__ void __launch_bounds__(GK_THREADS, (PREC == KABC_F64 ? 1 : 3)) k_ais_simulate_gk(AisBufs B, AisParams P, XPeer x, DModel m, RoundKeys rk, int colour) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
     AisCtrl *ctl = B.ctrl;
     if (ctl->err == KABC_ERR_PEER) return;

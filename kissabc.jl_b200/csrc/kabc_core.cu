@@ -150,7 +150,7 @@ k_eval_cost(DModel m, RoundKeys rk, const double *__restrict__ th, long long n, 
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, (PREC == KABC_F64 ? 1 : 3))
 k_eval_cost_gk(DModel m, RoundKeys rk, const double *__restrict__ th, long long n, uint32_t first_id, uint32_t epoch,
                double *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
@@ -174,7 +174,7 @@ k_eval_cost_list(DModel m, RoundKeys rk, const double *__restrict__ th, long lon
     out[i] = cost_thread<KIND, PREC>(m, rk, tag, (uint32_t)i, epoch, [&](int k) { return th[(long long)k * N + i]; }, ev);
 }
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, (PREC == KABC_F64 ? 1 : 3))
 k_eval_cost_list_gk(DModel m, RoundKeys rk, const double *__restrict__ th, long long N, const unsigned int *__restrict__ list,
                     const unsigned int *__restrict__ count, uint32_t tag, uint32_t epoch, double *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char gk_smem[];

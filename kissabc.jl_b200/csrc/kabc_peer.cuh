@@ -66,7 +66,10 @@ __device__ __forceinline__ bool last_block(unsigned int *ticket, bool sys = fals
 
 // Cross-rank barrier, called by EVERY thread of ONE block per rank (blockDim.x >= world).  Returns false on timeout.
 __device__ __forceinline__ bool xbarrier(const XPeer &x) {
-    if (x.world == 1) return true;
+    if (x.world == 1) { // single rank: still a block-level barrier (callers read what other threads wrote before it)
+        __syncthreads();
+        return true;
+    }
     __shared__ int s_ok;
     __threadfence_system(); // this thread's pushes and local writes, before the arrival
     if (threadIdx.x == 0) s_ok = 1;

@@ -228,7 +228,7 @@ __global__ void k_smc_init_prior(SmcBufs B, SmcParams P, DPriors pri, RoundKeys 
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS)
+__global__ void __launch_bounds__(GK_THREADS, (PREC == KABC_F64 ? 1 : 3))
 k_smc_init_gk(SmcBufs B, SmcParams P, DModel m, RoundKeys rk) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
     const long long Pn = P.P;
@@ -550,7 +550,8 @@ __device__ void sel_publish_consume(SmcBufs &B, const SmcParams &P, const XPeer 
         int n = 0;
         for (int r = 0; r < P.world; ++r) {
             const XSlot *s = xslot(B, P, P.rank, set, r);
-            const int nr = (int)s->v[XV_COUNT];
+            const unsigned long long nr64 = s->v[XV_COUNT];
+            const int nr = nr64 > (unsigned long long)SEL_CAP ? SEL_CAP : (int)nr64;
             for (int q = threadIdx.x; q < nr; q += blockDim.x)
                 if (n + q < SEL_CAP) s_buf[n + q] = s->cand[q];
             n += nr;
@@ -1230,7 +1231,7 @@ __global__ void __launch_bounds__(256) k_smc_simulate_lv(SmcBufs B, SmcParams P,
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(GK_THREADS) k_smc_simulate_gk(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
+__global__ void __launch_bounds__(GK_THREADS, (PREC == KABC_F64 ? 1 : 3)) k_smc_simulate_gk(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
     extern __shared__ __align__(16) unsigned char gk_smem[];
     __shared__ unsigned int s_scan[GK_THREADS];
     __shared__ unsigned long long s_res[4];
@@ -1614,6 +1615,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
     s->fused = (m.kind != KABC_MODEL_LV_SSA && m.kind != KABC_MODEL_GK_OCTILE);
     const size_t nd = (size_t)Pn * d;
+    const size_t nd_pad = (nd + 1) & ~(size_t)1, pn_pad = ((size_t)Pn + 1) & ~(size_t)1; // X, lpi 16-byte aligned (double2 loads)
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     // peer-visible block: out of the context's arena (multi rank), else a plain cached buffer
@@ -1630,7 +1632,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
         s->B.xb[0] = s->xlocal.p;
     }
     s->B.o_th = (long long)L.o_th; s->B.o_X = (long long)L.o_X; s->B.o_lpi = (long long)L.o_lpi; s->B.o_alive = (long long)L.o_alive;
-    A(s->state.alloc(ctx, nd + 2 * (size_t)Pn));
+    A(s->state.alloc(ctx, nd_pad + 2 * pn_pad));
     if (!s->fused) { A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, Pn)); A(s->work.alloc(ctx, Pn)); }
     A(s->alive.alloc(ctx, Pn)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
     A(s->hist.alloc(ctx, SEL_BINS)); A(s->cand.alloc(ctx, SEL_CAP)); A(s->ctrl.alloc(ctx, 1));
@@ -1643,7 +1645,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
         return set_error(KABC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
     memset(s->h_ctrl, 0, sizeof(SmcCtrl));
-    s->B.th = s->state.p; s->B.X = s->state.p + nd; s->B.lpi = s->B.X + Pn;
+    s->B.th = s->state.p; s->B.X = s->state.p + nd_pad; s->B.lpi = s->B.X + pn_pad;
     s->B.alive = s->alive.p; s->B.thp = s->thp.p; s->B.lpip = s->lpip.p; s->B.work = s->work.p;
     s->B.blockcnt = s->blockcnt.p; s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p;
     s->B.log = s->log.p; s->B.log_cap = log_cap;

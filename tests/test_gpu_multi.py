@@ -28,7 +28,7 @@ def _launch(tmp_path, world, mode, name, prec, N, iters, retrys, backend, env_ex
            str(iters), str(retrys), backend]
     env = dict(os.environ)
     env.update(env_extra or {})
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
