@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(CUT_THREADS) k_cut(SmcBufs B, SmcParams P, XPe
 __global__ void __launch_bounds__(CUT_THREADS) k_compact(SmcBufs B, SmcParams P, XPeer x, int force_identity, int barrier) {
     __shared__ unsigned int s_w[33];
     SmcCtrl *c = B.ctrl;
-    if (smc_skip(c) || (!force_identity && c->retry_done)) return;
+    if (force_identity ? (c->err == KABC_ERR_PEER) : (smc_skip(c) || c->retry_done)) return; // get_state runs after `stop` too
     const int resample = force_identity ? 0 : c->resample;
     const long long Pn = P.P;
     const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
@@ -1130,7 +1130,7 @@ k_smc_sweep(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys rk
 
 // ------------------------------------------------------------------ work-list path (Lotka-Volterra, g-and-k)
 template <int DM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk) {
     __shared__ long long s_off[KABC_MAX_PEERS + 1];
     SmcCtrl *c = B.ctrl;
@@ -1166,6 +1166,33 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk) {
     __syncthreads();
     if (pass) B.work[s_base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)li;
     tally_flush(c, tl);
+}
+
+// thread-per-particle simulators over the work list (the sweep in two kernels: KABC_UNFUSED=1; kept to measure the fused
+// kernel against)
+template <int KIND, int PREC>
+__global__ void __launch_bounds__(256) k_smc_simulate_list(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
+    __shared__ unsigned int s_scan[256];
+    __shared__ unsigned long long s_res[4];
+    SmcCtrl *c = B.ctrl;
+    if (smc_skip(c) || c->retry_done) return;
+    const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nwork = c->work_count;
+    SweepTally tl;
+    if ((w & ~31u) < nwork && w < nwork) {
+        const long long li = B.work[w];
+        const long long Pn = P.P;
+        const double *thp = B.thp;
+        long long ev = 0;
+        const double Xold = B.X[li];
+        const double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), c->epoch, [&](int k) { return thp[(long long)k * Pn + li]; }, ev);
+        const bool ok = smc_accept(B, P, c->eps, c->flag, li, Xp, B.lpip[li], [&](int k) { return thp[(long long)k * Pn + li]; });
+        tl.work = 1;
+        tl.acc = ok ? 1u : 0u;
+        note_final(tl.f, B.hist, c->h_klo, c->h_khi, c->h_shift, ok ? Xp : Xold);
+    }
+    tally_flush(c, tl);
+    if (last_block(&c->tk_sim)) sweep_finish<256>(B, P, x, close_iter, s_scan, s_res);
 }
 
 // Lotka-Volterra sweep: persistent lanes.  Event counts per trajectory differ by orders of magnitude, so a lane whose
@@ -1382,6 +1409,15 @@ static XLayout smc_xlayout(long long P, int d, int world) {
 }
 
 template <int KIND>
+static void smc_launch_list_t(kabc_smc *s, int ci) {
+    const unsigned blocks = (unsigned)((s->P.P + 255) / 256);
+    if (s->model.precision == KABC_F64)
+        k_smc_simulate_list<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+    else
+        k_smc_simulate_list<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+}
+
+template <int KIND>
 static void smc_launch_init_t(kabc_smc *s) {
     const unsigned blocks = (unsigned)((s->P.P + 255) / 256);
     if (s->model.precision == KABC_F64)
@@ -1467,7 +1503,12 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
         SMC_LAUNCHED(s, 1);
     } else {
         const unsigned pb = (unsigned)((s->P.P + 255) / 256);
-        if (s->model.kind == KABC_MODEL_LV_SSA) {
+        if (s->model.kind == KABC_MODEL_NORMAL_MEANSTD || s->model.kind == KABC_MODEL_MA2_AUTOCOV) {
+            k_smc_propose<2><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+            s->mark();
+            if (s->model.kind == KABC_MODEL_NORMAL_MEANSTD) smc_launch_list_t<KABC_MODEL_NORMAL_MEANSTD>(s, ci);
+            else smc_launch_list_t<KABC_MODEL_MA2_AUTOCOV>(s, ci);
+        } else if (s->model.kind == KABC_MODEL_LV_SSA) {
             k_smc_propose<3><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
             s->mark();
             long long cap = (long long)ctx->sm_count * 8;
@@ -1614,6 +1655,10 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->X = make_xpeer(ctx);
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
     s->fused = (m.kind != KABC_MODEL_LV_SSA && m.kind != KABC_MODEL_GK_OCTILE);
+    {
+        const char *e = getenv("KABC_UNFUSED");
+        if (e && e[0] == '1' && (m.kind == KABC_MODEL_NORMAL_MEANSTD || m.kind == KABC_MODEL_MA2_AUTOCOV)) s->fused = false;
+    }
     const size_t nd = (size_t)Pn * d;
     const size_t nd_pad = (nd + 1) & ~(size_t)1, pn_pad = ((size_t)Pn + 1) & ~(size_t)1; // X, lpi 16-byte aligned (double2 loads)
     cudaError_t e = cudaSuccess;

@@ -72,7 +72,16 @@ mutable struct Context
         check(ccall((:kabc_ctx_create, LIB), Cint, (Cint, UInt64, Ref{Ptr{Cvoid}}), device, seed, r))
         c = new(r[]); finalizer(x -> ccall((:kabc_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c); c
     end
+    # one rank of a multi-GPU job (one process per GPU): `id` = the 128 bytes of nccl_unique_id() made by rank 0 and moved by
+    # the host (MPI.Bcast!, Distributed).  The context exchanges and maps its peer arena by itself.
+    function Context(rank::Integer, world::Integer, id::Vector{UInt8}; device=0, seed=UInt64(0x4B49535341424300))
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:kabc_ctx_create_dist, LIB), Cint, (Cint, UInt64, Cint, Cint, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+                    device, seed, rank, world, id, r))
+        c = new(r[]); finalizer(x -> ccall((:kabc_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c); c
+    end
 end
+nccl_unique_id() = (id = Vector{UInt8}(undef, 128); check(ccall((:kabc_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)
 const DEFAULT = Ref{Union{Nothing,Context}}(nothing)
 ctx() = (DEFAULT[] === nothing && (DEFAULT[] = Context()); DEFAULT[])
 
