@@ -281,7 +281,7 @@ __device__ __forceinline__ double prior1_logpdf(const DPrior &p, double x) {
     if (p.kind == KABC_PRIOR_UNIFORM) return (x >= p.p0 && x <= p.p1) ? -p.c0 : -dinf();
     if (p.kind == KABC_PRIOR_TRUNC_NORMAL && !(x >= p.lo && x <= p.hi)) return -dinf();
     double z = xdiv(xsub(x, p.p0), p.p1);
-    double base = xsub(xdiv(-xadd(xmul(z, z), KABC_LOG2PI), 2.0), p.c0);
+    double base = xsub(xmul(-xadd(xmul(z, z), KABC_LOG2PI), 0.5), p.c0); // x * 0.5 == x / 2 exactly
     return p.kind == KABC_PRIOR_NORMAL ? base : xsub(base, p.c1);
 }
 // ref src/priors.jl:30-36: left-to-right sum from component 1

@@ -74,7 +74,7 @@ struct SmcCtrl {
 
 struct SmcParams { // launch constants
     long long N, P, lo; // population, shard size, first global index of the shard
-    int d, TS;          // parameters, doubles per theta row of the table (d rounded up to 2 or 4 for vector loads)
+    int d, TS;          // parameters, doubles per row of the table: [theta_0..theta_{d-1} | X | lpi] padded to an even count
     double alpha, mcmc_tol, epstol, r_epstol, min_r_ess, max_stretch, sqrt_np;
     long long mcmc_retrys;
     int max_iterations;
@@ -91,9 +91,10 @@ struct SmcBufs {
     double *th, *X, *lpi; // state of the shard
     unsigned char *alive;
     // peer-visible block of every rank (arena + the handle's offset; the local buffer when G = 1):
-    //   XSlot[2][G] | tab_th[P][TS] | tab_X[P] | tab_lpi[P] | tab_alive[P]
+    //   XSlot[2][G] | rows[P][TS] (one AoS row per particle: theta, X, lpi -- a partner costs one 16/32-byte read, the own
+    //   row one 32/48-byte read) | tab_alive[P]
     unsigned char *xb[KABC_MAX_PEERS];
-    long long o_th, o_X, o_lpi, o_alive; // byte offsets of the table planes inside xb[r]
+    long long o_th, o_alive; // byte offsets of the rows and of the alive flags inside xb[r]
     double *thp, *lpip;                  // proposals [d][P] (work-list path and trace)
     unsigned int *work, *blockcnt, *hist;
     unsigned long long *cand;
@@ -108,8 +109,6 @@ __device__ __forceinline__ XSlot *xslot(const SmcBufs &B, const SmcParams &P, in
     return reinterpret_cast<XSlot *>(B.xb[r]) + set * P.world + src;
 }
 __device__ __forceinline__ const double *tab_th(const SmcBufs &B, int r) { return reinterpret_cast<const double *>(B.xb[r] + B.o_th); }
-__device__ __forceinline__ const double *tab_X(const SmcBufs &B, int r) { return reinterpret_cast<const double *>(B.xb[r] + B.o_X); }
-__device__ __forceinline__ const double *tab_lpi(const SmcBufs &B, int r) { return reinterpret_cast<const double *>(B.xb[r] + B.o_lpi); }
 
 // an iteration queued behind a stop (or after an error) must leave the state untouched
 __device__ __forceinline__ bool smc_skip(const SmcCtrl *c) { return c->err || (c->honor_stop && c->stop); }
@@ -173,6 +172,24 @@ __device__ __forceinline__ void note_final(FinalNote &f, unsigned int *hist, uns
     if (key < klo) f.below += 1;
     else if (key > khi) f.above += 1;
     else atomicAdd(&hist[(key - klo) >> shift], 1u);
+}
+
+// sweep constants + tallies of a sweep CTA in shared memory
+struct SweepShared {
+    long long off[KABC_MAX_PEERS + 1];
+    double eps;
+    unsigned long long hklo, hkhi, kmin;
+    unsigned int acc, work, below, above, tile;
+    unsigned int cnt[SWEEP_THREADS / 32];
+    int flag, hshift;
+    uint32_t epoch;
+};
+__device__ __forceinline__ void note_final_shared(SweepShared &sh, unsigned int *hist, double X) {
+    const unsigned long long key = dkey(X);
+    atomicMin(&sh.kmin, key);
+    if (key < sh.hklo) atomicAdd(&sh.below, 1u);
+    else if (key > sh.hkhi) atomicAdd(&sh.above, 1u);
+    else atomicAdd(&hist[(key - sh.hklo) >> sh.hshift], 1u);
 }
 
 // ------------------------------------------------------------------ init, ref src/smc.jl:119-129
@@ -747,8 +764,6 @@ __global__ void __launch_bounds__(CUT_THREADS) k_compact(SmcBufs B, SmcParams P,
     const long long Pn = P.P;
     const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
     double *t_th = reinterpret_cast<double *>(B.xb[P.rank] + B.o_th);
-    double *t_X = reinterpret_cast<double *>(B.xb[P.rank] + B.o_X);
-    double *t_lpi = reinterpret_cast<double *>(B.xb[P.rank] + B.o_lpi);
     unsigned char *t_alive = B.xb[P.rank] + B.o_alive;
     unsigned int a[4] = {0u, 0u, 0u, 0u};
     for (int q = 0; q < 4; ++q)
@@ -764,9 +779,15 @@ __global__ void __launch_bounds__(CUT_THREADS) k_compact(SmcBufs B, SmcParams P,
         if (li >= Pn) continue;
         if (resample && !a[q]) continue;
         const long long e = resample ? (long long)pos++ : li;
-        for (int k = 0; k < P.d; ++k) t_th[e * P.TS + k] = B.th[(long long)k * Pn + li];
-        t_X[e] = B.X[li];
-        t_lpi[e] = B.lpi[li];
+        double *row = t_th + e * P.TS;
+        if (P.d == 2) { // rows are 32 bytes: two 128-bit stores
+            reinterpret_cast<double2 *>(row)[0] = make_double2(B.th[li], B.th[Pn + li]);
+            reinterpret_cast<double2 *>(row)[1] = make_double2(B.X[li], B.lpi[li]);
+        } else {
+            for (int k = 0; k < P.d; ++k) row[k] = B.th[(long long)k * Pn + li];
+            row[P.d] = B.X[li];
+            row[P.d + 1] = B.lpi[li];
+        }
         if (!resample) t_alive[e] = (unsigned char)a[q];
     }
     if (resample)
@@ -865,18 +886,25 @@ template <int DM>
 struct Proposed {
     double thp[DM], lpip, Xi;
 };
+// theta of table row t (first d doubles of the row); own = true also returns X and lpi (doubles d and d+1)
 template <int DM>
-__device__ __forceinline__ void load_row(const double *t, long long e, int TS, int d, double (&row)[DM]) {
-    if (DM == 2) {
-        const double2 v = *reinterpret_cast<const double2 *>(t + e * 2);
+__device__ __forceinline__ void load_row(const double *t, int d, double (&row)[DM], bool own, double &X, double &lp) {
+    if (DM == 2 && d == 2) {
+        const double2 v = reinterpret_cast<const double2 *>(t)[0];
         row[0] = v.x; row[1] = v.y;
-    } else if (DM == 4 || DM == 3) {
-        const double2 v0 = *reinterpret_cast<const double2 *>(t + e * 4), v1 = *reinterpret_cast<const double2 *>(t + e * 4 + 2);
-        row[0] = v0.x; row[1] = v0.y; row[2] = v1.x;
-        if (DM == 4) row[DM - 1] = v1.y;
+        if (own) { const double2 w = reinterpret_cast<const double2 *>(t)[1]; X = w.x; lp = w.y; }
+    } else if (DM <= 4 && d >= 3) { // d = 3, 4: rows of 6 doubles
+        const double2 v0 = reinterpret_cast<const double2 *>(t)[0], v1 = reinterpret_cast<const double2 *>(t)[1];
+        row[0] = v0.x; row[1] = v0.y; row[2 % DM] = v1.x;
+        if (DM == 4) row[3 % DM] = v1.y;
+        if (own) {
+            const double2 v2 = reinterpret_cast<const double2 *>(t)[2];
+            if (d == 3) { X = v1.y; lp = v2.x; } else { X = v2.x; lp = v2.y; }
+        }
     } else {
 #pragma unroll
-        for (int k = 0; k < DM; ++k) row[k] = k < d ? t[e * TS + k] : 0.0;
+        for (int k = 0; k < DM; ++k) row[k] = k < d ? t[k] : 0.0;
+        if (own) { X = t[d]; lp = t[d + 1]; }
     }
 }
 template <int DM>
@@ -895,9 +923,8 @@ __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParam
     // the particle's own row after the (possible) resampling
     long long el;
     const int ro = locate(off, G, resample ? (long long)((unsigned int)i % (unsigned int)n_src) : i, el);
-    double row[DM];
-    load_row<DM>(tab_th(B, ro), el, P.TS, P.d, row);
-    const double Xi = tab_X(B, ro)[el], lpi_i = tab_lpi(B, ro)[el];
+    double row[DM], Xi = 0.0, lpi_i = 0.0, unused0, unused1;
+    load_row<DM>(tab_th(B, ro) + el * P.TS, P.d, row, true, Xi, lpi_i);
     const bool alive_i = resample ? true : (B.alive[li] != 0);
     if (resample) {
 #pragma unroll
@@ -917,8 +944,8 @@ __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParam
         const int ra = locate(off, G, resample ? (long long)((unsigned int)a % (unsigned int)n_src) : a, ea);
         const int rb = locate(off, G, resample ? (long long)((unsigned int)b % (unsigned int)n_src) : b, eb);
         double pa[DM], pb[DM];
-        load_row<DM>(tab_th(B, ra), ea, P.TS, P.d, pa);
-        load_row<DM>(tab_th(B, rb), eb, P.TS, P.d, pb);
+        load_row<DM>(tab_th(B, ra) + ea * P.TS, P.d, pa, false, unused0, unused1);
+        load_row<DM>(tab_th(B, rb) + eb * P.TS, P.d, pb, false, unused0, unused1);
         z = next_normal(st);
         const double sc = xdiv(xmul(P.max_stretch, z), P.sqrt_np);
 #pragma unroll
@@ -1019,23 +1046,6 @@ __device__ __forceinline__ void tally_flush(SmcCtrl *c, SweepTally &t) {
 // the other CTAs of the SM keep the issue slots busy with their simulations.
 // Everything a thread does not need inside the simulator's inner loop lives in shared memory (sweep constants, tallies):
 // the kernel's register budget is the simulator's, which is what sets the occupancy of the issue-bound phase.
-struct SweepShared {
-    long long off[KABC_MAX_PEERS + 1];
-    double eps;
-    unsigned long long hklo, hkhi, kmin;
-    unsigned int acc, work, below, above, tile;
-    unsigned int cnt[SWEEP_THREADS / 32];
-    int flag, hshift;
-    uint32_t epoch;
-};
-__device__ __forceinline__ void note_final_shared(SweepShared &sh, unsigned int *hist, double X) {
-    const unsigned long long key = dkey(X);
-    atomicMin(&sh.kmin, key);
-    if (key < sh.hklo) atomicAdd(&sh.below, 1u);
-    else if (key > sh.hkhi) atomicAdd(&sh.above, 1u);
-    else atomicAdd(&hist[(key - sh.hklo) >> sh.hshift], 1u);
-}
-
 // MINB: CTAs per SM the register allocation must allow (6 -> 40 registers, 5 -> 48; neither spills inside the
 // simulators' draw loops); chosen at run time (KABC_SWEEP_CTAS) so that both can be measured
 template <int KIND, int PREC, int DM, int MINB>
@@ -1168,30 +1178,64 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk) {
     tally_flush(c, tl);
 }
 
-// thread-per-particle simulators over the work list (the sweep in two kernels: KABC_UNFUSED=1; kept to measure the fused
-// kernel against)
-template <int KIND, int PREC>
-__global__ void __launch_bounds__(256) k_smc_simulate_list(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
+// Thread-per-particle simulators over the work list: persistent CTAs claim chunks of 256 / L work items from an atomic
+// head.  L > 1 (normal model, F32): L lanes of a warp share a particle's draws (cost_normal_f32_lanes), so a chunk is
+// 1/L of a per-thread round and the kernel's tail -- the time between the first and the last CTA running dry -- shrinks
+// with it (at L = 1 a round is a third of the whole kernel and the last wave is mostly idle lanes).
+template <int KIND, int PREC, int L>
+__global__ void __launch_bounds__(256, 6) k_smc_simulate_list(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
     __shared__ unsigned int s_scan[256];
     __shared__ unsigned long long s_res[4];
+    __shared__ SweepShared sh; // sweep constants and tallies live in shared memory: the register budget is the draw loop's
     SmcCtrl *c = B.ctrl;
     if (smc_skip(c) || c->retry_done) return;
-    const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr unsigned int PER = 256 / L;
+    if (threadIdx.x == 0) {
+        sh.eps = c->eps; sh.flag = c->flag; sh.epoch = c->epoch;
+        sh.hklo = c->h_klo; sh.hkhi = c->h_khi; sh.hshift = c->h_shift;
+        sh.kmin = ~0ull; sh.acc = 0; sh.work = 0; sh.below = 0; sh.above = 0;
+    }
     const unsigned int nwork = c->work_count;
-    SweepTally tl;
-    if ((w & ~31u) < nwork && w < nwork) {
-        const long long li = B.work[w];
+    const int sub = (int)(threadIdx.x % L);
+    unsigned long long events = 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh.tile = atomicAdd(&c->lv_head, 1u);
+        __syncthreads();
+        const unsigned int base = sh.tile * PER;
+        if (base >= nwork) break;
+        const unsigned int w = base + threadIdx.x / L;
+        const bool valid = w < nwork;
+        const long long li = valid ? (long long)B.work[w] : 0;
         const long long Pn = P.P;
         const double *thp = B.thp;
         long long ev = 0;
-        const double Xold = B.X[li];
-        const double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), c->epoch, [&](int k) { return thp[(long long)k * Pn + li]; }, ev);
-        const bool ok = smc_accept(B, P, c->eps, c->flag, li, Xp, B.lpip[li], [&](int k) { return thp[(long long)k * Pn + li]; });
-        tl.work = 1;
-        tl.acc = ok ? 1u : 0u;
-        note_final(tl.f, B.hist, c->h_klo, c->h_khi, c->h_shift, ok ? Xp : Xold);
+        double Xp;
+        if (L > 1)
+            Xp = cost_normal_f32_lanes<L>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch, pushk(m, 0, thp[li]), pushk(m, 1, thp[Pn + li]), sub, valid);
+        else
+            Xp = valid ? cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch, [&](int k) { return thp[(long long)k * Pn + li]; }, ev) : 0.0;
+        if (valid && sub == 0) {
+            const double Xold = B.X[li];
+            const bool ok = smc_accept(B, P, sh.eps, sh.flag, li, Xp, B.lpip[li], [&](int k) { return thp[(long long)k * Pn + li]; });
+            note_final_shared(sh, B.hist, ok ? Xp : Xold);
+            atomicAdd(&sh.work, 1u);
+            if (ok) atomicAdd(&sh.acc, 1u);
+            if (KIND == KABC_MODEL_LV_SSA) events += (unsigned long long)ev;
+        }
     }
-    tally_flush(c, tl);
+    __syncthreads();
+    if (KIND == KABC_MODEL_LV_SSA) {
+        events = warp_sum_u64(events);
+        if ((threadIdx.x & 31) == 0 && events) atomicAdd(&c->sw_events, events);
+    }
+    if (threadIdx.x == 0) {
+        if (sh.acc) atomicAdd(&c->sw_accepted, (unsigned long long)sh.acc);
+        if (sh.work) atomicAdd(&c->sw_work, (unsigned long long)sh.work);
+        if (sh.below) atomicAdd(&c->sw_below, (unsigned long long)sh.below);
+        if (sh.above) atomicAdd(&c->sw_above, (unsigned long long)sh.above);
+        if (sh.kmin != ~0ull) atomicMin(&c->sw_minkey, sh.kmin);
+    }
     if (last_block(&c->tk_sim)) sweep_finish<256>(B, P, x, close_iter, s_scan, s_res);
 }
 
@@ -1317,10 +1361,10 @@ __global__ void __launch_bounds__(256) k_gather_full(SmcBufs B, SmcParams P, XPe
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / P.P);
         const long long e = i - (long long)r * P.P;
-        const double *t = tab_th(B, r);
-        if (th) for (int k = 0; k < P.d; ++k) th[(long long)k * N + i] = t[e * P.TS + k];
-        if (X) X[i] = tab_X(B, r)[e];
-        if (lpi) lpi[i] = tab_lpi(B, r)[e];
+        const double *t = tab_th(B, r) + e * P.TS;
+        if (th) for (int k = 0; k < P.d; ++k) th[(long long)k * N + i] = t[k];
+        if (X) X[i] = t[P.d];
+        if (lpi) lpi[i] = t[P.d + 1];
         if (alive) alive[i] = (B.xb[r] + B.o_alive)[e];
     }
     if (P.world == 1) return;
@@ -1393,28 +1437,40 @@ static int smc_check_cfg(const kabc_smc_config_t *cfg, int d) {
 
 #define SMC_LAUNCHED(s, n) do { (s)->launches += (n); (s)->ctx->launches += (n); } while (0)
 
-static inline int table_stride(int d) { return d <= 2 ? 2 : (d <= 4 ? 4 : d); }
+static inline int table_stride(int d) { return (d + 2 + 1) & ~1; } // [theta | X | lpi], even: rows stay 16-byte aligned
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 // layout of the peer-visible block of a handle (identical on every rank)
-struct XLayout { size_t o_th, o_X, o_lpi, o_alive, bytes; };
+struct XLayout { size_t o_th, o_alive, bytes; };
 static XLayout smc_xlayout(long long P, int d, int world) {
     XLayout L;
     size_t o = align256(sizeof(XSlot) * 2 * (size_t)world);
     L.o_th = o; o += align256((size_t)P * table_stride(d) * 8);
-    L.o_X = o; o += align256((size_t)P * 8);
-    L.o_lpi = o; o += align256((size_t)P * 8);
     L.o_alive = o; o += align256((size_t)P);
     L.bytes = o;
     return L;
 }
 
+static int smc_list_lanes() { // lanes per particle of the normal model's F32 simulator (KABC_SIM_LANES = 1, 2, 4, 8)
+    static const int v = [] { const char *e = getenv("KABC_SIM_LANES"); int q = e ? atoi(e) : 4; return (q == 1 || q == 2 || q == 8) ? q : 4; }();
+    return v;
+}
 template <int KIND>
 static void smc_launch_list_t(kabc_smc *s, int ci) {
-    const unsigned blocks = (unsigned)((s->P.P + 255) / 256);
+    const bool coop = KIND == KABC_MODEL_NORMAL_MEANSTD && s->model.precision != KABC_F64;
+    const int L = coop ? smc_list_lanes() : 1;
+    const long long need = (s->P.P * L + 255) / 256, cap = (long long)s->ctx->sm_count * 6;
+    const unsigned blocks = (unsigned)(need < cap ? need : cap);
+    cudaStream_t st = s->ctx->stream;
     if (s->model.precision == KABC_F64)
-        k_smc_simulate_list<KIND, KABC_F64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+        k_smc_simulate_list<KIND, KABC_F64, 1><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+    else if (!coop || L == 1)
+        k_smc_simulate_list<KIND, KABC_F32_ACC64, 1><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+    else if (L == 2)
+        k_smc_simulate_list<KABC_MODEL_NORMAL_MEANSTD, KABC_F32_ACC64, 2><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+    else if (L == 4)
+        k_smc_simulate_list<KABC_MODEL_NORMAL_MEANSTD, KABC_F32_ACC64, 4><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
     else
-        k_smc_simulate_list<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+        k_smc_simulate_list<KABC_MODEL_NORMAL_MEANSTD, KABC_F32_ACC64, 8><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
 }
 
 template <int KIND>
@@ -1656,8 +1712,10 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
     s->fused = (m.kind != KABC_MODEL_LV_SSA && m.kind != KABC_MODEL_GK_OCTILE);
     {
-        const char *e = getenv("KABC_UNFUSED");
-        if (e && e[0] == '1' && (m.kind == KABC_MODEL_NORMAL_MEANSTD || m.kind == KABC_MODEL_MA2_AUTOCOV)) s->fused = false;
+        // the headline simulators run propose -> work list -> simulate (lanes) unless KABC_FUSED=1 asks for the fused sweep
+        const char *e = getenv("KABC_FUSED");
+        const bool want_fused = e && e[0] == '1';
+        if (!want_fused && (m.kind == KABC_MODEL_NORMAL_MEANSTD || m.kind == KABC_MODEL_MA2_AUTOCOV)) s->fused = false;
     }
     const size_t nd = (size_t)Pn * d;
     const size_t nd_pad = (nd + 1) & ~(size_t)1, pn_pad = ((size_t)Pn + 1) & ~(size_t)1; // X, lpi 16-byte aligned (double2 loads)
@@ -1676,7 +1734,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
         A(s->xlocal.alloc(ctx, L.bytes));
         s->B.xb[0] = s->xlocal.p;
     }
-    s->B.o_th = (long long)L.o_th; s->B.o_X = (long long)L.o_X; s->B.o_lpi = (long long)L.o_lpi; s->B.o_alive = (long long)L.o_alive;
+    s->B.o_th = (long long)L.o_th; s->B.o_alive = (long long)L.o_alive;
     A(s->state.alloc(ctx, nd_pad + 2 * pn_pad));
     if (!s->fused) { A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, Pn)); A(s->work.alloc(ctx, Pn)); }
     A(s->alive.alloc(ctx, Pn)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
