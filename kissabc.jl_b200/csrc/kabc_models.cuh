@@ -106,60 +106,6 @@ __device__ __forceinline__ double cost_normal_f32(const DModel &m, const RoundKe
     return sqrt(d1 * d1 + d2 * d2);
 }
 
-// The same F32 cost with the draws of ONE particle shared by L lanes of a warp (L = 2, 4, 8): lane `sub` of the group takes the
-// Philox blocks b = sub, sub + L, ... (block b -> draws 4b..4b+3, as everywhere), the partial sums are folded with xor
-// shuffles inside the group (every lane ends with the same bits) and every lane finishes the distance.  A 1000-draw particle
-// becomes L work items of 250/L blocks: the unit of scheduling of the sweep kernel shrinks L-fold, which is what keeps its
-// tail short (one round of the per-thread version is a third of the whole kernel).  Only the order of the FP32 additions
-// differs from cost_normal_f32.  valid = false: the lane takes part in the shuffles only (work items past the list's end).
-template <int L>
-__device__ __forceinline__ double cost_normal_f32_lanes(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
-                                                        uint32_t epoch, double mu, double sigma, int sub, bool valid) {
-    const int n = m.n_draws;
-    const int nbf = valid ? (n >> 2) : 0; // full blocks
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    float ps[2] = {0.f, 0.f}, pl[2] = {0.f, 0.f};
-    _Pragma(KABC_STR(unroll KABC_NORMAL_UNROLL))
-    for (int b = sub; b < nbf; b += L) {
-        uint32_t w0, w1, w2, w3;
-        philox4x32_10(rk, (uint32_t)b, id, epoch, tag, w0, w1, w2, w3);
-        normal_pair_sums32(w0, w1, ps[0], pl[0]);
-        normal_pair_sums32(w2, w3, ps[1], pl[1]);
-    }
-    if (valid && (n & 3) && sub == 0) {
-        uint32_t w0, w1, w2, w3;
-        philox4x32_10(rk, (uint32_t)(n >> 2), id, epoch, tag, w0, w1, w2, w3);
-        float z[4];
-        normal_pair32(w0, w1, z[0], z[1]);
-        normal_pair32(w2, w3, z[2], z[3]);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q < (n & 3)) {
-                s1[q] = __fadd_rn(s1[q], z[q]);
-                s2[q] = __fmaf_rn(z[q], z[q], s2[q]);
-            }
-    }
-    float a = __fadd_rn(ps[0], ps[1]), bsum = __fadd_rn(pl[0], pl[1]);
-    float c1 = __fadd_rn(__fadd_rn(s1[0], s1[1]), s1[2]), c2 = __fadd_rn(__fadd_rn(s2[0], s2[1]), s2[2]);
-#pragma unroll
-    for (int o = 1; o < L; o <<= 1) {
-        a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
-        bsum = __fadd_rn(bsum, __shfl_xor_sync(0xffffffffu, bsum, o));
-        c1 = __fadd_rn(c1, __shfl_xor_sync(0xffffffffu, c1, o));
-        c2 = __fadd_rn(c2, __shfl_xor_sync(0xffffffffu, c2, o));
-    }
-    const double S1 = 1.6651092223153954 * (double)a + (double)c1;
-    const double S2 = -1.3862943611198906 * (double)bsum + (double)c2;
-    const double dn = (double)n;
-    const double mean = mu + sigma * (S1 / dn);
-    double var = (S2 - S1 * S1 / dn) / (double)(n - 1);
-    if (var < 0.0) var = 0.0;
-    const double sd = fabs(sigma) * sqrt(var);
-    const double d1 = mean - m.target[0];
-    const double d2 = (sd - m.target[1]) * m.param[0];
-    return sqrt(d1 * d1 + d2 * d2);
-}
-
 // ------------------------------------------------------------------ MA(2), SURVEY.md Appendix B
 // y_t = e_{t+2} + th1 e_{t+1} + th2 e_t ; tau_j = (1/n) sum_{t>=j} y_t y_{t-j} ; || tau - target ||_2
 __device__ __forceinline__ bool ma2_in_triangle(double t1, double t2) {

@@ -5,11 +5,9 @@
 //                                        WRITERS of X during the previous sweep, so the usual iteration needs one pass
 //   alive cut, flag, ESS      :135-142   k_cut
 //   cyclic-tiling resample    :145-153   k_cut (decision + scan), k_compact (table of the surviving rows)
-//   propose                   :160-167 } k_smc_sweep: ONE persistent kernel per sweep; a CTA alternates between proposing a
-//   prior-MH pre-test         :172-175 } tile of 256 particles (gathers through the resampling map, latency bound) and
-//   simulate + accept         :176-189 } simulating 256 queued survivors (issue bound), so that the two phases of different
-//                                        CTAs overlap on every SM and every simulating warp is full.
-//                                        (Lotka-Volterra / g-and-k: k_smc_propose -> work list -> k_smc_simulate_lv / _gk)
+//   propose                   :160-167   k_smc_propose  (phase A: own row through the resampling map, partners, proposal;
+//   prior-MH pre-test         :172-175    + prior tests; builds the work list)
+//   simulate + accept         :176-189   k_smc_simulate_list / _lv / _gk  (phase B over the work list: every warp full)
 //   retry / stop rules        :156-159,192-198   post_sweep()/post_iter() run by the LAST block of the sweep kernel
 // Every scalar that steers control flow lives in SmcCtrl in device memory; the host only reads `stop`.
 //
@@ -17,8 +15,8 @@
 // their state: th[k*P + li] (SoA FP64), X[li], lpi[li], alive[li].  Before every sweep the owner writes the rows a sweep
 // may READ into its TABLE -- the surviving rows compacted in index order when the iteration resamples (the j-th alive
 // particle of the population is entry j - off[r] of rank r's table, off = exclusive scan of the per-rank alive counts),
-// all rows otherwise -- in the rank's peer arena (kabc_peer.cuh), theta as one AoS row per particle so that a partner
-// costs one 16/32-byte read.  The sweep reads rows only through the table of their owner (NVLink peer loads for the
+// all rows otherwise -- in the rank's peer arena (kabc_peer.cuh), one AoS row [theta | X | lpi] per particle so that a
+// partner costs one 16/32-byte read and the own row one 32/48-byte read.  The sweep reads rows only through the table of their owner (NVLink peer loads for the
 // other ranks): its own row idx[i] = idxalive[i mod n_alive] (the reference's cyclic tiling, :146-147) and the two
 // partners a, b (:163-164); it writes only the state of its own shard.  So a rank receives O(P) rows per sweep whatever
 // G is, the quantile / cut / scan work on the shard only, and the ranks meet in four flag barriers per iteration
@@ -38,8 +36,6 @@ constexpr int SEL_THREADS = 512;
 constexpr int SEL_INSTANCES = 3;   // k_sel launches per iteration; whatever is left is finished by one block (rare)
 constexpr int SCAN_THREADS = 1024; // particles per block of the cut / compact kernels
 constexpr int CUT_THREADS = 256;
-constexpr int SWEEP_THREADS = 256;
-constexpr int QCAP = 2 * SWEEP_THREADS; // survivor queue of a sweep CTA
 
 enum { SEL_HIST = 0, SEL_CAND = 1, SEL_KEYS = 2, SEL_FINAL = 3 };
 
@@ -180,7 +176,6 @@ struct SweepShared {
     double eps;
     unsigned long long hklo, hkhi, kmin;
     unsigned int acc, work, below, above, tile;
-    unsigned int cnt[SWEEP_THREADS / 32];
     int flag, hshift;
     uint32_t epoch;
 };
@@ -1039,106 +1034,7 @@ __device__ __forceinline__ void tally_flush(SmcCtrl *c, SweepTally &t) {
     }
 }
 
-// ------------------------------------------------------------------ the fused sweep (thread-per-particle simulators)
-// Persistent CTAs pull tiles of 256 particles.  Propose phase: one particle per thread; proposals that pass the prior
-// tests are queued in shared memory (block scan).  As soon as 256 are queued the CTA simulates them, one per thread, all
-// warps full; the remainder is flushed when the tiles run out.  A CTA in its propose phase waits on (peer) gathers while
-// the other CTAs of the SM keep the issue slots busy with their simulations.
-// Everything a thread does not need inside the simulator's inner loop lives in shared memory (sweep constants, tallies):
-// the kernel's register budget is the simulator's, which is what sets the occupancy of the issue-bound phase.
-// MINB: CTAs per SM the register allocation must allow (6 -> 40 registers, 5 -> 48; neither spills inside the
-// simulators' draw loops); chosen at run time (KABC_SWEEP_CTAS) so that both can be measured
-template <int KIND, int PREC, int DM, int MINB>
-__global__ void __launch_bounds__(SWEEP_THREADS, MINB)
-k_smc_sweep(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys rk, int close_iter) {
-    extern __shared__ __align__(16) unsigned char q_raw[];
-    __shared__ SweepShared sh;
-    __shared__ unsigned int s_scan[SWEEP_THREADS];
-    __shared__ unsigned long long s_res[4];
-    SmcCtrl *c = B.ctrl;
-    if (smc_skip(c) || c->retry_done) return;
-    // queue planes: Xi[QCAP] | lpip[QCAP] | thp[d][QCAP] | li[QCAP]
-    double *q_x = reinterpret_cast<double *>(q_raw);
-    double *q_lp = q_x + QCAP;
-    double *q_th = q_lp + QCAP;
-    unsigned int *q_li = reinterpret_cast<unsigned int *>(q_th + (size_t)P.d * QCAP);
-    if (threadIdx.x <= P.world) sh.off[threadIdx.x] = c->off[threadIdx.x];
-    if (threadIdx.x == 0) {
-        sh.eps = c->eps; sh.flag = c->flag; sh.epoch = c->epoch;
-        sh.hklo = c->h_klo; sh.hkhi = c->h_khi; sh.hshift = c->h_shift;
-        sh.kmin = ~0ull; sh.acc = 0; sh.work = 0; sh.below = 0; sh.above = 0;
-    }
-    const long long ntiles = (P.P + SWEEP_THREADS - 1) / SWEEP_THREADS;
-    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int qn = 0; // queued survivors (uniform across the CTA)
-    bool more = true;
-    __syncthreads();
-    while (more || qn > 0) {
-        if (more) {
-            if (threadIdx.x == 0) sh.tile = atomicAdd(&c->tile_head, 1u);
-            __syncthreads();
-            const long long tile = sh.tile;
-            if (tile >= ntiles) more = false;
-            else {
-                const long long li = tile * SWEEP_THREADS + threadIdx.x;
-                Proposed<DM> pr;
-                bool pass = false, alive_i = false;
-                if (li < P.P) {
-                    pass = smc_propose_one<DM>(B, P, c, pri, rk, sh.off, li, pr, alive_i);
-                    if (alive_i && !pass) note_final_shared(sh, B.hist, pr.Xi);
-                }
-                const unsigned int ball = __ballot_sync(0xffffffffu, pass);
-                if (lane == 0) sh.cnt[warp] = __popc(ball);
-                __syncthreads();
-                unsigned int before = 0, tot = 0;
-#pragma unroll
-                for (int w = 0; w < SWEEP_THREADS / 32; ++w) {
-                    const unsigned int v = sh.cnt[w];
-                    before += (w < (int)warp) ? v : 0u;
-                    tot += v;
-                }
-                if (pass) {
-                    const unsigned int at = qn + before + __popc(ball & ((1u << lane) - 1u));
-                    q_li[at] = (unsigned int)li;
-                    q_x[at] = pr.Xi;
-                    q_lp[at] = pr.lpip;
-#pragma unroll
-                    for (int k = 0; k < DM; ++k)
-                        if (k < P.d) q_th[(size_t)k * QCAP + at] = pr.thp[k];
-                }
-                qn += tot;
-            }
-            __syncthreads();
-        }
-        if (qn >= SWEEP_THREADS || (!more && qn > 0)) {
-            const unsigned int take = qn < (unsigned)SWEEP_THREADS ? qn : (unsigned)SWEEP_THREADS;
-            const unsigned int at = qn - take + threadIdx.x;
-            if (threadIdx.x < take) {
-                const long long li = q_li[at];
-                long long ev = 0;
-                const double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch,
-                                                          [&](int k) { return q_th[(size_t)k * QCAP + at]; }, ev);
-                const bool ok = smc_accept(B, P, sh.eps, sh.flag, li, Xp, q_lp[at], [&](int k) { return q_th[(size_t)k * QCAP + at]; });
-                note_final_shared(sh, B.hist, ok ? Xp : q_x[at]);
-                const unsigned int okb = __ballot_sync(__activemask(), ok);
-                if (ok && (okb & ((1u << lane) - 1u)) == 0) atomicAdd(&sh.acc, (unsigned int)__popc(okb));
-            }
-            if (threadIdx.x == 0) sh.work += take;
-            qn -= take;
-            __syncthreads();
-        }
-    }
-    if (threadIdx.x == 0) {
-        if (sh.acc) atomicAdd(&c->sw_accepted, (unsigned long long)sh.acc);
-        if (sh.work) atomicAdd(&c->sw_work, (unsigned long long)sh.work);
-        if (sh.below) atomicAdd(&c->sw_below, (unsigned long long)sh.below);
-        if (sh.above) atomicAdd(&c->sw_above, (unsigned long long)sh.above);
-        if (sh.kmin != ~0ull) atomicMin(&c->sw_minkey, sh.kmin);
-    }
-    if (last_block(&c->tk_sim)) sweep_finish<SWEEP_THREADS>(B, P, x, close_iter, s_scan, s_res);
-}
-
-// ------------------------------------------------------------------ work-list path (Lotka-Volterra, g-and-k)
+// ------------------------------------------------------------------ propose kernel: phase A of a sweep, ref :160-167 (+ :172-175)
 template <int DM>
 __global__ void __launch_bounds__(256, 5)
 k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk) {
@@ -1178,25 +1074,24 @@ k_smc_propose(SmcBufs B, SmcParams P, DPriors pri, RoundKeys rk) {
     tally_flush(c, tl);
 }
 
-// Thread-per-particle simulators over the work list: persistent CTAs claim chunks of 256 / L work items from an atomic
-// head.  L > 1 (normal model, F32): L lanes of a warp share a particle's draws (cost_normal_f32_lanes), so a chunk is
-// 1/L of a per-thread round and the kernel's tail -- the time between the first and the last CTA running dry -- shrinks
-// with it (at L = 1 a round is a third of the whole kernel and the last wave is mostly idle lanes).
-template <int KIND, int PREC, int L>
+// Phase B of a sweep for the thread-per-particle simulators (ref :168-191): persistent CTAs claim chunks of 256 work items
+// from an atomic head, one particle per thread, every warp full (the list holds only proposals that passed the prior tests).
+// Tried and rejected (numbers in DESIGN.md section 5): L lanes of a warp sharing one particle's draws (finer chunks, but
+// +6 / +9 / +16 % time at L = 2 / 4 / 8) and one fused propose+simulate kernel with a per-CTA survivor queue (+8 %).
+template <int KIND, int PREC>
 __global__ void __launch_bounds__(256, 6) k_smc_simulate_list(SmcBufs B, SmcParams P, XPeer x, DModel m, RoundKeys rk, int close_iter) {
     __shared__ unsigned int s_scan[256];
     __shared__ unsigned long long s_res[4];
     __shared__ SweepShared sh; // sweep constants and tallies live in shared memory: the register budget is the draw loop's
     SmcCtrl *c = B.ctrl;
     if (smc_skip(c) || c->retry_done) return;
-    constexpr unsigned int PER = 256 / L;
+    constexpr unsigned int PER = 256;
     if (threadIdx.x == 0) {
         sh.eps = c->eps; sh.flag = c->flag; sh.epoch = c->epoch;
         sh.hklo = c->h_klo; sh.hkhi = c->h_khi; sh.hshift = c->h_shift;
         sh.kmin = ~0ull; sh.acc = 0; sh.work = 0; sh.below = 0; sh.above = 0;
     }
     const unsigned int nwork = c->work_count;
-    const int sub = (int)(threadIdx.x % L);
     unsigned long long events = 0;
     for (;;) {
         __syncthreads();
@@ -1204,18 +1099,15 @@ __global__ void __launch_bounds__(256, 6) k_smc_simulate_list(SmcBufs B, SmcPara
         __syncthreads();
         const unsigned int base = sh.tile * PER;
         if (base >= nwork) break;
-        const unsigned int w = base + threadIdx.x / L;
+        const unsigned int w = base + threadIdx.x;
         const bool valid = w < nwork;
         const long long li = valid ? (long long)B.work[w] : 0;
         const long long Pn = P.P;
         const double *thp = B.thp;
         long long ev = 0;
-        double Xp;
-        if (L > 1)
-            Xp = cost_normal_f32_lanes<L>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch, pushk(m, 0, thp[li]), pushk(m, 1, thp[Pn + li]), sub, valid);
-        else
-            Xp = valid ? cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch, [&](int k) { return thp[(long long)k * Pn + li]; }, ev) : 0.0;
-        if (valid && sub == 0) {
+        if ((w & ~31u) >= nwork) continue; // whole warp past the end of the list
+        const double Xp = valid ? cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch, [&](int k) { return thp[(long long)k * Pn + li]; }, ev) : 0.0;
+        if (valid) {
             const double Xold = B.X[li];
             const bool ok = smc_accept(B, P, sh.eps, sh.flag, li, Xp, B.lpip[li], [&](int k) { return thp[(long long)k * Pn + li]; });
             note_final_shared(sh, B.hist, ok ? Xp : Xold);
@@ -1399,11 +1291,8 @@ struct kabc_smc {
     DevBuf<unsigned char> tdec;
     SmcCtrl *h_ctrl = nullptr; // pinned
     bool inited = false;
-    bool fused = true;         // thread-per-particle simulators run inside k_smc_sweep
     long long launches = 0;
     int nblocks_scan = 0;
-    int sweep_blocks = 0;
-    size_t sweep_smem = 0;
     // one whole iteration (selection + cut + table + sweep, all control flow on the device) captured as a CUDA graph: a
     // single launch instead of six, so the short kernels run back to back even when the host is not ahead of the device
     cudaGraphExec_t iter_graph = nullptr;
@@ -1450,27 +1339,16 @@ static XLayout smc_xlayout(long long P, int d, int world) {
     return L;
 }
 
-static int smc_list_lanes() { // lanes per particle of the normal model's F32 simulator (KABC_SIM_LANES = 1, 2, 4, 8)
-    static const int v = [] { const char *e = getenv("KABC_SIM_LANES"); int q = e ? atoi(e) : 4; return (q == 1 || q == 2 || q == 8) ? q : 4; }();
-    return v;
-}
 template <int KIND>
 static void smc_launch_list_t(kabc_smc *s, int ci) {
-    const bool coop = KIND == KABC_MODEL_NORMAL_MEANSTD && s->model.precision != KABC_F64;
-    const int L = coop ? smc_list_lanes() : 1;
-    const long long need = (s->P.P * L + 255) / 256, cap = (long long)s->ctx->sm_count * 6;
-    const unsigned blocks = (unsigned)(need < cap ? need : cap);
+    static const bool full_grid = [] { const char *e = getenv("KABC_SIM_GRID"); return e && e[0] == 'f'; }(); // A/B: one chunk per CTA
+    const long long need = (s->P.P + 255) / 256, cap = (long long)s->ctx->sm_count * 6;
+    const unsigned blocks = (unsigned)((need < cap || full_grid) ? need : cap);
     cudaStream_t st = s->ctx->stream;
     if (s->model.precision == KABC_F64)
-        k_smc_simulate_list<KIND, KABC_F64, 1><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
-    else if (!coop || L == 1)
-        k_smc_simulate_list<KIND, KABC_F32_ACC64, 1><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
-    else if (L == 2)
-        k_smc_simulate_list<KABC_MODEL_NORMAL_MEANSTD, KABC_F32_ACC64, 2><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
-    else if (L == 4)
-        k_smc_simulate_list<KABC_MODEL_NORMAL_MEANSTD, KABC_F32_ACC64, 4><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+        k_smc_simulate_list<KIND, KABC_F64><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
     else
-        k_smc_simulate_list<KABC_MODEL_NORMAL_MEANSTD, KABC_F32_ACC64, 8><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+        k_smc_simulate_list<KIND, KABC_F32_ACC64><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
 }
 
 template <int KIND>
@@ -1481,33 +1359,6 @@ static void smc_launch_init_t(kabc_smc *s) {
     else
         k_smc_init<KIND, KABC_F32_ACC64><<<blocks, 256, 0, s->ctx->stream>>>(s->B, s->P, s->pri, s->model, s->ctx->rk);
     SMC_LAUNCHED(s, 1);
-}
-
-// the fused sweep kernel of a model: pointer (for occupancy / attributes) and launch
-typedef void (*sweep_fn_t)(SmcBufs, SmcParams, XPeer, DPriors, DModel, RoundKeys, int);
-static int smc_sweep_min_ctas() {
-    static const int v = [] { const char *e = getenv("KABC_SWEEP_CTAS"); return (e && e[0] == '5') ? 5 : 6; }();
-    return v;
-}
-template <int KIND>
-static sweep_fn_t smc_sweep_fn_t(int prec, int d) {
-    if (KIND == KABC_MODEL_DETERMINISTIC && d > 2)
-        return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, KABC_MAX_DIM, 1> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, KABC_MAX_DIM, 1>;
-    if (KIND == KABC_MODEL_DETERMINISTIC || KIND == KABC_MODEL_SOCKS)
-        return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, 2, 5> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, 2, 5>;
-    if (smc_sweep_min_ctas() == 5)
-        return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, 2, 5> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, 2, 5>;
-    return prec == KABC_F64 ? (sweep_fn_t)k_smc_sweep<KIND, KABC_F64, 2, 6> : (sweep_fn_t)k_smc_sweep<KIND, KABC_F32_ACC64, 2, 6>;
-}
-static sweep_fn_t smc_sweep_fn(const kabc_smc *s) {
-    const int prec = s->model.precision, d = s->P.d;
-    switch (s->model.kind) {
-    case KABC_MODEL_NORMAL_MEANSTD: return smc_sweep_fn_t<KABC_MODEL_NORMAL_MEANSTD>(prec, d);
-    case KABC_MODEL_MA2_AUTOCOV: return smc_sweep_fn_t<KABC_MODEL_MA2_AUTOCOV>(prec, d);
-    case KABC_MODEL_DETERMINISTIC: return smc_sweep_fn_t<KABC_MODEL_DETERMINISTIC>(prec, d);
-    case KABC_MODEL_SOCKS: return smc_sweep_fn_t<KABC_MODEL_SOCKS>(prec, d);
-    default: return nullptr;
-    }
 }
 
 static int smc_gk_grid(kabc_smc *s, size_t &smem) {
@@ -1553,38 +1404,44 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
     k_compact<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P, s->X, 0, 1);
     SMC_LAUNCHED(s, 1);
     s->mark();
-    if (s->fused) {
-        sweep_fn_t fn = smc_sweep_fn(s);
-        fn<<<s->sweep_blocks, SWEEP_THREADS, s->sweep_smem, ctx->stream>>>(s->B, s->P, s->X, s->pri, s->model, ctx->rk, ci);
-        SMC_LAUNCHED(s, 1);
-    } else {
-        const unsigned pb = (unsigned)((s->P.P + 255) / 256);
-        if (s->model.kind == KABC_MODEL_NORMAL_MEANSTD || s->model.kind == KABC_MODEL_MA2_AUTOCOV) {
-            k_smc_propose<2><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
-            s->mark();
-            if (s->model.kind == KABC_MODEL_NORMAL_MEANSTD) smc_launch_list_t<KABC_MODEL_NORMAL_MEANSTD>(s, ci);
-            else smc_launch_list_t<KABC_MODEL_MA2_AUTOCOV>(s, ci);
-        } else if (s->model.kind == KABC_MODEL_LV_SSA) {
-            k_smc_propose<3><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
-            s->mark();
-            long long cap = (long long)ctx->sm_count * 8;
-            const unsigned blocks = (unsigned)((long long)pb < cap ? (long long)pb : cap);
-            if (s->model.precision == KABC_F64)
-                k_smc_simulate_lv<KABC_F64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
-            else
-                k_smc_simulate_lv<KABC_F32_ACC64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
-        } else {
-            k_smc_propose<4><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
-            s->mark();
-            size_t smem;
-            int grid = smc_gk_grid(s, smem);
-            if (s->model.precision == KABC_F64)
-                k_smc_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
-            else
-                k_smc_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
-        }
-        SMC_LAUNCHED(s, 2);
+    const unsigned pb = (unsigned)((s->P.P + 255) / 256);
+    switch (s->model.kind) {
+    case KABC_MODEL_LV_SSA: {
+        k_smc_propose<3><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+        s->mark();
+        long long cap = (long long)ctx->sm_count * 8;
+        const unsigned blocks = (unsigned)((long long)pb < cap ? (long long)pb : cap);
+        if (s->model.precision == KABC_F64)
+            k_smc_simulate_lv<KABC_F64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
+        else
+            k_smc_simulate_lv<KABC_F32_ACC64><<<blocks, 256, 0, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
+        break;
     }
+    case KABC_MODEL_GK_OCTILE: {
+        k_smc_propose<4><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+        s->mark();
+        size_t smem;
+        int grid = smc_gk_grid(s, smem);
+        if (s->model.precision == KABC_F64)
+            k_smc_simulate_gk<KABC_F64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
+        else
+            k_smc_simulate_gk<KABC_F32_ACC64><<<grid, GK_THREADS, smem, ctx->stream>>>(s->B, s->P, s->X, s->model, ctx->rk, ci);
+        break;
+    }
+    default: {
+        if (s->P.d <= 2) k_smc_propose<2><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+        else if (s->P.d <= 4) k_smc_propose<4><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+        else k_smc_propose<KABC_MAX_DIM><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
+        s->mark();
+        switch (s->model.kind) {
+        case KABC_MODEL_NORMAL_MEANSTD: smc_launch_list_t<KABC_MODEL_NORMAL_MEANSTD>(s, ci); break;
+        case KABC_MODEL_MA2_AUTOCOV: smc_launch_list_t<KABC_MODEL_MA2_AUTOCOV>(s, ci); break;
+        case KABC_MODEL_DETERMINISTIC: smc_launch_list_t<KABC_MODEL_DETERMINISTIC>(s, ci); break;
+        default: smc_launch_list_t<KABC_MODEL_SOCKS>(s, ci); break;
+        }
+    }
+    }
+    SMC_LAUNCHED(s, 2);
     s->mark();
     KABC_CUDA_TRY(cudaGetLastError());
     return KABC_OK;
@@ -1710,13 +1567,6 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->P.rank = ctx->rank; s->P.world = ctx->world;
     s->X = make_xpeer(ctx);
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
-    s->fused = (m.kind != KABC_MODEL_LV_SSA && m.kind != KABC_MODEL_GK_OCTILE);
-    {
-        // the headline simulators run propose -> work list -> simulate (lanes) unless KABC_FUSED=1 asks for the fused sweep
-        const char *e = getenv("KABC_FUSED");
-        const bool want_fused = e && e[0] == '1';
-        if (!want_fused && (m.kind == KABC_MODEL_NORMAL_MEANSTD || m.kind == KABC_MODEL_MA2_AUTOCOV)) s->fused = false;
-    }
     const size_t nd = (size_t)Pn * d;
     const size_t nd_pad = (nd + 1) & ~(size_t)1, pn_pad = ((size_t)Pn + 1) & ~(size_t)1; // X, lpi 16-byte aligned (double2 loads)
     cudaError_t e = cudaSuccess;
@@ -1736,7 +1586,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     }
     s->B.o_th = (long long)L.o_th; s->B.o_alive = (long long)L.o_alive;
     A(s->state.alloc(ctx, nd_pad + 2 * pn_pad));
-    if (!s->fused) { A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, Pn)); A(s->work.alloc(ctx, Pn)); }
+    A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, Pn)); A(s->work.alloc(ctx, Pn));
     A(s->alive.alloc(ctx, Pn)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
     A(s->hist.alloc(ctx, SEL_BINS)); A(s->cand.alloc(ctx, SEL_CAP)); A(s->ctrl.alloc(ctx, 1));
     const long long log_cap = 1 << 14;
@@ -1757,16 +1607,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     cudaError_t e2 = cudaMemsetAsync(s->ctrl.p, 0, sizeof(SmcCtrl), ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(s->hist.p, 0, sizeof(unsigned int) * SEL_BINS, ctx->stream);
     // launch geometry of the sweep
-    if (e2 == cudaSuccess && s->fused) {
-        sweep_fn_t fn = smc_sweep_fn(s);
-        s->sweep_smem = (size_t)QCAP * (8 + 8 + 8 * (size_t)d + 4);
-        if (s->sweep_smem > 48 * 1024) e2 = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sweep_smem);
-        int per_sm = 0;
-        if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, SWEEP_THREADS, s->sweep_smem);
-        if (per_sm < 1) per_sm = 1;
-        const long long ntiles = (Pn + SWEEP_THREADS - 1) / SWEEP_THREADS, cap = (long long)ctx->sm_count * per_sm;
-        s->sweep_blocks = (int)(ntiles < cap ? ntiles : cap);
-    } else if (e2 == cudaSuccess && m.kind == KABC_MODEL_GK_OCTILE) {
+    if (e2 == cudaSuccess && m.kind == KABC_MODEL_GK_OCTILE) {
         const int smem = (int)gk_smem_bytes(m.n_draws, m.precision);
         if (m.precision == KABC_F64) {
             e2 = cudaFuncSetAttribute(k_smc_init_gk<KABC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
