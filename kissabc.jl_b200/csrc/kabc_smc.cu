@@ -62,7 +62,7 @@ struct SmcCtrl {
     unsigned long long accepted, cost_evals, events;
     unsigned long long sw_accepted, sw_work, sw_events, sw_minkey, sw_maxkey, sw_below, sw_above; // this rank, this sweep
     long long iteration;
-    unsigned int work_count, cand_count, epoch, lv_head, tile_head;
+    unsigned int work_count, cand_count, epoch, lv_head, tile_head, tiles_done;
     unsigned int tk_sel, tk_cut, tk_compact, tk_sim, tk_misc;
     int flag, resample, stop, err, sweeps, retry_done, resampled_log;
     int honor_stop; // kabc_smc_run enqueues one iteration ahead: once `stop` is set the queued kernels do nothing
@@ -93,6 +93,7 @@ struct SmcBufs {
     long long o_th, o_alive; // byte offsets of the rows and of the alive flags inside xb[r]
     double *thp, *lpip;                  // proposals [d][P] (work-list path and trace)
     unsigned int *work, *blockcnt, *hist;
+    unsigned int *fill;                  // entries of the work list written so far, per chunk of 256 (queued sweep)
     unsigned long long *cand;
     SmcCtrl *ctrl;
     kabc_smc_log_t *log;
@@ -672,7 +673,7 @@ __device__ void sweep_setup(SmcCtrl *c, const SmcParams &P, int resample, const 
     c->off[P.world] = run;
     c->resample = resample;
     c->sw_accepted = 0; c->sw_work = 0; c->sw_events = 0; c->sw_minkey = ~0ull; c->sw_maxkey = 0ull; c->sw_below = 0; c->sw_above = 0;
-    c->work_count = 0; c->lv_head = 0; c->tile_head = 0;
+    c->work_count = 0; c->lv_head = 0; c->tile_head = 0; c->tiles_done = 0;
     // window of the next quantile: every alive cost is < eps (<= with the flag), ref :137-139
     const double eps = c->eps;
     const unsigned long long khi = dkey(eps);
@@ -758,6 +759,10 @@ __global__ void __launch_bounds__(CUT_THREADS) k_compact(SmcBufs B, SmcParams P,
     const int resample = force_identity ? 0 : c->resample;
     const long long Pn = P.P;
     const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
+    { // the work list of the coming sweep starts empty
+        const long long nfill = (Pn + 255) / 256 + 1, gt = (long long)blockIdx.x * CUT_THREADS + threadIdx.x;
+        if (gt < nfill) B.fill[gt] = 0;
+    }
     double *t_th = reinterpret_cast<double *>(B.xb[P.rank] + B.o_th);
     unsigned char *t_alive = B.xb[P.rank] + B.o_alive;
     unsigned int a[4] = {0u, 0u, 0u, 0u};
@@ -1131,6 +1136,140 @@ __global__ void __launch_bounds__(256, 6) k_smc_simulate_list(SmcBufs B, SmcPara
     if (last_block(&c->tk_sim)) sweep_finish<256>(B, P, x, close_iter, s_scan, s_res);
 }
 
+// ------------------------------------------------------------------ the queued sweep (thread-per-particle simulators)
+// ONE persistent kernel runs both phases of a sweep.  Phase A units are TILES of 256 consecutive particles (propose: own
+// row and partner gathers -- NVLink peer loads on a multi-GPU job --, FP64 proposal arithmetic, prior tests); their
+// survivors are appended to a global work list.  Phase B units are CHUNKS of 256 consecutive list entries (simulate +
+// accept, every warp full).  A CTA that finds a complete chunk simulates it; otherwise it proposes the next tile; so
+// proposals are produced just ahead of their consumption, spread over the whole kernel, and their (peer) load latency is
+// covered by the other CTAs' draw loops, while the balance between CTAs is that of a dynamically claimed chunk.
+// Phase A of EVERY particle still reads only the frozen table and phase B only writes the state of its own particle, so
+// the result is the Jacobi update of the reference (:160-191) whatever the interleaving.
+// Protocol: a tile's entries are written, fenced, then counted into fill[chunk] (atomicAdd) and tiles_done; chunk h may be
+// claimed (CAS on the head) once fill[h] == 256, or == the remainder when all tiles are done.
+enum { QACT_SIM = 1, QACT_PROP = 2, QACT_EXIT = 3, QACT_RETRY = 4 };
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int KIND, int PREC, int DM>
+__global__ void __launch_bounds__(256, 6)
+k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys rk, int close_iter) {
+    __shared__ unsigned int s_scan[256];
+    __shared__ unsigned long long s_res[4];
+    __shared__ SweepShared sh;
+    __shared__ unsigned int s_cnt[8], s_base, s_act, s_unit, s_len;
+    SmcCtrl *c = B.ctrl;
+    if (smc_skip(c) || c->retry_done) return;
+    if (threadIdx.x <= P.world) sh.off[threadIdx.x] = c->off[threadIdx.x];
+    if (threadIdx.x == 0) {
+        sh.eps = c->eps; sh.flag = c->flag; sh.epoch = c->epoch;
+        sh.hklo = c->h_klo; sh.hkhi = c->h_khi; sh.hshift = c->h_shift;
+        sh.kmin = ~0ull; sh.acc = 0; sh.work = 0; sh.below = 0; sh.above = 0;
+    }
+    const long long Pn = P.P;
+    const unsigned int ntiles = (unsigned int)((Pn + 255) / 256);
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long t_wait0 = 0;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) {
+            unsigned int act = QACT_RETRY, unit = 0, len = 0;
+            const unsigned int h = ld_acquire_gpu_u32(&c->lv_head);
+            const unsigned int done = ld_acquire_gpu_u32(&c->tiles_done);
+            const unsigned int total = ld_acquire_gpu_u32(&c->work_count);
+            const unsigned int f = ld_acquire_gpu_u32(&B.fill[h]);
+            const bool all_done = done == ntiles;
+            const unsigned int rem = (all_done && total > h * 256u) ? (total - h * 256u) : 0u;
+            if (f == 256u || (all_done && rem > 0u && rem < 256u && f == rem)) {
+                if (atomicCAS(&c->lv_head, h, h + 1u) == h) { act = QACT_SIM; unit = h; len = f; }
+            } else if (ld_acquire_gpu_u32(&c->tile_head) < ntiles) {
+                const unsigned int t = atomicAdd(&c->tile_head, 1u);
+                if (t < ntiles) { act = QACT_PROP; unit = t; }
+            } else if (all_done && total <= h * 256u) {
+                act = QACT_EXIT;
+            } else { // tiles are in flight on other CTAs: bounded wait
+                const unsigned long long now = global_timer_ns();
+                if (t_wait0 == 0) t_wait0 = now;
+                if (now - t_wait0 > 5000000000ull) { if (!c->err) c->err = KABC_ERR_STATE; act = QACT_EXIT; }
+                __nanosleep(200);
+            }
+            if (act != QACT_RETRY) t_wait0 = 0;
+            s_act = act; s_unit = unit; s_len = len;
+        }
+        __syncthreads();
+        const unsigned int act = s_act, unit = s_unit, len = s_len;
+        __syncthreads();
+        if (act == QACT_EXIT) break;
+        if (act == QACT_PROP) {
+            const long long li = (long long)unit * 256 + threadIdx.x;
+            bool pass = false, alive_i = false;
+            if (li < Pn) {
+                Proposed<DM> pr;
+                pass = smc_propose_one<DM>(B, P, c, pri, rk, sh.off, li, pr, alive_i);
+                if (alive_i && !pass) note_final_shared(sh, B.hist, pr.Xi);
+                if (pass) {
+#pragma unroll
+                    for (int k = 0; k < DM; ++k)
+                        if (k < P.d) B.thp[(long long)k * Pn + li] = pr.thp[k];
+                    B.lpip[li] = pr.lpip;
+                }
+            }
+            const unsigned int ball = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) s_cnt[warp] = __popc(ball);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
+                s_base = tot ? atomicAdd(&c->work_count, tot) : 0u;
+                s_len = tot;
+            }
+            __syncthreads();
+            const unsigned int base = s_base, tot = s_len;
+            if (pass) B.work[base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)li;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) { // publish: per-chunk fill counts, then the tile
+                if (tot) {
+                    const unsigned int c0 = base / 256u, c1 = (base + tot - 1u) / 256u;
+                    if (c0 == c1) atomicAdd(&B.fill[c0], tot);
+                    else {
+                        const unsigned int first = (c0 + 1u) * 256u - base;
+                        atomicAdd(&B.fill[c0], first);
+                        atomicAdd(&B.fill[c1], tot - first);
+                    }
+                }
+                __threadfence();
+                atomicAdd(&c->tiles_done, 1u);
+            }
+        } else if (act == QACT_SIM) {
+            if (threadIdx.x < len && (threadIdx.x & ~31u) < len) {
+                const long long li = (long long)__ldcg(&B.work[unit * 256u + threadIdx.x]);
+                const double *thp = B.thp;
+                long long ev = 0;
+                const double Xp = cost_thread<KIND, PREC>(m, rk, ST_COST, (uint32_t)(P.lo + li), sh.epoch,
+                                                          [&](int k) { return __ldcg(&thp[(long long)k * Pn + li]); }, ev);
+                const double Xold = __ldcg(&B.X[li]);
+                const bool ok = smc_accept(B, P, sh.eps, sh.flag, li, Xp, __ldcg(&B.lpip[li]), [&](int k) { return __ldcg(&thp[(long long)k * Pn + li]); });
+                note_final_shared(sh, B.hist, ok ? Xp : Xold);
+                if (ok) atomicAdd(&sh.acc, 1u);
+            }
+            if (threadIdx.x == 0) sh.work += len;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sh.acc) atomicAdd(&c->sw_accepted, (unsigned long long)sh.acc);
+        if (sh.work) atomicAdd(&c->sw_work, (unsigned long long)sh.work);
+        if (sh.below) atomicAdd(&c->sw_below, (unsigned long long)sh.below);
+        if (sh.above) atomicAdd(&c->sw_above, (unsigned long long)sh.above);
+        if (sh.kmin != ~0ull) atomicMin(&c->sw_minkey, sh.kmin);
+    }
+    if (last_block(&c->tk_sim)) sweep_finish<256>(B, P, x, close_iter, s_scan, s_res);
+}
+
 // Lotka-Volterra sweep: persistent lanes.  Event counts per trajectory differ by orders of magnitude, so a lane whose
 // trajectory ended immediately pulls the next work item (warp-aggregated atomic on the work-list head) instead of
 // idling until the slowest lane of its warp finishes.  Per-particle arithmetic is unchanged (LvSim), so results do
@@ -1281,7 +1420,7 @@ struct kabc_smc {
     DevBuf<double> state, thp, lpip; // state = [th (d*P) | X (P) | lpi (P)]
     DevBuf<unsigned char> alive, xlocal; // xlocal: the peer-visible block when there are no peers (G = 1)
     bool in_arena = false;
-    DevBuf<unsigned int> work, blockcnt, hist;
+    DevBuf<unsigned int> work, blockcnt, hist, fill;
     DevBuf<unsigned long long> cand;
     DevBuf<SmcCtrl> ctrl;
     DevBuf<kabc_smc_log_t> log;
@@ -1349,6 +1488,22 @@ static void smc_launch_list_t(kabc_smc *s, int ci) {
         k_smc_simulate_list<KIND, KABC_F64><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
     else
         k_smc_simulate_list<KIND, KABC_F32_ACC64><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->model, s->ctx->rk, ci);
+}
+
+template <int KIND>
+static void smc_launch_queued_t(kabc_smc *s, int ci) {
+    const long long need = (s->P.P + 255) / 256, cap = (long long)s->ctx->sm_count * 6;
+    const unsigned blocks = (unsigned)(need < cap ? need : cap);
+    cudaStream_t st = s->ctx->stream;
+    const bool f64 = s->model.precision == KABC_F64;
+    if constexpr (KIND == KABC_MODEL_DETERMINISTIC) { // the only registered simulator with a free dimension
+        if (s->P.d > 2) {
+            k_smc_sweep_q<KIND, KABC_F64, KABC_MAX_DIM><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->pri, s->model, s->ctx->rk, ci);
+            return;
+        }
+    }
+    if (f64) k_smc_sweep_q<KIND, KABC_F64, 2><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->pri, s->model, s->ctx->rk, ci);
+    else k_smc_sweep_q<KIND, KABC_F32_ACC64, 2><<<blocks, 256, 0, st>>>(s->B, s->P, s->X, s->pri, s->model, s->ctx->rk, ci);
 }
 
 template <int KIND>
@@ -1429,6 +1584,19 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
         break;
     }
     default: {
+        static const bool split = [] { const char *e = getenv("KABC_SWEEP"); return e && e[0] == 's'; }(); // "split": two kernels
+        if (!split) {
+            switch (s->model.kind) {
+            case KABC_MODEL_NORMAL_MEANSTD: smc_launch_queued_t<KABC_MODEL_NORMAL_MEANSTD>(s, ci); break;
+            case KABC_MODEL_MA2_AUTOCOV: smc_launch_queued_t<KABC_MODEL_MA2_AUTOCOV>(s, ci); break;
+            case KABC_MODEL_DETERMINISTIC: smc_launch_queued_t<KABC_MODEL_DETERMINISTIC>(s, ci); break;
+            default: smc_launch_queued_t<KABC_MODEL_SOCKS>(s, ci); break;
+            }
+            SMC_LAUNCHED(s, 1);
+            s->mark();
+            KABC_CUDA_TRY(cudaGetLastError());
+            return KABC_OK;
+        }
         if (s->P.d <= 2) k_smc_propose<2><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
         else if (s->P.d <= 4) k_smc_propose<4><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
         else k_smc_propose<KABC_MAX_DIM><<<pb, 256, 0, ctx->stream>>>(s->B, s->P, s->pri, ctx->rk);
@@ -1586,7 +1754,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     }
     s->B.o_th = (long long)L.o_th; s->B.o_alive = (long long)L.o_alive;
     A(s->state.alloc(ctx, nd_pad + 2 * pn_pad));
-    A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, Pn)); A(s->work.alloc(ctx, Pn));
+    A(s->thp.alloc(ctx, nd)); A(s->lpip.alloc(ctx, Pn)); A(s->work.alloc(ctx, Pn)); A(s->fill.alloc(ctx, (size_t)(Pn + 255) / 256 + 2));
     A(s->alive.alloc(ctx, Pn)); A(s->blockcnt.alloc(ctx, s->nblocks_scan));
     A(s->hist.alloc(ctx, SEL_BINS)); A(s->cand.alloc(ctx, SEL_CAP)); A(s->ctrl.alloc(ctx, 1));
     const long long log_cap = 1 << 14;
@@ -1600,6 +1768,7 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     memset(s->h_ctrl, 0, sizeof(SmcCtrl));
     s->B.th = s->state.p; s->B.X = s->state.p + nd_pad; s->B.lpi = s->B.X + pn_pad;
     s->B.alive = s->alive.p; s->B.thp = s->thp.p; s->B.lpip = s->lpip.p; s->B.work = s->work.p;
+    s->B.fill = s->fill.p;
     s->B.blockcnt = s->blockcnt.p; s->B.hist = s->hist.p; s->B.cand = s->cand.p; s->B.ctrl = s->ctrl.p;
     s->B.log = s->log.p; s->B.log_cap = log_cap;
     memset(&s->B.tr, 0, sizeof s->B.tr);
