@@ -1172,28 +1172,34 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
     const unsigned int ntiles = (unsigned int)((Pn + 255) / 256);
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long t_wait0 = 0;
+    unsigned int my_chunk = 0xFFFFFFFFu; // thread 0: the chunk this CTA has claimed and not simulated yet
     __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) {
+            // Claims are plain atomicAdds (no retry loop: 888 CTAs claim thousands of units per sweep).  A CTA claims the next
+            // chunk first; while that chunk is incomplete it produces: it proposes tiles, whose survivors fill the chunks in
+            // order, its own included.  Claims past the end of the list are recognised once every tile is published.
             unsigned int act = QACT_RETRY, unit = 0, len = 0;
-            const unsigned int h = ld_acquire_gpu_u32(&c->lv_head);
+            if (my_chunk == 0xFFFFFFFFu) my_chunk = atomicAdd(&c->lv_head, 1u);
+            const unsigned int h = my_chunk;
             const unsigned int done = ld_acquire_gpu_u32(&c->tiles_done);
             const unsigned int total = ld_acquire_gpu_u32(&c->work_count);
-            const unsigned int f = ld_acquire_gpu_u32(&B.fill[h]);
+            const unsigned int f = ld_acquire_gpu_u32(&B.fill[h < ntiles ? h : ntiles]);
             const bool all_done = done == ntiles;
             const unsigned int rem = (all_done && total > h * 256u) ? (total - h * 256u) : 0u;
-            if (f == 256u || (all_done && rem > 0u && rem < 256u && f == rem)) {
-                if (atomicCAS(&c->lv_head, h, h + 1u) == h) { act = QACT_SIM; unit = h; len = f; }
+            if (h < ntiles && (f == 256u || (all_done && rem > 0u && rem < 256u && f == rem))) {
+                act = QACT_SIM; unit = h; len = f;
+                my_chunk = 0xFFFFFFFFu;
+            } else if (all_done && total <= h * 256u) {
+                act = QACT_EXIT;
             } else if (ld_acquire_gpu_u32(&c->tile_head) < ntiles) {
                 const unsigned int t = atomicAdd(&c->tile_head, 1u);
                 if (t < ntiles) { act = QACT_PROP; unit = t; }
-            } else if (all_done && total <= h * 256u) {
-                act = QACT_EXIT;
-            } else { // tiles are in flight on other CTAs: bounded wait
+            } else { // every tile is claimed, some are still in flight on other CTAs: bounded wait
                 const unsigned long long now = global_timer_ns();
                 if (t_wait0 == 0) t_wait0 = now;
                 if (now - t_wait0 > 5000000000ull) { if (!c->err) c->err = KABC_ERR_STATE; act = QACT_EXIT; }
-                __nanosleep(200);
+                __nanosleep(100);
             }
             if (act != QACT_RETRY) t_wait0 = 0;
             s_act = act; s_unit = unit; s_len = len;

@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PIPES = {"fmaheavy (IMAD.WIDE of Philox)": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
+PIPES = {"fmaheavy (IMAD.WIDE of Philox)": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
          "fma": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
          "alu": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
          "xu (MUFU)": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
@@ -43,7 +43,8 @@ def main():
         units = json.load(open(os.path.join(ROOT, "gpurun_out", f"ncu_units_{wl}.json")))
         it = units["units"][int(skipped) // units["units"][0]["launches_per_step"]]
         n_units = it["events"] if wl == "lv_smc" else it["evals"] / it["launches_per_step"]
-        tinst = g("smsp__thread_inst_executed.sum")
+        tinst = g("smsp__thread_inst_executed.sum") or g("sass__thread_inst_executed_true_per_opcode") or \
+            (g("smsp__inst_executed.sum") or 0) * 32.0
         dr, dw = g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         dru, dwu = unit_row[hdr.index("dram__bytes_read.sum")], unit_row[hdr.index("dram__bytes_write.sum")]
