@@ -444,9 +444,9 @@ class SmcSession:
         buf = (C.c_float * 16)()
         n = C.c_int()
         K.check(self.L.kabc_smc_profile_iteration(self.h, buf, 16, C.byref(n)))
-        names = ["sel_1", "sel_2", "sel_3", "cut", "compact_table", "sweep"]
-        if n.value == 7:  # work-list path (Lotka-Volterra, g-and-k)
-            names = names[:5] + ["propose", "simulate"]
+        names = ["sel_1", "sel_2", "cut", "compact_table", "sweep"]
+        if n.value == 6:  # two-kernel sweep (Lotka-Volterra, g-and-k, KABC_SWEEP=split)
+            names = names[:4] + ["propose", "simulate"]
         return {names[i]: float(buf[i]) for i in range(n.value)}
 
     def trace_enable(self, on=True):

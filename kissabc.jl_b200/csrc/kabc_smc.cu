@@ -33,8 +33,11 @@ constexpr int SEL_LOG2_BINS = 12;
 constexpr int SEL_BINS = 1 << SEL_LOG2_BINS;
 constexpr int SEL_CAP = 4096; // candidates sorted exactly by one block
 constexpr int SEL_THREADS = 512;
-constexpr int SEL_INSTANCES = 3;   // k_sel launches per iteration; whatever is left is finished by one block (rare)
-constexpr int SCAN_THREADS = 1024; // particles per block of the cut / compact kernels
+constexpr int SEL_INSTANCES = 2;   // k_sel launches per iteration (steady state needs one); whatever is left -- the third pass
+                                   // of iteration 1, runs of ties -- is finished by the last block of the last instance alone
+constexpr int SCAN_THREADS = 2048; // particles per block of the cut / compact kernels: 256 threads x 2 groups of 4; 2^20
+                                   // particles are 512 blocks = ONE wave (1024 blocks were 1.15 waves: the 2nd wave cost as much)
+constexpr int CUT_GROUPS = 2;
 constexpr int CUT_THREADS = 256;
 
 enum { SEL_HIST = 0, SEL_CAND = 1, SEL_KEYS = 2, SEL_FINAL = 3 };
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel(SmcBufs B, SmcParams P, XPe
 }
 
 // ------------------------------------------------------------------ alive cut + ESS + resample decision, ref :136-147
-// block b owns local particles [1024 b, 1024 b + 1024): 256 threads x 4 consecutive particles
+// block b owns local particles [2048 b, 2048 b + 2048): 256 threads x 8 consecutive particles
 __device__ __forceinline__ unsigned int block_excl_scan_256(unsigned int v, unsigned int *s_w, unsigned int &total) {
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int incl = v;
@@ -697,23 +700,26 @@ __global__ void __launch_bounds__(CUT_THREADS) k_cut(SmcBufs B, SmcParams P, XPe
     const double *X = B.X;
     const double eps = c->eps;
     const int flag = c->flag;
-    const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
     unsigned int cnt = 0;
-    if (base + 3 < P.P) {
-        const double2 x0 = *reinterpret_cast<const double2 *>(X + base), x1 = *reinterpret_cast<const double2 *>(X + base + 2);
-        uchar4 a;
-        a.x = flag ? (x0.x <= eps) : (x0.x < eps); a.y = flag ? (x0.y <= eps) : (x0.y < eps);
-        a.z = flag ? (x1.x <= eps) : (x1.x < eps); a.w = flag ? (x1.y <= eps) : (x1.y < eps);
-        *reinterpret_cast<uchar4 *>(B.alive + base) = a;
-        cnt = a.x + a.y + a.z + a.w;
-    } else {
-        for (int q = 0; q < 4; ++q)
-            if (base + q < P.P) {
-                const double xv = X[base + q];
-                const unsigned int a = flag ? (xv <= eps) : (xv < eps);
-                B.alive[base + q] = (unsigned char)a;
-                cnt += a;
-            }
+#pragma unroll
+    for (int g = 0; g < CUT_GROUPS; ++g) { // thread t owns particles [8t, 8t+8) of the block's 2048
+        const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * (4 * CUT_GROUPS) + 4 * g;
+        if (base + 3 < P.P) {
+            const double2 x0 = *reinterpret_cast<const double2 *>(X + base), x1 = *reinterpret_cast<const double2 *>(X + base + 2);
+            uchar4 a;
+            a.x = flag ? (x0.x <= eps) : (x0.x < eps); a.y = flag ? (x0.y <= eps) : (x0.y < eps);
+            a.z = flag ? (x1.x <= eps) : (x1.x < eps); a.w = flag ? (x1.y <= eps) : (x1.y < eps);
+            *reinterpret_cast<uchar4 *>(B.alive + base) = a;
+            cnt += a.x + a.y + a.z + a.w;
+        } else {
+            for (int q = 0; q < 4; ++q)
+                if (base + q < P.P) {
+                    const double xv = X[base + q];
+                    const unsigned int a = flag ? (xv <= eps) : (xv < eps);
+                    B.alive[base + q] = (unsigned char)a;
+                    cnt += a;
+                }
+        }
     }
     unsigned int total;
     block_excl_scan_256(cnt, s_w, total);
@@ -752,47 +758,80 @@ __global__ void __launch_bounds__(CUT_THREADS) k_cut(SmcBufs B, SmcParams P, XPe
 // ------------------------------------------------------------------ the table a sweep reads, ref :146-152
 // resampling: entry (blockcnt[b] + rank inside the block) of the table <- the alive rows of the shard in index order
 // (idxalive = (1:N)[alive] restricted to the shard), then `alive .= true`; otherwise entry li <- row li.
-__global__ void __launch_bounds__(CUT_THREADS) k_compact(SmcBufs B, SmcParams P, XPeer x, int force_identity, int barrier) {
+__global__ void __launch_bounds__(CUT_THREADS, 4) k_compact(SmcBufs B, SmcParams P, XPeer x, int force_identity, int barrier) {
     __shared__ unsigned int s_w[33];
     SmcCtrl *c = B.ctrl;
     if (force_identity ? (c->err == KABC_ERR_PEER) : (smc_skip(c) || c->retry_done)) return; // get_state runs after `stop` too
     const int resample = force_identity ? 0 : c->resample;
     const long long Pn = P.P;
-    const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * 4;
+    constexpr int PT = 4 * CUT_GROUPS; // particles per thread
+    const long long base = ((long long)blockIdx.x * CUT_THREADS + threadIdx.x) * PT;
     { // the work list of the coming sweep starts empty
         const long long nfill = (Pn + 255) / 256 + 1, gt = (long long)blockIdx.x * CUT_THREADS + threadIdx.x;
-        if (gt < nfill) B.fill[gt] = 0;
+        for (long long q = gt; q < nfill; q += (long long)gridDim.x * CUT_THREADS) B.fill[q] = 0;
     }
     double *t_th = reinterpret_cast<double *>(B.xb[P.rank] + B.o_th);
     unsigned char *t_alive = B.xb[P.rank] + B.o_alive;
-    unsigned int a[4] = {0u, 0u, 0u, 0u};
-    for (int q = 0; q < 4; ++q)
-        if (base + q < Pn) a[q] = B.alive[base + q];
+    unsigned int a[PT];
+    const bool fullv = base + PT - 1 < Pn;
+    if (fullv) {
+#pragma unroll
+        for (int g = 0; g < CUT_GROUPS; ++g) {
+            const uchar4 av = *reinterpret_cast<const uchar4 *>(B.alive + base + 4 * g);
+            a[4 * g] = av.x; a[4 * g + 1] = av.y; a[4 * g + 2] = av.z; a[4 * g + 3] = av.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < PT; ++q) a[q] = (base + q < Pn) ? B.alive[base + q] : 0u;
+    }
     unsigned int pos = 0;
     if (resample) {
-        unsigned int total;
-        pos = B.blockcnt[blockIdx.x] + block_excl_scan_256(a[0] + a[1] + a[2] + a[3], s_w, total);
-    }
+        unsigned int total, mine = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const long long li = base + q;
-        if (li >= Pn) continue;
-        if (resample && !a[q]) continue;
-        const long long e = resample ? (long long)pos++ : li;
-        double *row = t_th + e * P.TS;
-        if (P.d == 2) { // rows are 32 bytes: two 128-bit stores
-            reinterpret_cast<double2 *>(row)[0] = make_double2(B.th[li], B.th[Pn + li]);
-            reinterpret_cast<double2 *>(row)[1] = make_double2(B.X[li], B.lpi[li]);
-        } else {
+        for (int q = 0; q < PT; ++q) mine += a[q];
+        pos = B.blockcnt[blockIdx.x] + block_excl_scan_256(mine, s_w, total);
+    }
+    if (fullv && P.d == 2 && (Pn & 1) == 0) { // the common shape: vector loads of the SoA state, two 128-bit stores per 32-byte row
+        double t0[PT], t1[PT], xx[PT], ll[PT];
+#pragma unroll
+        for (int g = 0; g < PT / 2; ++g) {
+            const double2 v0 = *reinterpret_cast<const double2 *>(B.th + base + 2 * g), v1 = *reinterpret_cast<const double2 *>(B.th + Pn + base + 2 * g);
+            const double2 v2 = *reinterpret_cast<const double2 *>(B.X + base + 2 * g), v3 = *reinterpret_cast<const double2 *>(B.lpi + base + 2 * g);
+            t0[2 * g] = v0.x; t0[2 * g + 1] = v0.y; t1[2 * g] = v1.x; t1[2 * g + 1] = v1.y;
+            xx[2 * g] = v2.x; xx[2 * g + 1] = v2.y; ll[2 * g] = v3.x; ll[2 * g + 1] = v3.y;
+        }
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            if (resample && !a[q]) continue;
+            const long long e = resample ? (long long)pos++ : base + q;
+            double2 *row = reinterpret_cast<double2 *>(t_th + e * 4);
+            row[0] = make_double2(t0[q], t1[q]);
+            row[1] = make_double2(xx[q], ll[q]);
+            if (!resample) t_alive[e] = (unsigned char)a[q];
+        }
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < PT; ++q) {
+            const long long li = base + q;
+            if (li >= Pn) continue;
+            if (resample && !a[q]) continue;
+            const long long e = resample ? (long long)pos++ : li;
+            double *row = t_th + e * P.TS;
             for (int k = 0; k < P.d; ++k) row[k] = B.th[(long long)k * Pn + li];
             row[P.d] = B.X[li];
             row[P.d + 1] = B.lpi[li];
+            if (!resample) t_alive[e] = (unsigned char)a[q];
         }
-        if (!resample) t_alive[e] = (unsigned char)a[q];
     }
-    if (resample)
-        for (int q = 0; q < 4; ++q)
-            if (base + q < Pn) B.alive[base + q] = 1;
+    if (resample) {
+        if (fullv) {
+#pragma unroll
+            for (int g = 0; g < CUT_GROUPS; ++g) *reinterpret_cast<uchar4 *>(B.alive + base + 4 * g) = make_uchar4(1, 1, 1, 1);
+        } else {
+            for (int q = 0; q < PT; ++q)
+                if (base + q < Pn) B.alive[base + q] = 1;
+        }
+    }
     if (!barrier || P.world == 1) return;
     if (!last_block(&c->tk_compact)) return;
     if (!xbarrier(x)) raise_peer_error(c); // every table is complete before any rank's sweep reads it
