@@ -49,14 +49,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 // true for exactly one block of the grid: the last one to arrive (its reads see every other block's writes).
 // sys: the other blocks wrote into PEER memory, which the last block is about to publish with a barrier.
+// One fence per block, by the thread that takes the ticket AFTER the block-wide barrier (the pattern of a cooperative
+// grid sync): fences are cumulative over what the barrier ordered before them, and a fence.sys costs microseconds -- one
+// per warp of a 512-thread block was most of a barrier's latency.
 __device__ __forceinline__ bool last_block(unsigned int *ticket, bool sys = false) {
     __shared__ int s_last;
-    if (sys) __threadfence_system();
-    else __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        if (sys) __threadfence_system();
+        else __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        __threadfence();
+    }
     __syncthreads();
-    if (s_last) __threadfence();
     return s_last;
 }
 
@@ -65,31 +70,32 @@ __device__ __forceinline__ bool last_block(unsigned int *ticket, bool sys = fals
 #endif
 
 // Cross-rank barrier, called by EVERY thread of ONE block per rank (blockDim.x >= world).  Returns false on timeout.
+// Thread r (r < world, all in warp 0) handles peer r: fence.sys (cumulative over the block's earlier writes, which the
+// block barrier ordered before it), release-store of the sequence number into the peer's flag array, acquire-spin on the
+// peer's slot of the own flag array; the closing block barrier orders every thread's later reads after the acquires.
 __device__ __forceinline__ bool xbarrier(const XPeer &x) {
     if (x.world == 1) { // single rank: still a block-level barrier (callers read what other threads wrote before it)
         __syncthreads();
         return true;
     }
     __shared__ int s_ok;
-    __threadfence_system(); // this thread's pushes and local writes, before the arrival
     if (threadIdx.x == 0) s_ok = 1;
     __syncthreads();
     const unsigned long long n = *x.seq + 1ull;
     const int r = (int)threadIdx.x;
-    if (r < x.world && r != x.rank)
-        st_release_sys(reinterpret_cast<unsigned long long *>(x.arena[r]) + x.rank, n);
     if (r < x.world && r != x.rank) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long *>(x.arena[r]) + x.rank, n);
         const unsigned long long *f = reinterpret_cast<const unsigned long long *>(x.arena[x.rank]) + r;
         const unsigned long long t0 = global_timer_ns();
         unsigned int spins = 0;
         while (ld_acquire_sys(f) < n) {
             if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > KABC_PEER_TIMEOUT_NS) { s_ok = 0; break; }
-            __nanosleep(64);
         }
+        __threadfence_system();
     }
     __syncthreads();
     if (threadIdx.x == 0) *x.seq = n; // also after a timeout: the job is dead anyway, keep the counters aligned
-    __threadfence_system();
     __syncthreads();
     return s_ok != 0;
 }
