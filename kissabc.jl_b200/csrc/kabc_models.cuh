@@ -251,6 +251,77 @@ struct LvSim {
     __device__ __forceinline__ double result() const { return capped ? dinf() : xsqrt(xdiv(acc, (double)(2 * G))); }
 };
 
+// F32 instantiation: the copy numbers are exact in FP32 (< 2^24: the event cap bounds them), propensities, waiting time
+// and reaction choice are FP32 with MUFU lg2 / rcp (no FP64 division per event), the clock is FP64 (one DADD per event: a
+// 20 000-event trajectory must not drift across the 16 recording times) and so are the <= 32 squared grid differences.
+// Same Philox words in the same roles as the F64 machine; trajectories decorrelate from it after the first waiting time
+// that rounds differently, so this mode is compared with F64 in distribution (tests/test_gpu_parity.py).
+template <>
+struct LvSim<true> {
+    float c1, c2, c3, X, Y;
+    double t, dt, acc;
+    long long ev, max_events;
+    uint32_t blk, w2, w3, id, epoch, tag;
+    int g, G, have;
+    bool capped;
+
+    __device__ __forceinline__ void init(const DModel &m, uint32_t tag_, uint32_t id_, uint32_t epoch_, double l1, double l2,
+                                         double l3) {
+        c1 = (float)xexp(l1); c2 = (float)xexp(l2); c3 = (float)xexp(l3);
+        X = (float)m.param[0]; Y = (float)m.param[1];
+        G = (int)m.param[3];
+        max_events = (long long)m.param[4];
+        dt = xdiv(m.param[2], (double)G);
+        t = 0.0; acc = 0.0; g = 0; ev = 0; blk = 0; w2 = 0; w3 = 0; have = 0; capped = false;
+        id = id_; epoch = epoch_; tag = tag_;
+    }
+    __device__ __forceinline__ bool step(const DModel &m, const RoundKeys &rk) {
+        if (g >= G) return true;
+        const float a1 = __fmul_rn(c1, X), a2 = __fmul_rn(__fmul_rn(c2, X), Y), a3 = __fmul_rn(c3, Y);
+        const float a0 = __fadd_rn(__fadd_rn(a1, a2), a3);
+        double tn;
+        uint32_t u1 = 0;
+        if (a0 > 0.f) {
+            if (ev >= max_events) { capped = true; return true; }
+            uint32_t u0;
+            if (have == 0) {
+                uint32_t w0, w1;
+                philox4x32_10(rk, blk, id, epoch, tag, w0, w1, w2, w3);
+                blk += 1;
+                have = 1;
+                u0 = w0; u1 = w1;
+            } else {
+                have = 0;
+                u0 = w2; u1 = w3;
+            }
+            const float uf = __fmaf_rn(__uint2float_rn(u0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+            float rcp;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(a0));
+            const float wait = __fmul_rn(__fmul_rn(mufu_lg2(uf), -0.6931471805599453f), rcp);
+            tn = t + (double)wait;
+        } else {
+            tn = dinf();
+        }
+        while (g < G && (double)(g + 1) * dt <= tn) { // record the pre-event state
+            const double dx = (double)X - m.target[g], dy = (double)Y - m.target[G + g];
+            acc += dx * dx;
+            acc += dy * dy;
+            ++g;
+        }
+        if (g >= G) return true;
+        // 24-bit uniform strictly inside (0,1): (w+0.5) 2^-32 rounds to 1.0f for the top 128 words, and r = a0 would fire a
+        // reaction whose propensity is zero
+        const float r = __fmul_rn(__fmaf_rn((float)(u1 >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f), a0);
+        if (r < a1) X += 1.f;
+        else if (r < __fadd_rn(a1, a2)) { X -= 1.f; Y += 1.f; }
+        else Y -= 1.f;
+        t = tn;
+        ++ev;
+        return false;
+    }
+    __device__ __forceinline__ double result() const { return capped ? dinf() : sqrt(acc / (double)(2 * G)); }
+};
+
 template <bool F32>
 __device__ __forceinline__ double cost_lv(const DModel &m, const RoundKeys &rk, uint32_t tag, uint32_t id,
                                           uint32_t epoch, double l1, double l2, double l3, long long &events) {

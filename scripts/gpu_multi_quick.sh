@@ -2,7 +2,8 @@
 N=${1:-2}
 mkdir -p gpurun_out
 if ! timeout 120 python __graft_entry__.py --smoke > gpurun_out/smoke.txt 2>&1; then echo "SMOKE FAILED"; tail -20 gpurun_out/smoke.txt; exit 1; fi
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -v --timeout 300 -x -k "nccl and (normal_small or lv_smc or ais)" 2>&1 | grep -E "PASSED|FAILED|SKIPPED|ERROR|passed|failed|Error|assert" | tail -4
+KABC_TEST_WORLDS=${KABC_TEST_WORLDS:-$N} timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -v --timeout 300 -x -k "nccl and (normal_small or lv_smc or ais or normal_smc)" 2>&1 | grep -E "PASSED|FAILED|SKIPPED|ERROR|passed|failed|Error|assert" > gpurun_out/multi_parity_${N}gpu.txt
+tail -4 gpurun_out/multi_parity_${N}gpu.txt
 for G in 1 $N; do
   if [ $G = 1 ]; then L="python"; else L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29618"; fi
   timeout 300 $L bench.py --gpus $G --steps 20 --warmup 5 --no-cpu-baseline --no-extra 2>gpurun_out/bench_${G}gpu.err | grep '^{' > gpurun_out/bench_${G}gpu.json

@@ -36,7 +36,11 @@ def _worlds(backend):
     g = _ngpu()
     if backend == "gloo":
         return [2, 3]
-    return [w for w in (2, 4, 8) if w <= g]
+    ws = [w for w in (2, 4, 8) if w <= g]
+    only = os.environ.get("KABC_TEST_WORLDS")  # e.g. "8": a single world size on an expensive multi-GPU lease
+    if only:
+        ws = [w for w in ws if str(w) in only.split(",")]
+    return ws
 
 
 def _check_smc(kabc, ctx, tmp_path, world, name, prec, N, iters, retrys):
