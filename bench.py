@@ -35,11 +35,11 @@ import numpy as np  # noqa: E402
 SEED = 0x4B49535341424300
 # SURVEY.md section 8(d) pre-implementation estimate of the algorithmic thread-instructions per unit of work: only used when
 # profiles/instr_table.json has no MEASURED figure for the workload (the line then says so)
-W_SURVEY = {"normal_smc": 2.7e4, "ma2_smc": 3.0e3, "gk_ais": 6.7e5, "lv_smc": 52.0}
+W_SURVEY = {"normal_smc": 2.7e4, "ma2_smc": 3.0e3, "gk_ais": 6.7e5, "lv_smc": 52.0, "null_smc": 1.0e3}
 WORKLOADS = list(W_SURVEY)
 # algorithmic state bytes per cost evaluation of an smc sweep at d parameters: 8(3d+1)+1 read, 8(d+2) written
 STATE_BYTES = lambda d: 8 * (3 * d + 1) + 1 + 8 * (d + 2)  # noqa: E731
-EPS_TARGET = {"normal_smc": 0.0111, "ma2_smc": 0.1, "lv_smc": None, "gk_ais": None}
+EPS_TARGET = {"normal_smc": 0.0111, "ma2_smc": 0.1, "lv_smc": None, "gk_ais": None, "null_smc": None}
 FLUSH_BYTES = 256 << 20  # > 126 MB L2
 
 
@@ -120,13 +120,15 @@ def oracle_objects(O, name):
         return O.make_priors([("uniform", -2, 2), ("uniform", -1, 1)]), O.make_model(O.MA2_AUTOCOV, 100, MA2_TARGET), 2
     if name == "gk_ais":
         return O.make_priors([("uniform", 0, 10)] * 4), O.make_model(O.GK_OCTILE, 10000, GK_TARGET, (0.8,)), 4
+    if name == "null_smc":
+        return O.make_priors([("uniform", 0, 3)]), O.make_model(O.DETERMINISTIC, 0, (1.5,), (1.0,)), 1
     return (O.make_priors([("uniform", -2, 1), ("uniform", -7, -4), ("uniform", -2, 1)]),
             O.make_model(O.LV_SSA, 0, LV_TARGET_X + LV_TARGET_Y, (50, 100, 30, 16, 20000)), 3)
 
 
 # particles / walkers of the CPU legs.  The headline workload runs at the device arm's own size (2^20 particles: ~1.5 s of CPU
 # work per step on 16 threads); the heavier simulators run on a bounded sample, as the contract allows.
-REF_PARTICLES = {"normal_smc": 1 << 20, "ma2_smc": 1 << 20, "lv_smc": 1 << 13, "gk_ais": 1 << 10}
+REF_PARTICLES = {"normal_smc": 1 << 20, "ma2_smc": 1 << 20, "lv_smc": 1 << 13, "gk_ais": 1 << 10, "null_smc": 1 << 20}
 
 
 def cpu_baseline(name, budget_s=14.0, threads=None):
@@ -453,7 +455,7 @@ def main():
     peaks, peak_src = measured_peaks()
     sm_count = ctx.sm_count()
     if not args.no_extra and world == 1 and name == "normal_smc":
-        for wl, lg, st in (("ma2_smc", 20, 20), ("lv_smc", 20, 6), ("gk_ais", 18, 3)):
+        for wl, lg, st in (("ma2_smc", 20, 20), ("lv_smc", 20, 6), ("gk_ais", 18, 3), ("null_smc", 20, 20)):
             try:
                 x = time_workload(k, ctx, wl, "f32", 1 << lg, 1, st, 3, None, dev)
                 units = x["events"] if wl == "lv_smc" else x["evals"]
@@ -463,6 +465,13 @@ def main():
                                                      sm_count, 1, x["clocks"], peaks, peak_src, x["is_ais"])}
                 if wl == "lv_smc":
                     extra[wl]["ssa_events_per_s"] = x["events"] / (x["ms_total"] * 1e-3)
+                if wl == "null_smc":  # state sweep against the HBM roofline: every particle's rows move once per iteration
+                    per_it = x["N"] * (STATE_BYTES(x["d"]) + 8 * (x["d"] + 2) * 2)  # sweep + table write/read of [theta|X|lpi]
+                    gbs = per_it * st / (x["ms_total"] * 1e-3) / 1e9
+                    extra[wl]["hbm_sweep"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                              "bytes_per_iteration": per_it,
+                                              "note": "algorithmic state bytes of one iteration with a null simulator (L2 flushed before each); "
+                                                      "the iteration is launch/latency bound, not HBM bound"}
             except Exception as exc:  # an extra line must never take the headline down
                 extra[wl] = {"error": str(exc)[:300]}
 

@@ -469,6 +469,7 @@ static void ais_launch_sim_t(kabc_ais *s, long long n, int colour) {
 }
 
 static int ais_enqueue_half(kabc_ais *s, int colour) {
+    NvtxRange nv(colour == 0 ? "kabc:ais:half-step red" : "kabc:ais:half-step black");
     kabc_ctx *ctx = s->ctx;
     const AisOwn own = ais_own(s->P.N, ctx->rank, ctx->world);
     const long long n = own.n[colour];
@@ -497,6 +498,7 @@ static int ais_enqueue_half(kabc_ais *s, int colour) {
 
 // one red/black sweep = 2 half-steps = 4 kernels, replayed from a CUDA graph (small ensembles are launch bound)
 static int ais_launch_sweep(kabc_ais *s) {
+    NvtxRange nv("kabc:ais:sweep");
     kabc_ctx *ctx = s->ctx;
     static const bool env_off = [] { const char *e = getenv("KABC_NO_GRAPH"); return e && e[0] == '1'; }();
     if (!s->graph_ok || env_off) {

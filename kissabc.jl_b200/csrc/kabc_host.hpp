@@ -107,6 +107,14 @@ int ingest_model(const kabc_model_t *model, int d, DModel &out);
 int arena_reserve(kabc_ctx *ctx, size_t bytes);
 int arena_alloc(kabc_ctx *ctx, size_t bytes, size_t *offset);
 void arena_release(kabc_ctx *ctx); // one user less; the bump pointer rewinds when nobody is left
+// NVTX ranges around the phases of an iteration (header-only NVTX3: no-ops unless a profiler is attached).
+// Under a CUDA graph replay the ranges of the captured launches are those of the capture.
+void nvtx_push(const char *name);
+void nvtx_pop();
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtx_push(name); }
+    ~NvtxRange() { nvtx_pop(); }
+};
 int eval_cost_list_device(kabc_ctx *ctx, const DModel &m, const double *d_th, long long N, const unsigned int *list,
                           const unsigned int *count, long long max_count, uint32_t tag, uint32_t epoch, double *d_out);
 

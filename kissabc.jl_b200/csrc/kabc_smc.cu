@@ -1569,6 +1569,7 @@ static int smc_gk_grid(kabc_smc *s, size_t &smem) {
 }
 
 static int smc_enqueue_init(kabc_smc *s) {
+    NvtxRange nv("kabc:smc:init");
     kabc_ctx *ctx = s->ctx;
     k_smc_reset<<<4, 1024, 0, ctx->stream>>>(s->B, s->P);
     SMC_LAUNCHED(s, 1);
@@ -1599,6 +1600,7 @@ static int smc_enqueue_init(kabc_smc *s) {
 
 // the table a sweep reads + one MCMC sweep (+ bookkeeping and the next quantile's first histogram in its last block)
 static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
+    NvtxRange nv("kabc:smc:table+sweep");
     kabc_ctx *ctx = s->ctx;
     const int ci = close_iter ? 1 : 0;
     k_compact<<<s->nblocks_scan, CUT_THREADS, 0, ctx->stream>>>(s->B, s->P, s->X, 0, 1);
@@ -1661,6 +1663,7 @@ static int smc_enqueue_sweep(kabc_smc *s, bool close_iter) {
 }
 
 static int smc_enqueue_cut(kabc_smc *s) {
+    NvtxRange nv("kabc:smc:quantile+cut");
     kabc_ctx *ctx = s->ctx;
     int sel_blocks = (int)((s->P.P + SEL_THREADS * 16 - 1) / (SEL_THREADS * 16));
     if (sel_blocks > ctx->sm_count * 2) sel_blocks = ctx->sm_count * 2;
@@ -1721,6 +1724,7 @@ static void smc_drop_graph(kabc_smc *s) {
 // enqueue one iteration: through the captured graph when the launch sequence is fixed (no retry sweeps, which need the
 // host between sweeps), else kernel by kernel
 static int smc_launch_iteration(kabc_smc *s) {
+    NvtxRange nv("kabc:smc:iteration");
     kabc_ctx *ctx = s->ctx;
     static const bool env_off = [] { const char *e = getenv("KABC_NO_GRAPH"); return e && e[0] == '1'; }();
     const bool eligible = s->graph_ok && !env_off && !s->prof && s->P.mcmc_retrys == 0;

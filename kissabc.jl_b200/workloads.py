@@ -1,5 +1,5 @@
 """The benchmark configurations of BASELINE.json as product-side descriptors."""
-from .api import Factored, GandK, LotkaVolterra, MA2, NormalMeanStd, Normal, Truncated, Uniform
+from .api import Deterministic, Factored, GandK, LotkaVolterra, MA2, NormalMeanStd, Normal, Truncated, Uniform
 
 # observed summaries (fixed synthetic data; no external datasets)
 MA2_TARGET = [0.72, 0.2]  # E[tau1], E[tau2] at theta = (0.6, 0.2): th1 + th1 th2, th2
@@ -32,4 +32,11 @@ def lv(prec="f32", n=0, cap=LV_MAX_EVENTS):
             LotkaVolterra(LV_TARGET_X + LV_TARGET_Y, 50, 100, 30, cap, precision=prec))
 
 
-WORKLOADS = {"normal_smc": normal, "ma2_smc": ma2, "gk_ais": gk, "lv_smc": lv}
+def null(prec="f64", n=0):
+    """SURVEY.md 8(d) sanity sweep: smc with a (nearly) null simulator, |theta - 1.5| -- what is left is the state traffic of an
+    iteration (quantile, cut, table, gathers, accept), to be read against the measured HBM bandwidth."""
+    del prec, n
+    return Factored(Uniform(0, 3)), Deterministic(1, 1.5)
+
+
+WORKLOADS = {"normal_smc": normal, "ma2_smc": ma2, "gk_ais": gk, "lv_smc": lv, "null_smc": null}
