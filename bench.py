@@ -419,7 +419,7 @@ def main():
     if not args.no_e2e and not is_ais:
         import ctypes as C
         eps_t = EPS_TARGET[name]
-        kw = dict(nparticles=N, ctx=ctx)
+        kw = dict(nparticles=N, ctx=ctx, gather="all" if world == 1 else "root")
         if eps_t is not None:
             kw["epstol"] = eps_t
         else:
@@ -435,10 +435,11 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         h2d = d * C.sizeof(k._capi.PriorT) + C.sizeof(k._capi.ModelT) + C.sizeof(k._capi.SmcConfigT)
-        d2h = N * (8 * d + 1 + 8) + 56 * res.iterations
+        d2h = N * (8 * d + 1 + 8) + 56 * res.iterations  # theta, alive, C on the receiving rank + the iteration log
         e2e = {"value": res.cost_evals / dt, "unit": "cost evals/s", "h2d_bytes_per_step": h2d / max(res.iterations, 1),
                "d2h_bytes_per_step": d2h / max(res.iterations, 1),
-               "call": "kissabc_jl_b200.smc(prior, cost, nparticles=N, epstol=target) on every rank (every rank receives the whole result)",
+               "call": "kissabc_jl_b200.smc(prior, cost, nparticles=N, epstol=target" + (")" if world == 1 else ", gather='root') on every rank (collective; "
+                       "rank 0 receives the whole result)"),
                "iterations": res.iterations, "cost_evals": res.cost_evals, "eps": res.eps, "time_s": dt, "eps_target": eps_t}
     elif not args.no_e2e and is_ais:
         post = k.ApproxKernelizedPosterior(prior, cost, 0.5)

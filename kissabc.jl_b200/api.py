@@ -470,10 +470,14 @@ def _bundle(theta_rows: np.ndarray):
 
 def smc(prior, cost: DeviceCost, *, nparticles=100, alpha=0.95, mcmc_retrys=0, mcmc_tol=0.015, epstol=0.0,
         r_epstol=None, min_r_ess=None, max_stretch=2.0, verbose=False, parallel=False, max_iterations=0,
-        ctx: Optional[Context] = None) -> SmcResult:
+        ctx: Optional[Context] = None, gather: str = "all") -> SmcResult:
     """smc(prior, cost; kw...) -> (P, C, eps), ref src/smc.jl:92-206.  `parallel` is accepted and ignored
-    (the device path is always parallel); `rng` is replaced by the context seed."""
+    (the device path is always parallel); `rng` is replaced by the context seed.
+    Multi-rank contexts: the call is collective.  gather="all" (default): every rank receives the whole result;
+    gather="root": only rank 0 copies the particles out (P and C are None on the other ranks; eps, iterations, log everywhere)."""
     del parallel
+    if gather not in ("all", "root"):
+        raise KissABCError(K.ERR_INVALID_ARG, "gather must be 'all' or 'root'")
     if not isinstance(cost, DeviceCost):
         raise KissABCError(K.ERR_INVALID_ARG, "the device path needs a registered DeviceCost, not a closure")
     ctx = ctx or default_context()
@@ -481,20 +485,27 @@ def smc(prior, cost: DeviceCost, *, nparticles=100, alpha=0.95, mcmc_retrys=0, m
     cfg = smc_config(nparticles, alpha, mcmc_retrys, mcmc_tol, epstol, r_epstol, min_r_ess, max_stretch, verbose,
                      max_iterations)
     d, N = len(prior), int(nparticles)
-    th = np.empty((d, max(N, 1))); alive = np.empty(max(N, 1), dtype=np.uint8); X = np.empty(max(N, 1))
+    want = gather == "all" or ctx.rank == 0
+    th = np.empty((d, max(N, 1))) if want else None
+    alive = np.empty(max(N, 1), dtype=np.uint8) if want else None
+    X = np.empty(max(N, 1)) if want else None
     eps, it, evals = C.c_double(), C.c_int64(), C.c_int64()
     cap = 1 << 13
     logbuf = (K.SmcLogT * cap)()
     m = cost._pod()
-    K.check(ctx.L.kabc_smc_run(ctx.h, prior._pods(), d, C.byref(m), C.byref(cfg), K.dptr(th), K.u8ptr(alive),
-                               K.dptr(X), C.byref(eps), C.byref(it), C.byref(evals), logbuf, cap))
+    K.check(ctx.L.kabc_smc_run(ctx.h, prior._pods(), d, C.byref(m), C.byref(cfg), K.dptr(th) if want else None,
+                               K.u8ptr(alive) if want else None, K.dptr(X) if want else None, C.byref(eps), C.byref(it),
+                               C.byref(evals), logbuf, cap))
     n = min(it.value, cap)
     log = [dict((f, getattr(logbuf[i], f)) for f, _ in K.SmcLogT._fields_) for i in range(n)]
     if verbose:
         for r in log:
             print(f"(iteration, ϵ, ESS) = ({r['iteration']}, {r['eps']!r}, {r['n_alive']})")
-    return SmcResult(P=_bundle(th[:, alive.astype(bool)]), C=X, eps=eps.value, iterations=it.value,
-                     cost_evals=evals.value, log=log)
+    if not want:
+        return SmcResult(P=None, C=None, eps=eps.value, iterations=it.value, cost_evals=evals.value, log=log)
+    mask = alive.astype(bool)
+    rows = th if mask.all() else th[:, mask]  # after a resampling iteration everything is alive: no copy of the 8 d N bytes
+    return SmcResult(P=_bundle(rows), C=X, eps=eps.value, iterations=it.value, cost_evals=evals.value, log=log)
 
 
 # --------------------------------------------------------------------------------------- ABCDE, pfilter

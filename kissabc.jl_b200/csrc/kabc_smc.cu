@@ -78,6 +78,7 @@ struct SmcParams { // launch constants
     long long mcmc_retrys;
     int max_iterations;
     int rank, world;
+    int prefetch; // queued sweep: request the partner rows of a tile with cp.async one chunk ahead (KABC_PREFETCH=0 disables)
 };
 
 struct SmcTrace {
@@ -963,8 +964,7 @@ __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParam
     long long el;
     const int ro = locate(off, G, resample ? (long long)((unsigned int)i % (unsigned int)n_src) : i, el);
     double row[DM], Xi = 0.0, lpi_i = 0.0, unused0, unused1;
-    if (DM == 2 && pf) { row[0] = pf[0]; row[1 % DM] = pf[1]; Xi = pf[2]; lpi_i = pf[3]; } // rows prefetched by smc_prefetch_one
-    else load_row<DM>(tab_th(B, ro) + el * P.TS, P.d, row, true, Xi, lpi_i);
+    load_row<DM>(tab_th(B, ro) + el * P.TS, P.d, row, true, Xi, lpi_i);
     const bool alive_i = resample ? true : (B.alive[li] != 0);
     if (resample) {
 #pragma unroll
@@ -984,7 +984,7 @@ __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParam
         const int ra = locate(off, G, resample ? (long long)((unsigned int)a % (unsigned int)n_src) : a, ea);
         const int rb = locate(off, G, resample ? (long long)((unsigned int)b % (unsigned int)n_src) : b, eb);
         double pa[DM], pb[DM];
-        if (DM == 2 && pf) { pa[0] = pf[4]; pa[1 % DM] = pf[5]; pb[0] = pf[6]; pb[1 % DM] = pf[7]; }
+        if (DM == 2 && pf) { pa[0] = pf[0]; pa[1 % DM] = pf[1]; pb[0] = pf[2]; pb[1 % DM] = pf[3]; } // prefetched by smc_prefetch_one
         else {
             load_row<DM>(tab_th(B, ra) + ea * P.TS, P.d, pa, false, unused0, unused1);
             load_row<DM>(tab_th(B, rb) + eb * P.TS, P.d, pb, false, unused0, unused1);
@@ -1033,10 +1033,11 @@ __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParam
     return pass;
 }
 
-// Stage 1 of a proposal at d = 2: the row addresses depend only on the particle's Philox stream and on the table offsets,
-// so the own row (32 B) and the two partner rows (16 B each) are requested with cp.async (LDGSTS: global -- possibly peer --
-// memory to shared memory, no destination registers) long before the proposal arithmetic needs them; the CTA simulates a
-// chunk in between, which covers the NVLink round trips of a multi-GPU job.  slot: 8 doubles of this thread in shared memory.
+// Stage 1 of a proposal at d = 2: the partner rows are RANDOM rows of the whole population (7/8 of them on other GPUs of an
+// 8-GPU job) and their addresses depend only on the particle's Philox stream and on the table offsets, so they are requested
+// with cp.async (LDGSTS: global -- possibly peer -- memory to shared memory, no destination registers) long before the
+// proposal arithmetic needs them; the CTA simulates a chunk in between, which covers the NVLink round trips.  The own row is
+// a coalesced read of consecutive table entries and stays a plain load.  slot: 4 doubles of this thread in shared memory.
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
@@ -1049,11 +1050,6 @@ __device__ __forceinline__ void smc_prefetch_one(const SmcBufs &B, const SmcPara
     const int G = P.world;
     const int resample = c->resample;
     const long long n_src = off[G];
-    long long el;
-    const int ro = locate(off, G, resample ? (long long)((unsigned int)i % (unsigned int)n_src) : i, el);
-    const double *own = tab_th(B, ro) + el * 4;
-    cp_async16(slot, own);
-    cp_async16(slot + 2, own + 2);
     if (resample || B.alive[li] != 0) {
         Stream st(rk, ST_PROPOSE, (uint32_t)i, c->epoch);
         long long a = i, b = i;
@@ -1062,8 +1058,8 @@ __device__ __forceinline__ void smc_prefetch_one(const SmcBufs &B, const SmcPara
         long long ea, eb;
         const int ra = locate(off, G, resample ? (long long)((unsigned int)a % (unsigned int)n_src) : a, ea);
         const int rb = locate(off, G, resample ? (long long)((unsigned int)b % (unsigned int)n_src) : b, eb);
-        cp_async16(slot + 4, tab_th(B, ra) + ea * 4);
-        cp_async16(slot + 6, tab_th(B, rb) + eb * 4);
+        cp_async16(slot, tab_th(B, ra) + ea * 4);
+        cp_async16(slot + 2, tab_th(B, rb) + eb * 4);
     }
 }
 
@@ -1240,7 +1236,7 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
     __shared__ unsigned long long s_res[4];
     __shared__ SweepShared sh;
     __shared__ unsigned int s_cnt[8], s_base, s_act, s_unit, s_len;
-    __shared__ __align__(16) double s_pf[DM == 2 ? 2 * 256 * 8 : 2]; // prefetched rows: [sub-particle][thread][own 4 | a 2 | b 2]
+    __shared__ __align__(16) double s_pf[DM == 2 ? 2 * 256 * 4 : 2]; // prefetched partner rows: [sub-particle][thread][a 2 | b 2]
     SmcCtrl *c = B.ctrl;
     if (smc_skip(c) || c->retry_done) return;
     if (threadIdx.x <= P.world) sh.off[threadIdx.x] = c->off[threadIdx.x];
@@ -1253,7 +1249,7 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
     const unsigned int ntiles = (unsigned int)((Pn + QTILE - 1) / QTILE);
     const unsigned int nchunks_max = (unsigned int)((Pn + 255) / 256);
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool can_prefetch = DM == 2 && P.d == 2;
+    const bool can_prefetch = DM == 2 && P.d == 2 && P.prefetch;
     unsigned long long t_wait0 = 0;
     unsigned int my_chunk = 0xFFFFFFFFu, pending = 0xFFFFFFFFu; // thread 0: claimed chunk, prefetched tile
     bool sim_since_prefetch = false;
@@ -1302,7 +1298,7 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
 #pragma unroll
                 for (int sp = 0; sp < 2; ++sp) {
                     const long long li = (long long)unit * QTILE + sp * 256 + threadIdx.x;
-                    if (li < Pn) smc_prefetch_one(B, P, c, rk, sh.off, li, &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 8 : 0)]);
+                    if (li < Pn) smc_prefetch_one(B, P, c, rk, sh.off, li, &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 4 : 0)]);
                 }
                 cp_async_commit();
             }
@@ -1316,7 +1312,7 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
                 if (li < Pn) {
                     Proposed<DM> pr;
                     pass[sp] = smc_propose_one<DM>(B, P, c, pri, rk, sh.off, li, pr, alive_i,
-                                                   can_prefetch ? &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 8 : 0)] : nullptr);
+                                                   can_prefetch ? &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 4 : 0)] : nullptr);
                     if (alive_i && !pass[sp]) note_final_shared(sh, B.hist, pr.Xi);
                     if (pass[sp]) {
 #pragma unroll
@@ -1500,7 +1496,7 @@ __global__ void k_recount(SmcBufs B, SmcParams P) {
 // the whole population (rows of every rank, read from the identity tables) in the caller's layout: theta[k*N + i], ...
 __global__ void __launch_bounds__(256) k_gather_full(SmcBufs B, SmcParams P, XPeer x, double *th, double *X, double *lpi,
                                                      unsigned char *alive) {
-    const long long N = P.N;
+    const long long N = (th || X || lpi || alive) ? P.N : 0; // a rank that wants nothing only takes part in the barrier
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / P.P);
         const long long e = i - (long long)r * P.P;
@@ -1849,6 +1845,10 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->P.sqrt_np = sqrt((double)d);
     s->P.mcmc_retrys = cfg->mcmc_retrys; s->P.max_iterations = cfg->max_iterations;
     s->P.rank = ctx->rank; s->P.world = ctx->world;
+    {
+        const char *e = getenv("KABC_PREFETCH");
+        s->P.prefetch = (e && e[0] == '0') ? 0 : 1;
+    }
     s->X = make_xpeer(ctx);
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
     const size_t nd = (size_t)Pn * d;
