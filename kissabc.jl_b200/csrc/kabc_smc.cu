@@ -78,7 +78,8 @@ struct SmcParams { // launch constants
     long long mcmc_retrys;
     int max_iterations;
     int rank, world;
-    int prefetch; // queued sweep: request the partner rows of a tile with cp.async one chunk ahead (KABC_PREFETCH=0 disables)
+    int prefetch; // queued sweep: request the partner rows of a tile with cp.async one chunk ahead (KABC_PREFETCH=0/1)
+    int nsub;     // queued sweep: particles per thread of a tile (tile = 256 nsub particles; KABC_TILE=256/512)
 };
 
 struct SmcTrace {
@@ -1223,7 +1224,7 @@ __global__ void __launch_bounds__(256, 6) k_smc_simulate_list(SmcBufs B, SmcPara
 // complete once fill[h] == 256, or == the remainder when all tiles are published.  Chunk and tile claims are plain
 // atomicAdds (a CAS loop on the list head serialised the 888 CTAs: 3.5 ms per sweep).
 enum { QACT_SIM = 1, QACT_PREFETCH = 2, QACT_FINISH = 3, QACT_EXIT = 4, QACT_RETRY = 5 };
-constexpr int QTILE = 512; // particles per tile: two per thread
+constexpr int QSUB_MAX = 2; // a tile is 256 or 512 consecutive particles: one or two per thread
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1246,6 +1247,7 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
         sh.kmin = ~0ull; sh.acc = 0; sh.work = 0; sh.below = 0; sh.above = 0;
     }
     const long long Pn = P.P;
+    const int QTILE = 256 * P.nsub;
     const unsigned int ntiles = (unsigned int)((Pn + QTILE - 1) / QTILE);
     const unsigned int nchunks_max = (unsigned int)((Pn + 255) / 256);
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1296,20 +1298,20 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
         if (act == QACT_PREFETCH) {
             if (can_prefetch) {
 #pragma unroll
-                for (int sp = 0; sp < 2; ++sp) {
+                for (int sp = 0; sp < QSUB_MAX; ++sp) {
                     const long long li = (long long)unit * QTILE + sp * 256 + threadIdx.x;
-                    if (li < Pn) smc_prefetch_one(B, P, c, rk, sh.off, li, &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 4 : 0)]);
+                    if (sp < P.nsub && li < Pn) smc_prefetch_one(B, P, c, rk, sh.off, li, &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 4 : 0)]);
                 }
                 cp_async_commit();
             }
         } else if (act == QACT_FINISH) {
             if (can_prefetch) cp_async_wait_all(); // every thread reads back only what it requested itself
             bool pass[2] = {false, false};
-#pragma unroll 1
-            for (int sp = 0; sp < 2; ++sp) {
+#pragma unroll
+            for (int sp = 0; sp < QSUB_MAX; ++sp) {
                 const long long li = (long long)unit * QTILE + sp * 256 + threadIdx.x;
                 bool alive_i = false;
-                if (li < Pn) {
+                if (sp < P.nsub && li < Pn) {
                     Proposed<DM> pr;
                     pass[sp] = smc_propose_one<DM>(B, P, c, pri, rk, sh.off, li, pr, alive_i,
                                                    can_prefetch ? &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 4 : 0)] : nullptr);
@@ -1846,8 +1848,11 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->P.mcmc_retrys = cfg->mcmc_retrys; s->P.max_iterations = cfg->max_iterations;
     s->P.rank = ctx->rank; s->P.world = ctx->world;
     {
-        const char *e = getenv("KABC_PREFETCH");
-        s->P.prefetch = (e && e[0] == '0') ? 0 : 1;
+        // measured (profiles/scaling_r2.md): on one GPU the plain queue with 256-particle tiles is fastest; with peers the
+        // partner rows are prefetched one chunk ahead and a tile holds two particles per thread
+        const char *e = getenv("KABC_PREFETCH"), *t = getenv("KABC_TILE");
+        s->P.prefetch = e ? (e[0] == '1') : (ctx->world > 1);
+        s->P.nsub = t ? (atoi(t) == 512 ? 2 : 1) : (s->P.prefetch ? 2 : 1);
     }
     s->X = make_xpeer(ctx);
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
