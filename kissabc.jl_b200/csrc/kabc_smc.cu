@@ -78,8 +78,6 @@ struct SmcParams { // launch constants
     long long mcmc_retrys;
     int max_iterations;
     int rank, world;
-    int prefetch; // queued sweep: request the partner rows of a tile with cp.async one chunk ahead (KABC_PREFETCH=0/1)
-    int nsub;     // queued sweep: particles per thread of a tile (tile = 256 nsub particles; KABC_TILE=256/512)
 };
 
 struct SmcTrace {
@@ -951,7 +949,7 @@ __device__ __forceinline__ void load_row(const double *t, int d, double (&row)[D
 template <int DM>
 __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParams &P, const SmcCtrl *c, const DPriors &pri,
                                                 const RoundKeys &rk, const long long *off, long long li, Proposed<DM> &out,
-                                                bool &alive_out, const double *pf = nullptr) {
+                                                bool &alive_out) {
     const long long Pn = P.P, i = P.lo + li;
     const int G = P.world;
     const int resample = c->resample;
@@ -985,11 +983,8 @@ __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParam
         const int ra = locate(off, G, resample ? (long long)((unsigned int)a % (unsigned int)n_src) : a, ea);
         const int rb = locate(off, G, resample ? (long long)((unsigned int)b % (unsigned int)n_src) : b, eb);
         double pa[DM], pb[DM];
-        if (DM == 2 && pf) { pa[0] = pf[0]; pa[1 % DM] = pf[1]; pb[0] = pf[2]; pb[1 % DM] = pf[3]; } // prefetched by smc_prefetch_one
-        else {
-            load_row<DM>(tab_th(B, ra) + ea * P.TS, P.d, pa, false, unused0, unused1);
-            load_row<DM>(tab_th(B, rb) + eb * P.TS, P.d, pb, false, unused0, unused1);
-        }
+        load_row<DM>(tab_th(B, ra) + ea * P.TS, P.d, pa, false, unused0, unused1);
+        load_row<DM>(tab_th(B, rb) + eb * P.TS, P.d, pb, false, unused0, unused1);
         z = next_normal(st);
         const double sc = xdiv(xmul(P.max_stretch, z), P.sqrt_np);
 #pragma unroll
@@ -1032,36 +1027,6 @@ __device__ __forceinline__ bool smc_propose_one(const SmcBufs &B, const SmcParam
         }
     }
     return pass;
-}
-
-// Stage 1 of a proposal at d = 2: the partner rows are RANDOM rows of the whole population (7/8 of them on other GPUs of an
-// 8-GPU job) and their addresses depend only on the particle's Philox stream and on the table offsets, so they are requested
-// with cp.async (LDGSTS: global -- possibly peer -- memory to shared memory, no destination registers) long before the
-// proposal arithmetic needs them; the CTA simulates a chunk in between, which covers the NVLink round trips.  The own row is
-// a coalesced read of consecutive table entries and stays a plain load.  slot: 4 doubles of this thread in shared memory.
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void smc_prefetch_one(const SmcBufs &B, const SmcParams &P, const SmcCtrl *c, const RoundKeys &rk,
-                                                 const long long *off, long long li, double *slot) {
-    const long long i = P.lo + li;
-    const int G = P.world;
-    const int resample = c->resample;
-    const long long n_src = off[G];
-    if (resample || B.alive[li] != 0) {
-        Stream st(rk, ST_PROPOSE, (uint32_t)i, c->epoch);
-        long long a = i, b = i;
-        while (a == i) a = (long long)index_of(st.next(), (uint32_t)P.N);
-        while (b == i || b == a) b = (long long)index_of(st.next(), (uint32_t)P.N);
-        long long ea, eb;
-        const int ra = locate(off, G, resample ? (long long)((unsigned int)a % (unsigned int)n_src) : a, ea);
-        const int rb = locate(off, G, resample ? (long long)((unsigned int)b % (unsigned int)n_src) : b, eb);
-        cp_async16(slot, tab_th(B, ra) + ea * 4);
-        cp_async16(slot + 2, tab_th(B, rb) + eb * 4);
-    }
 }
 
 // ------------------------------------------------------------------ accept, ref :176-189
@@ -1211,20 +1176,17 @@ __global__ void __launch_bounds__(256, 6) k_smc_simulate_list(SmcBufs B, SmcPara
 }
 
 // ------------------------------------------------------------------ the queued sweep (thread-per-particle simulators)
-// ONE persistent kernel runs both phases of a sweep.  Phase A units are TILES of 512 consecutive particles (propose: own
+// ONE persistent kernel runs both phases of a sweep.  Phase A units are TILES of 256 consecutive particles (propose: own
 // row and partner gathers -- NVLink peer loads on a multi-GPU job --, FP64 proposal arithmetic, prior tests); their
 // survivors are appended to a global work list.  Phase B units are CHUNKS of 256 consecutive list entries (simulate +
-// accept, one particle per thread, every warp full).  A CTA claims the next chunk; while that chunk is incomplete it
-// produces tiles.  A tile is produced in two stages: PREFETCH (row addresses from the Philox stream, cp.async of the
-// rows into shared memory) and FINISH (proposal arithmetic, prior tests, append); when the CTA's chunk is ready it
-// prefetches a tile, simulates the chunk, then finishes the tile -- the rows cross NVLink under its own draw loops.
-// Phase A of EVERY particle reads only the frozen table and phase B only writes the state of its own particle, so the
-// result is the Jacobi update of the reference (:160-191) whatever the interleaving.
-// Protocol: a tile's entries are written, fenced, then counted into fill[chunk] (atomicAdd) and tiles_done; chunk h is
-// complete once fill[h] == 256, or == the remainder when all tiles are published.  Chunk and tile claims are plain
-// atomicAdds (a CAS loop on the list head serialised the 888 CTAs: 3.5 ms per sweep).
-enum { QACT_SIM = 1, QACT_PREFETCH = 2, QACT_FINISH = 3, QACT_EXIT = 4, QACT_RETRY = 5 };
-constexpr int QSUB_MAX = 2; // a tile is 256 or 512 consecutive particles: one or two per thread
+// accept, every warp full).  A CTA that finds a complete chunk simulates it; otherwise it proposes the next tile; so
+// proposals are produced just ahead of their consumption, spread over the whole kernel, and their (peer) load latency is
+// covered by the other CTAs' draw loops, while the balance between CTAs is that of a dynamically claimed chunk.
+// Phase A of EVERY particle still reads only the frozen table and phase B only writes the state of its own particle, so
+// the result is the Jacobi update of the reference (:160-191) whatever the interleaving.
+// Protocol: a tile's entries are written, fenced, then counted into fill[chunk] (atomicAdd) and tiles_done; chunk h may be
+// claimed (CAS on the head) once fill[h] == 256, or == the remainder when all tiles are done.
+enum { QACT_SIM = 1, QACT_PROP = 2, QACT_EXIT = 3, QACT_RETRY = 4 };
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1237,7 +1199,6 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
     __shared__ unsigned long long s_res[4];
     __shared__ SweepShared sh;
     __shared__ unsigned int s_cnt[8], s_base, s_act, s_unit, s_len;
-    __shared__ __align__(16) double s_pf[DM == 2 ? 2 * 256 * 4 : 2]; // prefetched partner rows: [sub-particle][thread][a 2 | b 2]
     SmcCtrl *c = B.ctrl;
     if (smc_skip(c) || c->retry_done) return;
     if (threadIdx.x <= P.world) sh.off[threadIdx.x] = c->off[threadIdx.x];
@@ -1247,41 +1208,32 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
         sh.kmin = ~0ull; sh.acc = 0; sh.work = 0; sh.below = 0; sh.above = 0;
     }
     const long long Pn = P.P;
-    const int QTILE = 256 * P.nsub;
-    const unsigned int ntiles = (unsigned int)((Pn + QTILE - 1) / QTILE);
-    const unsigned int nchunks_max = (unsigned int)((Pn + 255) / 256);
+    const unsigned int ntiles = (unsigned int)((Pn + 255) / 256);
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool can_prefetch = DM == 2 && P.d == 2 && P.prefetch;
     unsigned long long t_wait0 = 0;
-    unsigned int my_chunk = 0xFFFFFFFFu, pending = 0xFFFFFFFFu; // thread 0: claimed chunk, prefetched tile
-    bool sim_since_prefetch = false;
+    unsigned int my_chunk = 0xFFFFFFFFu; // thread 0: the chunk this CTA has claimed and not simulated yet
     __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) {
+            // Claims are plain atomicAdds (no retry loop: 888 CTAs claim thousands of units per sweep).  A CTA claims the next
+            // chunk first; while that chunk is incomplete it produces: it proposes tiles, whose survivors fill the chunks in
+            // order, its own included.  Claims past the end of the list are recognised once every tile is published.
             unsigned int act = QACT_RETRY, unit = 0, len = 0;
             if (my_chunk == 0xFFFFFFFFu) my_chunk = atomicAdd(&c->lv_head, 1u);
             const unsigned int h = my_chunk;
             const unsigned int done = ld_acquire_gpu_u32(&c->tiles_done);
             const unsigned int total = ld_acquire_gpu_u32(&c->work_count);
-            const unsigned int f = ld_acquire_gpu_u32(&B.fill[h < nchunks_max ? h : nchunks_max]);
+            const unsigned int f = ld_acquire_gpu_u32(&B.fill[h < ntiles ? h : ntiles]);
             const bool all_done = done == ntiles;
             const unsigned int rem = (all_done && total > h * 256u) ? (total - h * 256u) : 0u;
-            const bool ready = h < nchunks_max && (f == 256u || (all_done && rem > 0u && rem < 256u && f == rem));
-            const bool tiles_left = ld_acquire_gpu_u32(&c->tile_head) < ntiles;
-            // a prefetched tile is finished after ONE chunk at most, and at once when the list is short or when no tile is
-            // left to claim (near the end other CTAs are waiting for exactly these entries)
-            if (pending != 0xFFFFFFFFu && (sim_since_prefetch || !ready || !tiles_left)) {
-                act = QACT_FINISH; unit = pending;
-                pending = 0xFFFFFFFFu;
-            } else if (pending == 0xFFFFFFFFu && tiles_left && (can_prefetch || !ready)) {
-                const unsigned int t = atomicAdd(&c->tile_head, 1u); // before simulating: start the next tile's loads
-                if (t < ntiles) { act = QACT_PREFETCH; unit = t; pending = t; sim_since_prefetch = false; }
-            } else if (ready) {
+            if (h < ntiles && (f == 256u || (all_done && rem > 0u && rem < 256u && f == rem))) {
                 act = QACT_SIM; unit = h; len = f;
                 my_chunk = 0xFFFFFFFFu;
-                sim_since_prefetch = true;
             } else if (all_done && total <= h * 256u) {
                 act = QACT_EXIT;
+            } else if (ld_acquire_gpu_u32(&c->tile_head) < ntiles) {
+                const unsigned int t = atomicAdd(&c->tile_head, 1u);
+                if (t < ntiles) { act = QACT_PROP; unit = t; }
             } else { // every tile is claimed, some are still in flight on other CTAs: bounded wait
                 const unsigned long long now = global_timer_ns();
                 if (t_wait0 == 0) t_wait0 = now;
@@ -1295,37 +1247,22 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
         const unsigned int act = s_act, unit = s_unit, len = s_len;
         __syncthreads();
         if (act == QACT_EXIT) break;
-        if (act == QACT_PREFETCH) {
-            if (can_prefetch) {
+        if (act == QACT_PROP) {
+            const long long li = (long long)unit * 256 + threadIdx.x;
+            bool pass = false, alive_i = false;
+            if (li < Pn) {
+                Proposed<DM> pr;
+                pass = smc_propose_one<DM>(B, P, c, pri, rk, sh.off, li, pr, alive_i);
+                if (alive_i && !pass) note_final_shared(sh, B.hist, pr.Xi);
+                if (pass) {
 #pragma unroll
-                for (int sp = 0; sp < QSUB_MAX; ++sp) {
-                    const long long li = (long long)unit * QTILE + sp * 256 + threadIdx.x;
-                    if (sp < P.nsub && li < Pn) smc_prefetch_one(B, P, c, rk, sh.off, li, &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 4 : 0)]);
-                }
-                cp_async_commit();
-            }
-        } else if (act == QACT_FINISH) {
-            if (can_prefetch) cp_async_wait_all(); // every thread reads back only what it requested itself
-            bool pass[2] = {false, false};
-#pragma unroll
-            for (int sp = 0; sp < QSUB_MAX; ++sp) {
-                const long long li = (long long)unit * QTILE + sp * 256 + threadIdx.x;
-                bool alive_i = false;
-                if (sp < P.nsub && li < Pn) {
-                    Proposed<DM> pr;
-                    pass[sp] = smc_propose_one<DM>(B, P, c, pri, rk, sh.off, li, pr, alive_i,
-                                                   can_prefetch ? &s_pf[(DM == 2 ? (sp * 256 + threadIdx.x) * 4 : 0)] : nullptr);
-                    if (alive_i && !pass[sp]) note_final_shared(sh, B.hist, pr.Xi);
-                    if (pass[sp]) {
-#pragma unroll
-                        for (int k = 0; k < DM; ++k)
-                            if (k < P.d) B.thp[(long long)k * Pn + li] = pr.thp[k];
-                        B.lpip[li] = pr.lpip;
-                    }
+                    for (int k = 0; k < DM; ++k)
+                        if (k < P.d) B.thp[(long long)k * Pn + li] = pr.thp[k];
+                    B.lpip[li] = pr.lpip;
                 }
             }
-            const unsigned int ball0 = __ballot_sync(0xffffffffu, pass[0]), ball1 = __ballot_sync(0xffffffffu, pass[1]);
-            if (lane == 0) s_cnt[warp] = __popc(ball0) + __popc(ball1);
+            const unsigned int ball = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) s_cnt[warp] = __popc(ball);
             __syncthreads();
             if (threadIdx.x == 0) {
                 unsigned int tot = 0;
@@ -1336,26 +1273,24 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
             }
             __syncthreads();
             const unsigned int base = s_base, tot = s_len;
-            const unsigned int lm = (1u << lane) - 1u;
-            const unsigned int o0 = s_cnt[warp] + __popc(ball0 & lm), o1 = s_cnt[warp] + __popc(ball0) + __popc(ball1 & lm);
-            if (pass[0]) B.work[base + o0] = (unsigned int)((long long)unit * QTILE + threadIdx.x);
-            if (pass[1]) B.work[base + o1] = (unsigned int)((long long)unit * QTILE + 256 + threadIdx.x);
+            if (pass) B.work[base + s_cnt[warp] + __popc(ball & ((1u << lane) - 1u))] = (unsigned int)li;
+            __threadfence();
             __syncthreads();
-            if (threadIdx.x == 0) { // publish: per-chunk fill counts, then the tile (one fence, after the block barrier)
-                __threadfence();
+            if (threadIdx.x == 0) { // publish: per-chunk fill counts, then the tile
                 if (tot) {
                     const unsigned int c0 = base / 256u, c1 = (base + tot - 1u) / 256u;
-                    for (unsigned int cc = c0; cc <= c1; ++cc) {
-                        const unsigned int lo_e = cc * 256u > base ? cc * 256u : base;
-                        const unsigned int hi_e = (cc + 1u) * 256u < base + tot ? (cc + 1u) * 256u : base + tot;
-                        atomicAdd(&B.fill[cc], hi_e - lo_e);
+                    if (c0 == c1) atomicAdd(&B.fill[c0], tot);
+                    else {
+                        const unsigned int first = (c0 + 1u) * 256u - base;
+                        atomicAdd(&B.fill[c0], first);
+                        atomicAdd(&B.fill[c1], tot - first);
                     }
                 }
                 __threadfence();
                 atomicAdd(&c->tiles_done, 1u);
             }
         } else if (act == QACT_SIM) {
-            if (threadIdx.x < len) {
+            if (threadIdx.x < len && (threadIdx.x & ~31u) < len) {
                 const long long li = (long long)__ldcg(&B.work[unit * 256u + threadIdx.x]);
                 const double *thp = B.thp;
                 long long ev = 0;
@@ -1847,13 +1782,6 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->P.sqrt_np = sqrt((double)d);
     s->P.mcmc_retrys = cfg->mcmc_retrys; s->P.max_iterations = cfg->max_iterations;
     s->P.rank = ctx->rank; s->P.world = ctx->world;
-    {
-        // measured (profiles/scaling_r2.md): on one GPU the plain queue with 256-particle tiles is fastest; with peers the
-        // partner rows are prefetched one chunk ahead and a tile holds two particles per thread
-        const char *e = getenv("KABC_PREFETCH"), *t = getenv("KABC_TILE");
-        s->P.prefetch = e ? (e[0] == '1') : (ctx->world > 1);
-        s->P.nsub = t ? (atoi(t) == 512 ? 2 : 1) : (s->P.prefetch ? 2 : 1);
-    }
     s->X = make_xpeer(ctx);
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
     const size_t nd = (size_t)Pn * d;
