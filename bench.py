@@ -245,14 +245,16 @@ def roofline_of(name, prec, d, units, evals, ms_total, kernel_us, units_per_laun
     t = instr_table(name, prec)
     w = t["thread_inst_per_unit"] if t else W_SURVEY[name]
     out = {"bound": "issue",
-           "kernel": "k_ais_simulate*" if is_ais else ("k_smc_simulate_lv / _gk" if name in ("lv_smc", "gk_ais") else "k_smc_sweep<model,precision> (fused propose + simulate + accept)"),
+           "kernel": "k_ais_simulate*" if is_ais else ("k_smc_simulate_lv" if name == "lv_smc" else "k_smc_sweep_q<model,precision> (queued propose tiles + simulate chunks + accept)"),
            "unit": "T thread-instr/s (SM issue slots: SMs x 4 x 32 x f_clk at the sampled clock, one GPU)",
            "peak": r_issue / 1e12, "w_instr_per_unit": w,
            "w_source": (t["source"] if t else "SURVEY.md 8(d) pre-implementation estimate (no ncu capture of this workload yet)"),
            "unit_of_work": "SSA event" if name == "lv_smc" else "cost eval"}
     if kernel_us and units_per_launch:
         ach = units_per_launch * w / (kernel_us * 1e-6)
-        out.update({"achieved": ach / 1e12, "frac": ach / r_issue, "kernel_us": kernel_us, "units_per_launch": units_per_launch})
+        out.update({"achieved": ach / 1e12, "frac": ach / r_issue, "kernel_us": kernel_us, "units_per_launch": units_per_launch,
+                    "frac_note": "executed THREAD-instructions (predicated-off lanes excluded) over issue slots x 32 lanes; ncu's "
+                                 "issue_active (warp-instructions over issue slots) of the same kernel is reported beside it"})
     else:
         out.update({"achieved": None, "frac": None, "kernel_us": None})
     ach_step = units * w / (ms_total * 1e-3) / world
@@ -328,6 +330,9 @@ def time_workload(k, ctx, name, prec, n_per_gpu, world, steps, warmup, dist_mod,
     ms_total = max(per_rank)
     # warm per-kernel times of a few more iterations: the dominant kernel's own event-timed duration
     kernel_us, units_per_launch, ktimes = None, None, None
+    if is_ais:  # no per-kernel hook for AIS: a sweep is two half-steps, each one propose + one simulate launch
+        kernel_us = ms_total / max(steps, 1) * 1e3 / 2
+        units_per_launch = evals / max(steps, 1) / 2 / world
     if not is_ais:
         acc, n_prof = {}, 4
         e1 = evals_now()

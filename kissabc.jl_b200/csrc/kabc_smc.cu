@@ -142,6 +142,11 @@ __device__ __forceinline__ int sel_shift(unsigned long long klo, unsigned long l
     const int bl = range ? 64 - __clzll((long long)range) : 0;
     return bl > SEL_LOG2_BINS ? bl - SEL_LOG2_BINS : 0;
 }
+// bins a histogram over [klo,khi] with this shift can touch (the rest of the 4096 stay zero and are not exchanged)
+__device__ __forceinline__ int sel_used_bins(unsigned long long klo, unsigned long long khi, int shift) {
+    const unsigned long long nb = ((khi - klo) >> shift) + 1ull;
+    return nb < (unsigned long long)SEL_BINS ? (int)nb : SEL_BINS;
+}
 __device__ __forceinline__ void raise_peer_error(SmcCtrl *c) {
     if (threadIdx.x == 0 && !c->err) c->err = KABC_ERR_PEER;
     __syncthreads();
@@ -382,11 +387,13 @@ __device__ void sel_after_hist(SmcBufs &B, const SmcParams &P, const XPeer &x, i
     constexpr int PER = SEL_BINS / NT;
     SmcCtrl *c = B.ctrl;
     unsigned int loc[PER];
+    const int nb_used = sel_used_bins(c->h_klo, c->h_khi, c->h_shift);
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
         const int bin = threadIdx.x * PER + q;
         unsigned int s = 0;
-        for (int r = 0; r < P.world; ++r) s += xslot(B, P, P.rank, set, r)->hist[bin];
+        if (bin < nb_used)
+            for (int r = 0; r < P.world; ++r) s += xslot(B, P, P.rank, set, r)->hist[bin];
         loc[q] = s;
     }
     SelRange R;
@@ -538,9 +545,10 @@ __device__ void sel_publish_consume(SmcBufs &B, const SmcParams &P, const XPeer 
     SmcCtrl *c = B.ctrl;
     const int set = (int)((*x.seq + 1ull) & 1ull);
     if (st == SEL_HIST) {
+        const int nb_used = sel_used_bins(c->h_klo, c->h_khi, c->h_shift);
         for (int r = 0; r < P.world; ++r) {
             XSlot *s = xslot(B, P, r, set, P.rank);
-            for (int q = threadIdx.x; q < SEL_BINS; q += blockDim.x) s->hist[q] = __ldcg(&B.hist[q]);
+            for (int q = threadIdx.x; q < nb_used; q += blockDim.x) s->hist[q] = __ldcg(&B.hist[q]);
             if (threadIdx.x == 0) { s->v[XV_MINKEY] = c->sw_minkey; s->v[XV_MAXKEY] = c->sw_maxkey; }
         }
         __syncthreads();
@@ -876,9 +884,10 @@ __device__ void sweep_finish(SmcBufs &B, const SmcParams &P, const XPeer &x, int
                              unsigned long long *s_res) {
     SmcCtrl *c = B.ctrl;
     const int set = (int)((*x.seq + 1ull) & 1ull);
+    const int nb_used = sel_used_bins(c->h_klo, c->h_khi, c->h_shift);
     for (int r = 0; r < P.world; ++r) {
         XSlot *s = xslot(B, P, r, set, P.rank);
-        for (int q = threadIdx.x; q < SEL_BINS; q += NT) s->hist[q] = __ldcg(&B.hist[q]);
+        for (int q = threadIdx.x; q < nb_used; q += NT) s->hist[q] = __ldcg(&B.hist[q]);
         if (threadIdx.x == 0) {
             s->v[XV_ACC] = c->sw_accepted; s->v[XV_WORK] = c->sw_work; s->v[XV_EVENTS] = c->sw_events;
             s->v[XV_MINKEY] = c->sw_minkey; s->v[XV_MAXKEY] = c->sw_maxkey; s->v[XV_BELOW] = c->sw_below; s->v[XV_ABOVE] = c->sw_above;

@@ -56,7 +56,8 @@ def main():
             "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "binding_pipe": {"name": top[1], "pct": top[0]}, "pipes_pct": pipes,
             "registers": g("launch__registers_per_thread"), "warps_active_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active"),
-            "duration_us_under_ncu": g("gpu__time_duration.sum"),
+            "duration_us_under_ncu": (g("gpu__time_duration.sum") or 0.0) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(
+                unit_row[hdr.index("gpu__time_duration.sum")], 1.0),
             "dram_bytes_per_launch": dr * scale.get(dru, 1.0) + dw * scale.get(dwu, 1.0),
             "source": f"ncu --set full, launch {int(skipped) + 1} of {kre} (smsp__thread_inst_executed.sum / units of that launch), commit {commit}",
             "commit": commit}
