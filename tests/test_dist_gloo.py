@@ -1,9 +1,11 @@
 """N>1 host logic on CPU: world_size-2 `gloo` processes.
 
 (1) the NCCL-id broadcast plumbing and the shard partition of kissabc.jl_b200/dist.py;
-(2) the multi-rank smc SCHEDULE itself (replicated state, sharded sweep, all-gather of the shard rows + summed
-    counters, redundant quantile/cut/resample) emulated with the CPU oracle: the 2-rank run must reproduce the
-    single-process run bit for bit.  The device path uses exactly this schedule (kabc_smc.cu).
+(2) a multi-rank smc SCHEDULE (sharded sweep: every rank proposes / simulates / accepts its own particles against the
+    pre-sweep ensemble; rows and summed counters exchanged after the sweep; quantile / cut / resample decided from replicated
+    scalars) emulated with the CPU oracle: the 2-rank run must reproduce the single-process run bit for bit -- the property
+    the device path relies on (kabc_smc.cu shards the state as well and reads rows from their owners; its own multi-rank
+    runs are checked on the GPU, tests/test_gpu_multi.py, with ranks sharing one GPU when only one is visible).
 """
 import os
 import socket
