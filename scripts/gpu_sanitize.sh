@@ -30,7 +30,9 @@ for n in (300, 5000):
     print("abcde/pfilter", n, a.nsim, f.eps, f.nreps)
 print("done")
 PY
-compute-sanitizer --tool memcheck --error-exitcode 3 python gpurun_out/san.py 2>&1 | tail -8
-echo "memcheck rc=$?"
-compute-sanitizer --tool racecheck --error-exitcode 3 python gpurun_out/san.py 2>&1 | tail -8
-echo "racecheck rc=$?"
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 3 python gpurun_out/san.py > gpurun_out/san_memcheck.log 2>&1
+echo "memcheck rc=$?" | tee -a gpurun_out/san_memcheck.log
+tail -12 gpurun_out/san_memcheck.log
+timeout 420 compute-sanitizer --tool racecheck --error-exitcode 3 python gpurun_out/san.py > gpurun_out/san_racecheck.log 2>&1
+echo "racecheck rc=$?" | tee -a gpurun_out/san_racecheck.log
+tail -12 gpurun_out/san_racecheck.log
