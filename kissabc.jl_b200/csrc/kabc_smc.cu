@@ -78,6 +78,7 @@ struct SmcParams { // launch constants
     long long mcmc_retrys;
     int max_iterations;
     int rank, world;
+    unsigned int prop_cap; // queued sweep: most tiles in flight (claimed, not yet published) at any time; 0 = no limit
 };
 
 struct SmcTrace {
@@ -190,7 +191,8 @@ struct SweepShared {
 };
 __device__ __forceinline__ void note_final_shared(SweepShared &sh, unsigned int *hist, double X) {
     const unsigned long long key = dkey(X);
-    atomicMin(&sh.kmin, key);
+    // a 64-bit shared-memory min is a CAS loop (ATOMS.CAST.SPIN): only the rare keys under the running minimum try
+    if (key < *reinterpret_cast<volatile unsigned long long *>(&sh.kmin)) atomicMin(&sh.kmin, key);
     if (key < sh.hklo) atomicAdd(&sh.below, 1u);
     else if (key > sh.hkhi) atomicAdd(&sh.above, 1u);
     else atomicAdd(&hist[(key - sh.hklo) >> sh.hshift], 1u);
@@ -1227,7 +1229,7 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
             // Claims are plain atomicAdds (no retry loop: 888 CTAs claim thousands of units per sweep).  A CTA claims the next
             // chunk first; while that chunk is incomplete it produces: it proposes tiles, whose survivors fill the chunks in
             // order, its own included.  Claims past the end of the list are recognised once every tile is published.
-            unsigned int act = QACT_RETRY, unit = 0, len = 0;
+            unsigned int act = QACT_RETRY, unit = 0, len = 0, claimed = 0;
             if (my_chunk == 0xFFFFFFFFu) my_chunk = atomicAdd(&c->lv_head, 1u);
             const unsigned int h = my_chunk;
             const unsigned int done = ld_acquire_gpu_u32(&c->tiles_done);
@@ -1240,9 +1242,14 @@ k_smc_sweep_q(SmcBufs B, SmcParams P, XPeer x, DPriors pri, DModel m, RoundKeys 
                 my_chunk = 0xFFFFFFFFu;
             } else if (all_done && total <= h * 256u) {
                 act = QACT_EXIT;
-            } else if (ld_acquire_gpu_u32(&c->tile_head) < ntiles) {
+            } else if ((claimed = ld_acquire_gpu_u32(&c->tile_head)) < ntiles && !(P.prop_cap && claimed - done >= P.prop_cap)) {
                 const unsigned int t = atomicAdd(&c->tile_head, 1u);
                 if (t < ntiles) { act = QACT_PROP; unit = t; }
+            } else if (claimed < ntiles) {
+                // multi-GPU: a proposal is three peer loads per particle; when every CTA proposes at once (the start of a
+                // sweep) the link queues them all and no chunk completes until all do.  Bounding the tiles in flight lets the
+                // first chunks complete -- and their simulation start -- while the rest of the proposals stream behind them.
+                __nanosleep(200);
             } else { // every tile is claimed, some are still in flight on other CTAs: bounded wait
                 const unsigned long long now = global_timer_ns();
                 if (t_wait0 == 0) t_wait0 = now;
@@ -1791,6 +1798,10 @@ int kabc_smc_create(kabc_ctx_t *ctx, const kabc_prior_t *prior, int d, const kab
     s->P.sqrt_np = sqrt((double)d);
     s->P.mcmc_retrys = cfg->mcmc_retrys; s->P.max_iterations = cfg->max_iterations;
     s->P.rank = ctx->rank; s->P.world = ctx->world;
+    {   // tiles in flight in the queued sweep (k_smc_sweep_q): KABC_PROP_CAP bounds them, 0 = unbounded (the default)
+        const char *e = getenv("KABC_PROP_CAP");
+        s->P.prop_cap = e ? (unsigned int)strtoul(e, nullptr, 10) : 0u;
+    }
     s->X = make_xpeer(ctx);
     s->nblocks_scan = (int)((Pn + SCAN_THREADS - 1) / SCAN_THREADS);
     const size_t nd = (size_t)Pn * d;
