@@ -238,7 +238,7 @@ __global__ void k_pf_accept(PmcBufs B, long long N, int d, unsigned int *pend2) 
     if (w >= n) return;
     const long long i = B.list[w];
     const double Cp = B.Cp[i];
-    if (Cp > B.ctrl->eps || Cp != Cp) { // ref :320-322
+    if (Cp > B.ctrl->eps) { // ref :320-322 (a NaN cost compares false and is accepted, as in the reference)
         pend2[atomicAdd(&B.ctrl->n_pend2, 1u)] = (unsigned int)i;
         return;
     }

@@ -1526,7 +1526,7 @@ int kor_pfilter_run(uint64_t seed, const kor_prior_t *prior, int d, const kor_mo
                 if (kor_log(next_uniform(&st)) > fmin(0.0, ll - lp[i])) continue;
                 const double Cp = cost_dispatch(model, seed, ST_COST, d, p, (uint32_t)i, round);
                 gev += 1;
-                if (Cp > eps || Cp != Cp) continue;
+                if (Cp > eps) continue; /* ref :320: a NaN cost compares false and is accepted */
                 C[i] = Cp;
                 for (int k = 0; k < d; ++k) th[(int64_t)k * N + i] = p[k];
                 lp[i] = ll;
