@@ -192,6 +192,9 @@ rand(r::PhiloxRNG, sp::SpecRange{T}) where {T} = sp.first + T((UInt64(next_u32!(
 # rand(rng, 1:n) / rand(rng, eachindex(v))  (src/smc.jl:163-164, src/transition.jl:6-54)  and  rand(rng, (1,1,1,1,2,2,3))  (:62)
 rand(r::PhiloxRNG, rg::AbstractUnitRange{T}) where {T<:Integer} = first(rg) + T((UInt64(next_u32!(r)) * UInt64(length(rg))) >> 32)
 rand(r::PhiloxRNG, t::Tuple) = t[rand(r, 1:length(t))]
+# a tuple of Ints is also a `Dims`: Random has `rand(::AbstractRNG, ::Dims)` ("needed to disambiguate"), which would make the
+# call above ambiguous for exactly the tuple the reference draws from -- settle it with the most specific method
+rand(r::PhiloxRNG, t::Dims) = t[rand(r, 1:length(t))]
 
 function randn(r::PhiloxRNG)
     w0 = next_u32!(r); w1 = next_u32!(r)
