@@ -20,6 +20,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_*.json")))
+PYREF = sorted(glob.glob(os.path.join(HERE, "golden", "pyref_*.json")))
 RTOL = 1e-12
 
 
@@ -127,6 +128,20 @@ def _check_ais_fixture(O, fx):
     close(out, ref, "emitted samples")
     th, lp, ll = a2.state()
     close(th.ravel(), f64(fx["theta"]), "final ensemble"); close(lp, f64(fx["lp"]), "final log-prior"); close(ll, f64(fx["ll"]), "final ll")
+
+
+# ---- the same comparisons against a SECOND restatement of the reference (tests/golden/make_pyref_fixtures.py): the Julia of
+# src/smc.jl, src/transition.jl, src/types.jl:51-75, src/KissABC.jl:35-80 transliterated line by line into Python, with the
+# platform's log / exp, pairwise mean / std and hypot like the reference.  Not the reference itself (parity stays unpinned), but
+# every accept / cut / resample decision of five whole runs (1.3e7 Philox words) is taken identically by two independent codes.
+@pytest.mark.parametrize("path", PYREF, ids=[os.path.basename(p)[:-5] for p in PYREF])
+def test_python_transliteration_of_the_reference_matches_oracle_serial_mode(oracle, path):
+    fx = json.load(open(path))
+    (_check_smc_fixture if fx["kind"] == "smc" else _check_ais_fixture)(oracle, fx)
+
+
+def test_python_transliteration_fixtures_are_committed():
+    assert len(PYREF) == 5
 
 
 def _b(x):
