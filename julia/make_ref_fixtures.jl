@@ -95,25 +95,28 @@ function smc_fixture(name, prior_spec, prior, mkcost, model_spec; kw...)
     println("ref_smc_$(name): ", length(its), " iterations, eps = ", res.ϵ, ", alive = ", length(P[1].particles))
 end
 
-function ais_fixture(name, prior_spec, prior, mkcost, model_spec, scale, N, steps, ntransitions)
+function ais_fixture(name, prior_spec, prior, mkcost, model_spec, scale, N, steps, ntransitions; posterior=0)
     rng = PhiloxRNG(SEED)
-    model = ApproxKernelizedPosterior(prior, mkcost(rng), scale)
+    # posterior = 1: the hard-threshold ApproxPosterior (src/types.jl:76-104), `scale` is its maxcost and the second slot of a
+    # log-density is the cost
+    model = posterior == 1 ? ApproxPosterior(prior, mkcost(rng), scale) : ApproxKernelizedPosterior(prior, mkcost(rng), scale)
     spl = AIS(N)
     sample0, state = AbstractMCMC.step(rng, model, spl)                       # src/KissABC.jl:35-64
     flat(ps) = [Float64(p.x[k]) for k in 1:length(prior), p in ps]           # d x N
     th_init = flat(state.sample)
-    lp_init = [ld.logprior for ld in state.loglikelihood]; ll_init = [ld.loglikelihood for ld in state.loglikelihood]
+    lp_init = [ld[1] for ld in state.loglikelihood]; ll_init = [ld[2] for ld in state.loglikelihood]   # (logprior, loglikelihood | cost)
     samples = [collect(Float64, sample0.x)]
     for s in 1:steps
         smp, state = AbstractMCMC.step(rng, model, spl, state; ntransitions=ntransitions)   # src/KissABC.jl:66-80
         push!(samples, collect(Float64, smp.x))
     end
     th = flat(state.sample)
-    lp = [ld.logprior for ld in state.loglikelihood]; ll = [ld.loglikelihood for ld in state.loglikelihood]
+    lp = [ld[1] for ld in state.loglikelihood]; ll = [ld[2] for ld in state.loglikelihood]
     open(joinpath(OUT, "ref_ais_$(name).json"), "w") do io
         write(io, jobj([
             "kind" => jstr("ais"), "name" => jstr(name), "seed" => string(SEED), "prior" => prior_spec, "model" => model_spec,
             "scale" => bits(scale), "nwalkers" => string(N), "steps" => string(steps), "ntransitions" => string(ntransitions),
+            "posterior" => string(posterior),
             "theta_init" => jbits(vec(permutedims(th_init))), "lp_init" => jbits(lp_init), "ll_init" => jbits(ll_init),
             "samples" => jarr([jbits(s) for s in samples]),
             "theta" => jbits(vec(permutedims(th))), "lp" => jbits(lp), "ll" => jbits(ll),
@@ -139,3 +142,5 @@ ais_fixture("normal", UU_NORMAL, Factored(Uniform(1, 3), Uniform(0.01, 0.2)), r 
             "{\"kind\":\"normal\",\"n\":100}", 0.05, 12, 60, 3)
 ais_fixture("ma2", UU_MA2, Factored(Uniform(-2, 2), Uniform(-1, 1)), r -> cost_ma2(r, 100, MA2_T),
             "{\"kind\":\"ma2\",\"n\":100}", 0.2, 10, 40, 2)
+ais_fixture("hard_normal", UU_NORMAL, Factored(Uniform(1, 3), Uniform(0.01, 0.2)), r -> cost_normal(r, 100),
+            "{\"kind\":\"normal\",\"n\":100}", 0.3, 12, 60, 3; posterior=1)

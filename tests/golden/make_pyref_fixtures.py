@@ -239,6 +239,33 @@ class KernelizedPosterior:
         return -rng.randexp() <= lW
 
 
+class HardPosterior:                                                           # ApproxPosterior, src/types.jl:76-104
+    def __init__(self, prior, cost, maxcost):
+        self.prior, self.cost, self.maxcost = prior, cost, maxcost
+
+    def loglike(self, x):
+        lp = self.prior.logpdf(x)
+        cs = -lp
+        if math.isfinite(lp):
+            cs = self.cost(x)
+        return (lp, cs)
+
+    @staticmethod
+    def valid(ld):
+        return math.isfinite(ld[1]) and math.isfinite(ld[0])
+
+    def accept(self, rng, old_ld, new_ld, corr):
+        if not math.isfinite(corr):
+            raise RuntimeError("ld_correction is invalid")
+        if not self.valid(old_ld):
+            raise RuntimeError("starting sample invalid.")
+        if not self.valid(new_ld):
+            return False
+        lW = corr + new_ld[0] - old_ld[0]
+        lW2 = max(self.maxcost, old_ld[1]) - new_ld[1]
+        return (-rng.randexp() <= lW) and lW2 >= 0
+
+
 def stretch_propose(rng, d, ps, i):                                            # src/transition.jl:50-59
     n = len(ps)
     a = i
@@ -337,12 +364,12 @@ def smc_fixture(name, prior_spec, prior, mkcost, model_spec, **kw):
     print(f"pyref_smc_{name}: {len(res['shown'])} iterations, eps = {res['eps']}, alive = {res['P'].shape[1]}, words = {rng.consumed}")
 
 
-def ais_fixture(name, prior_spec, prior, mkcost, model_spec, scale, N, steps, ntransitions):
+def ais_fixture(name, prior_spec, prior, mkcost, model_spec, scale, N, steps, ntransitions, posterior=0):
     rng = PhiloxRNG(SEED)
-    model = KernelizedPosterior(prior, mkcost(rng), scale)
+    model = (HardPosterior if posterior else KernelizedPosterior)(prior, mkcost(rng), scale)
     (th0, lp0, ll0), samples, (th, lp, ll) = ais_run(model, rng, N, steps, ntransitions)
     fx = {"kind": "ais", "name": name, "seed": str(SEED), "prior": prior_spec, "model": model_spec, "scale": bits(scale),
-          "nwalkers": str(N), "steps": str(steps), "ntransitions": str(ntransitions),
+          "nwalkers": str(N), "steps": str(steps), "ntransitions": str(ntransitions), "posterior": str(posterior),
           "theta_init": jbits(th0), "lp_init": jbits(lp0), "ll_init": jbits(ll0), "samples": [jbits(s) for s in samples],
           "theta": jbits(th), "lp": jbits(lp), "ll": jbits(ll), "words_consumed": str(rng.consumed),
           "generator": "tests/golden/make_pyref_fixtures.py (Python transliteration of the reference; NOT Julia)"}
@@ -356,7 +383,7 @@ MA2_T = (0.72, 0.2)
 
 if __name__ == "__main__":
     O.build()
-    # the same five cases as julia/make_ref_fixtures.jl
+    # the same six cases as julia/make_ref_fixtures.jl
     smc_fixture("normal_defaults", UU_NORMAL, FactoredUniform((1, 3), (0.01, 0.2)), lambda r: cost_normal(r, 200),
                 {"kind": "normal", "n": 200}, nparticles=400, epstol=0.05)
     smc_fixture("normal_sparse_resampling", UU_NORMAL, FactoredUniform((1, 3), (0.01, 0.2)), lambda r: cost_normal(r, 100),
@@ -367,3 +394,5 @@ if __name__ == "__main__":
                 {"kind": "normal", "n": 100}, 0.05, 12, 60, 3)
     ais_fixture("ma2", UU_MA2, FactoredUniform((-2, 2), (-1, 1)), lambda r: cost_ma2(r, 100, MA2_T),
                 {"kind": "ma2", "n": 100}, 0.2, 10, 40, 2)
+    ais_fixture("hard_normal", UU_NORMAL, FactoredUniform((1, 3), (0.01, 0.2)), lambda r: cost_normal(r, 100),
+                {"kind": "normal", "n": 100}, 0.3, 12, 60, 3, posterior=1)       # ApproxPosterior(prior, cost, maxcost = 0.3)

@@ -115,13 +115,14 @@ def _check_ais_fixture(O, fx):
     pri, mod = _objects(O, fx)
     N, steps, nt = int(fx["nwalkers"]), int(fx["steps"]), int(fx["ntransitions"])
     scale = float(f64([fx["scale"]])[0])
-    a = O.Ais(int(fx["seed"]), pri, mod, O.ais_config(N, steps + 1, ntransitions=nt, scale=scale))
+    post = int(fx.get("posterior", 0))  # 1: ApproxPosterior (src/types.jl:76-104), `scale` = maxcost, the second slot holds the cost
+    a = O.Ais(int(fx["seed"]), pri, mod, O.ais_config(N, steps + 1, ntransitions=nt, scale=scale, posterior=post))
     a.set_serial()
     a.init()
     th, lp, ll = a.state()
     close(th.ravel(), f64(fx["theta_init"]), "ensemble after the init step (ref src/KissABC.jl:50-61)")
     close(lp, f64(fx["lp_init"]), "log-prior after init"); close(ll, f64(fx["ll_init"]), "log-likelihood after init")
-    a2 = O.Ais(int(fx["seed"]), pri, mod, O.ais_config(N, steps + 1, ntransitions=nt, scale=scale))
+    a2 = O.Ais(int(fx["seed"]), pri, mod, O.ais_config(N, steps + 1, ntransitions=nt, scale=scale, posterior=post))
     a2.set_serial()
     out = a2.run_sequential()                                                     # the reference's own schedule, src/KissABC.jl:66-80
     ref = np.array([f64(s_) for s_ in fx["samples"]]).T                           # d x (steps+1)
@@ -141,7 +142,7 @@ def test_python_transliteration_of_the_reference_matches_oracle_serial_mode(orac
 
 
 def test_python_transliteration_fixtures_are_committed():
-    assert len(PYREF) == 5
+    assert len(PYREF) == 6
 
 
 def _b(x):
