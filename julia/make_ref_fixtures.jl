@@ -55,6 +55,13 @@ function cost_ma2(rng, n, target)                  # SURVEY.md Appendix B
     end
 end
 
+function cost_noisyprod(rng)                       # test/runtests.jl:105-112 with the run's rng instead of the global one
+    function (θ)
+        n, du = θ
+        abs((n * n + du) * (n + randn(rng) * 0.01) - 5.5)
+    end
+end
+
 # `verbose && @show iteration, ϵ, ESS` (src/smc.jl:143) is the only per-iteration output of the reference: capture it
 function capture_stdout(f)
     path, io = mktemp()
@@ -127,7 +134,8 @@ function ais_fixture(name, prior_spec, prior, mkcost, model_spec, scale, N, step
 end
 
 # prior specs in the oracle's notation (tests/common.py): only laws whose Distributions.jl sampler is a fixed transform of
-# rand / randn (Uniform: a + (b-a) rand; Normal: mu + sigma randn) can be replayed; Truncated uses its own rejection scheme
+# rand / randn / rand(a:b) (Uniform: a + (b-a) rand; Normal: mu + sigma randn; DiscreteUniform: rand(rng, a:b)) can be
+# replayed; Truncated uses its own rejection scheme
 const UU_NORMAL = "[[\"uniform\",1,3],[\"uniform\",0.01,0.2]]"
 const UU_MA2 = "[[\"uniform\",-2,2],[\"uniform\",-1,1]]"
 const MA2_T = (0.72, 0.2)
@@ -142,5 +150,8 @@ ais_fixture("normal", UU_NORMAL, Factored(Uniform(1, 3), Uniform(0.01, 0.2)), r 
             "{\"kind\":\"normal\",\"n\":100}", 0.05, 12, 60, 3)
 ais_fixture("ma2", UU_MA2, Factored(Uniform(-2, 2), Uniform(-1, 1)), r -> cost_ma2(r, 100, MA2_T),
             "{\"kind\":\"ma2\",\"n\":100}", 0.2, 10, 40, 2)
+# discrete component: DiscreteUniform is sampled as rand(rng, a:b) and push_p rounds it (src/types.jl:32)
+smc_fixture("noisyprod_discrete", "[[\"normal\",1,0.5],[\"duniform\",1,10]]", Factored(Normal(1, 0.5), DiscreteUniform(1, 10)),
+            cost_noisyprod, "{\"kind\":\"noisyprod\"}"; nparticles=200, epstol=0.02)
 ais_fixture("hard_normal", UU_NORMAL, Factored(Uniform(1, 3), Uniform(0.01, 0.2)), r -> cost_normal(r, 100),
             "{\"kind\":\"normal\",\"n\":100}", 0.3, 12, 60, 3; posterior=1)

@@ -126,6 +126,53 @@ class FactoredUniform:
         return s
 
 
+LOG2PI = 1.8378770664093453
+
+
+class Factored:
+    """Factored(Normal | Uniform | DiscreteUniform ...): rand / logpdf / push_p as Distributions.jl + src/priors.jl + src/types.jl:28-32"""
+    def __init__(self, *comps):
+        self.c = comps                                # ("normal", mu, sigma) | ("uniform", a, b) | ("duniform", a, b)
+
+    def __len__(self):
+        return len(self.c)
+
+    def rand(self, rng):
+        out = []
+        for kind, p0, p1 in self.c:
+            if kind == "normal":
+                out.append(p0 + p1 * rng.randn())             # d.mu + d.sigma * randn(rng)
+            elif kind == "uniform":
+                out.append(p0 + (p1 - p0) * rng.rand())
+            else:
+                out.append(float(rng.rand_range(p0, p1 - p0 + 1)))   # rand(rng, d.a:d.b)
+        return np.array(out)
+
+    def push(self, x):                                # push_p: float(p) | round(Int, p) (ties to even, like Python's round)
+        return np.array([float(round(v)) if c[0] == "duniform" else float(v) for c, v in zip(self.c, x)])
+
+    def logpdf(self, x):
+        s = None
+        for (kind, p0, p1), v in zip(self.c, x):
+            if kind == "normal":
+                z = (v - p0) / p1
+                lp = -(z * z + LOG2PI) / 2 - math.log(p1)     # StatsFuns.normlogpdf
+            elif kind == "uniform":
+                lp = -math.log(p1 - p0) if p0 <= v <= p1 else -math.inf
+            else:
+                pv = 1 / (p1 - p0 + 1)
+                lp = math.log(pv) if (p0 <= v <= p1 and v == math.floor(v)) else -math.inf
+            s = lp if s is None else s + lp
+        return s
+
+
+def cost_noisyprod(rng):                              # test/runtests.jl:105-112 with the run's rng instead of the global one
+    def cost(theta):
+        n, du = theta
+        return abs((n * n + du) * (n + rng.randn() * 0.01) - 5.5)
+    return cost
+
+
 def quantile(v, p):
     """Statistics.quantile(v, p) (type 7: alpha = beta = 1), operation by operation -- numpy's `quantile` interpolates with a
     different rounding (b - (b-a)(1-t) for t >= 0.5), which is within 1e-12 but is not what the reference computes"""
@@ -146,9 +193,10 @@ def smc(prior, cost, rng, nparticles=100, alpha=0.95, mcmc_retrys=0, mcmc_tol=0.
     min_r_ess = alpha ** 2 if min_r_ess is None else min_r_ess
     Np = len(prior)
     N = nparticles
+    push = getattr(prior, "push", lambda x: x)                                 # push_p(prior, .): identity for continuous laws
     th = [prior.rand(rng) for _ in range(N)]                                   # :119
-    Xs = np.array([cost(th[i]) for i in range(N)])                             # :120-123 (push_p = identity: continuous laws)
-    lpis = np.array([prior.logpdf(th[i]) for i in range(N)])                   # :125
+    Xs = np.array([cost(push(th[i])) for i in range(N)])                       # :120-123
+    lpis = np.array([prior.logpdf(push(th[i])) for i in range(N)])             # :125
     eps = math.inf
     alive = np.ones(N, dtype=bool)
     shown = []
@@ -188,13 +236,13 @@ def smc(prior, cost, rng, nparticles=100, alpha=0.95, mcmc_retrys=0, mcmc_tol=0.
                 if not alive[i]:
                     continue
                 lprob, thp, logcorr = new_p[i]
-                lpip = prior.logpdf(thp)
+                lpip = prior.logpdf(push(thp))
                 if lpip < 0 and not math.isfinite(lpip):
                     continue
                 d_ = lpip - lpis[i] + logcorr
                 lM = d_ if d_ != d_ else min(d_, 0.0)                          # Julia's min propagates NaN
                 if lprob < lM:
-                    Xp = cost(thp)
+                    Xp = cost(push(thp))
                     if flag:
                         if Xp > eps:
                             continue
@@ -208,7 +256,7 @@ def smc(prior, cost, rng, nparticles=100, alpha=0.95, mcmc_retrys=0, mcmc_tol=0.
                 break
         if 2 * abs(epsv - eps) < r_epstol * (abs(epsv) + abs(eps)) or eps <= epstol or accepted < mcmc_tol * N:
             break
-    P = np.array([th[i] for i in range(N) if alive[i]]).T                      # :200-204
+    P = np.array([push(th[i]) for i in range(N) if alive[i]]).T                # :200-204
     return dict(P=P, C=Xs, eps=eps, shown=shown)
 
 
@@ -383,7 +431,7 @@ MA2_T = (0.72, 0.2)
 
 if __name__ == "__main__":
     O.build()
-    # the same six cases as julia/make_ref_fixtures.jl
+    # the same seven cases as julia/make_ref_fixtures.jl
     smc_fixture("normal_defaults", UU_NORMAL, FactoredUniform((1, 3), (0.01, 0.2)), lambda r: cost_normal(r, 200),
                 {"kind": "normal", "n": 200}, nparticles=400, epstol=0.05)
     smc_fixture("normal_sparse_resampling", UU_NORMAL, FactoredUniform((1, 3), (0.01, 0.2)), lambda r: cost_normal(r, 100),
@@ -394,5 +442,7 @@ if __name__ == "__main__":
                 {"kind": "normal", "n": 100}, 0.05, 12, 60, 3)
     ais_fixture("ma2", UU_MA2, FactoredUniform((-2, 2), (-1, 1)), lambda r: cost_ma2(r, 100, MA2_T),
                 {"kind": "ma2", "n": 100}, 0.2, 10, 40, 2)
+    smc_fixture("noisyprod_discrete", [["normal", 1, 0.5], ["duniform", 1, 10]], Factored(("normal", 1, 0.5), ("duniform", 1, 10)),
+                cost_noisyprod, {"kind": "noisyprod"}, nparticles=200, epstol=0.02)
     ais_fixture("hard_normal", UU_NORMAL, FactoredUniform((1, 3), (0.01, 0.2)), lambda r: cost_normal(r, 100),
                 {"kind": "normal", "n": 100}, 0.3, 12, 60, 3, posterior=1)       # ApproxPosterior(prior, cost, maxcost = 0.3)
