@@ -20,6 +20,9 @@
  * test/runtests.jl:8-22, the type-7 quantile against numpy, the README
  * posterior (README.md:64-66,84) and the statistical fixtures of
  * test/runtests.jl:77-86,133-175 (see tests/test_oracle_*.py).
+ * Cross-check (not a reference run): the SERIAL mode below takes the same decisions as a line-by-line Python transliteration
+ * of the reference's Julia on seven whole runs (tests/golden/make_pyref_fixtures.py, tests/test_ref_fixtures.py); the same
+ * test consumes tests/golden/ref_*.json once julia/make_ref_fixtures.jl has been run on a box with Julia.
  */
 #ifndef KABC_ORACLE_H
 #define KABC_ORACLE_H
