@@ -1,13 +1,13 @@
 // kabc_smc.cu -- smc(prior, cost; ...) on device.  Restates src/smc.jl:92-206 of KissABC.jl 3.0.1:
 //   init                      :119-129   k_smc_init / k_smc_init_prior + k_smc_init_gk, k_smc_post_init
-//   eps = quantile(Xs[alive]) :134       k_sel x3 (exact two-rank bucket select on FP64 keys + Statistics.jl type-7
+//   eps = quantile(Xs[alive]) :134       k_sel x2 (exact two-rank bucket select on FP64 keys + Statistics.jl type-7
 //                                        interpolation); the first histogram of an iteration is accumulated by the
 //                                        WRITERS of X during the previous sweep, so the usual iteration needs one pass
 //   alive cut, flag, ESS      :135-142   k_cut
 //   cyclic-tiling resample    :145-153   k_cut (decision + scan), k_compact (table of the surviving rows)
-//   propose                   :160-167   k_smc_propose  (phase A: own row through the resampling map, partners, proposal;
-//   prior-MH pre-test         :172-175    + prior tests; builds the work list)
-//   simulate + accept         :176-189   k_smc_simulate_list / _lv / _gk  (phase B over the work list: every warp full)
+//   propose                   :160-167   tiles of k_smc_sweep_q, or k_smc_propose (phase A: own row through the resampling
+//   prior-MH pre-test         :172-175    map, partners, proposal, prior tests; survivors go onto the work list)
+//   simulate + accept         :176-189   chunks of k_smc_sweep_q, or k_smc_simulate_list / _lv / _gk (phase B: every warp full)
 //   retry / stop rules        :156-159,192-198   post_sweep()/post_iter() run by the LAST block of the sweep kernel
 // Every scalar that steers control flow lives in SmcCtrl in device memory; the host only reads `stop`.
 //
@@ -15,9 +15,9 @@
 // their state: th[k*P + li] (SoA FP64), X[li], lpi[li], alive[li].  Before every sweep the owner writes the rows a sweep
 // may READ into its TABLE -- the surviving rows compacted in index order when the iteration resamples (the j-th alive
 // particle of the population is entry j - off[r] of rank r's table, off = exclusive scan of the per-rank alive counts),
-// all rows otherwise -- in the rank's peer arena (kabc_peer.cuh), one AoS row [theta | X | lpi] per particle so that a
-// partner costs one 16/32-byte read and the own row one 32/48-byte read.  The sweep reads rows only through the table of their owner (NVLink peer loads for the
-// other ranks): its own row idx[i] = idxalive[i mod n_alive] (the reference's cyclic tiling, :146-147) and the two
+// all rows otherwise -- in the rank's peer arena (kabc_peer.cuh), one AoS row [theta | X | lpi] per particle (a partner
+// costs one 16/32-byte read, the own row one 32/48-byte read).  A sweep reads rows only through their owner's table (peer
+// loads for the other ranks): its own row idx[i] = idxalive[i mod n_alive] (the reference's cyclic tiling, :146-147) and the two
 // partners a, b (:163-164); it writes only the state of its own shard.  So a rank receives O(P) rows per sweep whatever
 // G is, the quantile / cut / scan work on the shard only, and the ranks meet in four flag barriers per iteration
 // (histogram + sweep counters, candidate keys, alive counts, table complete) -- no NCCL on the data path, no host.
